@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Generate golden vectors from the UNMODIFIED reference (run in the build container).
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Imports ``src.models.convlstm.ConvLSTMCell`` (and ``Generator``) from
+``/root/reference`` (override with ``$PLC_REFERENCE``), runs them on CPU in fp32
+with fixed seeds, and writes small ``.npz`` fixtures next to this script.  The
+reference tree does not travel to the GPU box; these fixtures do.
+
+Fixtures
+  cell_*.npz     one ``ConvLSTMCell.forward`` (convlstm.py:16-28) + autograd grads
+  rollout_*.npz  the stacked 2-cell T-loop of generator.py:156-171 + autograd grads
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("PLC_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+from src.models.convlstm import ConvLSTMCell  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# (name, B, Cin, Ch, H, W, k, seed)
+CELL_CASES = [
+    ("cell_b2_c16_h16_12x15_k3", 2, 16, 16, 12, 15, 3, 101),
+    ("cell_b1_c8_h32_9x7_k5", 1, 8, 32, 9, 7, 5, 102),
+    ("cell_b2_c16_h32_16x16_k3", 2, 16, 32, 16, 16, 3, 103),
+    ("cell_b1_c24_h16_5x6_k3", 1, 24, 16, 5, 6, 3, 104),
+    ("cell_b1_c64_h64_16x8_k3", 1, 64, 64, 16, 8, 3, 105),
+    ("cell_b3_c1_h16_6x6_k1", 3, 1, 16, 6, 6, 1, 106),
+]
+
+# (name, B, T, hidden_dims(2), H, W, seed)  -- wiring of generator.py:57-58
+ROLLOUT_CASES = [
+    ("rollout_b2_t5_h16_32_8x10", 2, 5, (16, 32), 8, 10, 201),
+    ("rollout_b1_t4_h32_16_6x9", 1, 4, (32, 16), 6, 9, 202),
+]
+
+
+def np32(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+def gen_cell(name, b, cin, ch, hh, ww, k, seed):
+    torch.manual_seed(seed)
+    cell = ConvLSTMCell(cin, ch, kernel_size=k)
+    x = torch.randn(b, cin, hh, ww, requires_grad=True)
+    h = (0.5 * torch.randn(b, ch, hh, ww)).requires_grad_()
+    c = torch.randn(b, ch, hh, ww, requires_grad=True)
+    h2, c2 = cell(x, h, c)
+    gh = torch.randn_like(h2)
+    gc = torch.randn_like(c2)
+    (h2 * gh).sum().add((c2 * gc).sum()).backward()
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        x=np32(x), h=np32(h), c=np32(c),
+        weight=np32(cell.conv.weight), bias=np32(cell.conv.bias),
+        h_next=np32(h2), c_next=np32(c2), gh=np32(gh), gc=np32(gc),
+        dx=np32(x.grad), dh_prev=np32(h.grad), dc_prev=np32(c.grad),
+        dW=np32(cell.conv.weight.grad), db=np32(cell.conv.bias.grad),
+        k=np.int32(k))
+
+
+def gen_rollout(name, b, t_steps, hd, hh, ww, seed):
+    torch.manual_seed(seed)
+    cell1 = ConvLSTMCell(hd[0], hd[0])          # generator.py:57
+    cell2 = ConvLSTMCell(hd[0], hd[1])          # generator.py:58
+    x_seq = torch.randn(b, t_steps, hd[0], hh, ww, requires_grad=True)
+    h1 = torch.zeros(b, hd[0], hh, ww)          # generator.py:156-160
+    c1 = torch.zeros_like(h1)
+    h2 = torch.zeros(b, hd[1], hh, ww)
+    c2 = torch.zeros_like(h2)
+    tr = {k_: [] for k_ in ("h1", "c1", "h2", "c2")}
+    for t in range(t_steps):                    # generator.py:164-171
+        h1, c1 = cell1(x_seq[:, t], h1, c1)
+        h2, c2 = cell2(h1, h2, c2)
+        for k_, v in (("h1", h1), ("c1", c1), ("h2", h2), ("c2", c2)):
+            tr[k_].append(v)
+    out = torch.stack(tr["h2"], dim=1)
+    d_out = torch.randn_like(out)
+    (out * d_out).sum().backward()
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        x_seq=np32(x_seq), d_out=np32(d_out),
+        w1=np32(cell1.conv.weight), b1=np32(cell1.conv.bias),
+        w2=np32(cell2.conv.weight), b2=np32(cell2.conv.bias),
+        h1=np32(torch.stack(tr["h1"], 1)), c1=np32(torch.stack(tr["c1"], 1)),
+        h2=np32(torch.stack(tr["h2"], 1)), c2=np32(torch.stack(tr["c2"], 1)),
+        dx_seq=np32(x_seq.grad),
+        dW1=np32(cell1.conv.weight.grad), db1=np32(cell1.conv.bias.grad),
+        dW2=np32(cell2.conv.weight.grad), db2=np32(cell2.conv.bias.grad))
+
+
+def main():
+    torch.set_num_threads(1)
+    for case in CELL_CASES:
+        gen_cell(*case)
+    for case in ROLLOUT_CASES:
+        gen_rollout(*case)
+    print("wrote", len(CELL_CASES) + len(ROLLOUT_CASES), "fixtures to", HERE)
+
+
+if __name__ == "__main__":
+    main()

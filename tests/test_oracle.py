@@ -1,0 +1,159 @@
+"""Pin the oracle: restatement vs golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py), closed-form known answers, and --
+when /root/reference is present (build container only) -- the live reference."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files, load_golden
+from oracle import convlstm_oracle as O
+
+T = torch.from_numpy
+
+
+@pytest.mark.parametrize("path", golden_files("cell_"), ids=os.path.basename)
+def test_cell_forward_matches_reference_golden(path):
+    g = load_golden(path)
+    h2, c2 = O.cell_forward(T(g["x"]), T(g["h"]), T(g["c"]), T(g["weight"]), T(g["bias"]))
+    # same ATen ops, same dtype -> tight
+    np.testing.assert_allclose(h2.numpy(), g["h_next"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(c2.numpy(), g["c_next"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("path", golden_files("cell_"), ids=os.path.basename)
+def test_cell_backward_matches_reference_autograd_golden(path):
+    g = load_golden(path)
+    d = torch.float64
+    r = O.cell_backward(T(g["x"]).to(d), T(g["h"]).to(d), T(g["c"]).to(d), T(g["weight"]).to(d),
+                        T(g["bias"]).to(d), T(g["gh"]).to(d), T(g["gc"]).to(d))
+    for key in ("dx", "dh_prev", "dc_prev", "dW", "db"):
+        ref = g[key]
+        got = r[key].to(torch.float32).numpy()
+        scale = np.abs(ref).max() + 1e-12
+        assert np.abs(got - ref).max() / scale < 2e-5, key
+
+
+@pytest.mark.parametrize("path", golden_files("rollout_"), ids=os.path.basename)
+def test_rollout_matches_reference_golden(path):
+    g = load_golden(path)
+    ws, bs = [T(g["w1"]), T(g["w2"])], [T(g["b1"]), T(g["b2"])]
+    out, state, trace = O.stack_forward(T(g["x_seq"]), ws, bs, return_all=True)
+    for t, row in enumerate(trace):
+        (h1, c1), (h2, c2) = row
+        np.testing.assert_allclose(h1.numpy(), g["h1"][:, t], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(c1.numpy(), g["c1"][:, t], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(h2.numpy(), g["h2"][:, t], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(c2.numpy(), g["c2"][:, t], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(out.numpy(), g["h2"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("path", golden_files("rollout_"), ids=os.path.basename)
+def test_rollout_bptt_matches_reference_autograd_golden(path):
+    g = load_golden(path)
+    d = torch.float64
+    ws, bs = [T(g["w1"]).to(d), T(g["w2"]).to(d)], [T(g["b1"]).to(d), T(g["b2"]).to(d)]
+    dx, dws, dbs = O.stack_backward(T(g["x_seq"]).to(d), ws, bs, T(g["d_out"]).to(d))
+    for got, key in ((dx, "dx_seq"), (dws[0], "dW1"), (dws[1], "dW2"), (dbs[0], "db1"), (dbs[1], "db2")):
+        ref = g[key]
+        scale = np.abs(ref).max() + 1e-12
+        assert np.abs(got.to(torch.float32).numpy() - ref).max() / scale < 5e-5, key
+
+
+# ---- closed-form known answers -----------------------
+
+def test_kat_zero_weights():
+    # W=0, b=0  =>  c' = 0.5*c ; h' = 0.5*tanh(0.5*c);  c=2 -> c'=1.0, h'=0.380797088
+    w = torch.zeros(4 * 8, 8 + 8, 3, 3)
+    b = torch.zeros(4 * 8)
+    x = torch.randn(1, 8, 5, 5)
+    h = torch.randn(1, 8, 5, 5)
+    c = torch.full((1, 8, 5, 5), 2.0)
+    h2, c2 = O.cell_forward(x, h, c, w, b)
+    assert torch.allclose(c2, torch.full_like(c2, 1.0))
+    assert torch.allclose(h2, torch.full_like(h2, 0.380797088), atol=1e-7)
+
+
+def test_kat_zero_state_zero_input_bias_only():
+    torch.manual_seed(0)
+    ch = 4
+    w = torch.randn(4 * ch, 2 + ch, 3, 3)
+    b = torch.randn(4 * ch)
+    z = torch.zeros(1, ch, 6, 7)
+    h2, c2 = O.cell_forward(torch.zeros(1, 2, 6, 7), z, z, w, b)
+    bi, bf, bo, bg = b.split(ch)
+    c_exp = torch.sigmoid(bi) * torch.tanh(bg)
+    h_exp = torch.sigmoid(bo) * torch.tanh(c_exp)
+    # uniform in the interior AND at the borders (zero padding adds nothing)
+    assert torch.allclose(c2, c_exp.view(1, ch, 1, 1).expand_as(c2), atol=1e-7)
+    assert torch.allclose(h2, h_exp.view(1, ch, 1, 1).expand_as(h2), atol=1e-7)
+
+
+def test_kat_channel_and_gate_order():
+    # identity centre-tap weights: gate G of hidden channel j reads ONLY input channel src.
+    ch, cin = 3, 2
+    x = torch.randn(1, cin, 4, 4)
+    h = torch.randn(1, ch, 4, 4)
+    c = torch.randn(1, ch, 4, 4)
+    w = torch.zeros(4 * ch, cin + ch, 3, 3)
+    # i-gate of channel 0 <- x channel 1 ; g-gate of channel 0 <- h channel 2
+    w[0 * ch + 0, 1, 1, 1] = 1.0
+    w[3 * ch + 0, cin + 2, 1, 1] = 1.0
+    h2, c2 = O.cell_forward(x, h, c, w, torch.zeros(4 * ch))
+    i0 = torch.sigmoid(x[:, 1])
+    g0 = torch.tanh(h[:, 2])
+    c_exp0 = 0.5 * c[:, 0] + i0 * g0
+    assert torch.allclose(c2[:, 0], c_exp0, atol=1e-6)
+    assert torch.allclose(c2[:, 1], 0.5 * c[:, 1], atol=1e-6)  # untouched channels: f=0.5, g=0
+    assert torch.allclose(h2[:, 0], 0.5 * torch.tanh(c_exp0), atol=1e-6)
+
+
+def test_kat_zero_padding_border_pixel():
+    # a single non-zero border pixel spreads only to its in-bounds 3x3 neighbourhood
+    ch = 2
+    w = torch.zeros(4 * ch, 1 + ch, 3, 3)
+    w[3 * ch:, 0] = 1.0  # g gate sums the 3x3 window of x
+    x = torch.zeros(1, 1, 5, 5)
+    x[0, 0, 0, 4] = 3.0
+    z = torch.zeros(1, ch, 5, 5)
+    _, c2 = O.cell_forward(x, z, z, w, torch.zeros(4 * ch))
+    nz = (c2[0, 0] != 0).nonzero().tolist()
+    assert sorted(nz) == [[0, 3], [0, 4], [1, 3], [1, 4]]
+    assert torch.allclose(c2[0, 0, 0, 4], 0.5 * torch.tanh(torch.tensor(3.0)))
+
+
+def test_even_kernel_rejected_like_reference():
+    # padding k//2 with even k changes the spatial size -> c' = f*c + i*g cannot broadcast
+    w = torch.zeros(8, 4, 4, 4)
+    z = torch.zeros(1, 2, 6, 6)
+    with pytest.raises(RuntimeError):
+        O.cell_forward(torch.zeros(1, 2, 6, 6), z, z, w, torch.zeros(8))
+
+
+def test_encoder_forecaster_shapes_and_noinput_layer():
+    torch.manual_seed(1)
+    ch = 8
+    enc_w = [torch.randn(4 * ch, 4 + ch, 3, 3) * 0.1, torch.randn(4 * ch, ch + ch, 3, 3) * 0.1]
+    fc_w = [torch.randn(4 * ch, ch, 3, 3) * 0.1, torch.randn(4 * ch, ch + ch, 3, 3) * 0.1]
+    bz = [torch.zeros(4 * ch)] * 2
+    x = torch.randn(2, 3, 4, 5, 6)
+    out, st = O.encoder_forecaster_forward(x, enc_w, bz, fc_w, bz, t_out=4)
+    assert out.shape == (2, 4, ch, 5, 6) and len(st) == 2
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_oracle_matches_live_reference_cell():
+    sys.path.insert(0, REF)
+    sys.dont_write_bytecode = True
+    from src.models.convlstm import ConvLSTMCell
+    torch.manual_seed(7)
+    cell = ConvLSTMCell(5, 7, kernel_size=5)
+    x, h, c = torch.randn(2, 5, 9, 11), torch.randn(2, 7, 9, 11), torch.randn(2, 7, 9, 11)
+    hr, cr = cell(x, h, c)
+    ho, co = O.cell_forward(x, h, c, cell.conv.weight.detach(), cell.conv.bias.detach())
+    assert torch.allclose(hr, ho, atol=1e-6) and torch.allclose(cr, co, atol=1e-6)
