@@ -1,0 +1,120 @@
+/*
+ * plc.h -- C ABI of the B200-native ConvLSTM recurrence (libplc.so).
+ *
+ * The reference (Tomzhuiowewie/Pl-ConvLSTM-GAN) has no FFI: its hot path is the Python
+ * nn.Module `ConvLSTMCell` (src/models/convlstm.py:4-28) called from the T-loop of
+ * `Generator.forward` (src/models/generator.py:156-171).  This header is the boundary a
+ * replacement binds instead of `nn.Conv2d` + the ~10 ATen pointwise ops of that module;
+ * every entry point cites the reference lines it replaces.  Host-side mirror of the
+ * nn.Module API: pl-convlstm-gan_b200/nn.py; binding stub: INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all device buffers are caller-owned.
+ *   - activations are NHWC ("channels_last"): element (b, y, x, ch) at ((b*H + y)*W + x)*C + ch.
+ *     The logical shape stays the reference's [B, C, H, W] (torch.channels_last strides).
+ *   - every function returns PLC_OK (0) or a negative PlcStatus; the message is available
+ *     from plc_last_error() (thread-local).  There is NO fallback path: an unsupported
+ *     shape, a misaligned pointer or a missing sm_100 device is an error.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - re-entrant; callable from PyTorch's autograd worker threads.
+ */
+#ifndef PLC_H_
+#define PLC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLC_ABI_VERSION 1
+
+typedef enum PlcStatus {
+  PLC_OK = 0,
+  PLC_ERR_BAD_DESC = -1,     /* null / inconsistent descriptor                         */
+  PLC_ERR_UNSUPPORTED = -2,  /* shape or mode this build has no kernel for              */
+  PLC_ERR_ALIGNMENT = -3,    /* pointer not 16-byte aligned / channel count constraint  */
+  PLC_ERR_NULL_ARG = -4,
+  PLC_ERR_CUDA = -5,         /* CUDA runtime / driver error (message has the detail)    */
+  PLC_ERR_WORKSPACE = -6     /* workspace too small                                     */
+} PlcStatus;
+
+typedef enum PlcMode {
+  /* bf16 operands, fp32 accumulation in TMEM (tcgen05), fp32 cell state, tanh.approx gates.
+     x, h: bf16; c: fp32.  Requires Cin % 8 == 0 (0 allowed), Ch % 16 == 0.                */
+  PLC_MODE_BF16_TC = 0,
+  /* fp32 validation mode: fp32 SIMT FMA, exact expf/tanhf.  x, h, c: fp32.  Any Cin, Ch.  */
+  PLC_MODE_FP32 = 1
+} PlcMode;
+
+/* which packed-weight image plc_pack_weight produces */
+typedef enum PlcPackKind {
+  PLC_PACK_FWD = 0,   /* gate conv of convlstm.py:18 (also used for gate recompute in backward) */
+  PLC_PACK_DGRAD = 1  /* transposed/flipped image for d(cat(x,h)) = conv_transpose(dZ, W)      */
+} PlcPackKind;
+
+/* One ConvLSTM cell step problem.  Mirrors ConvLSTMCell(input_dim=Cin, hidden_dim=Ch,
+ * kernel_size=k, bias=has_bias) of convlstm.py:5-14 applied to a [B, *, H, W] batch.       */
+typedef struct PlcCellDesc {
+  int32_t B, H, W;
+  int32_t Cin;      /* channels of x (0 = no input tensor: forecaster first layer)          */
+  int32_t Ch;       /* hidden channels; conv has 4*Ch output channels in i,f,o,g order      */
+  int32_t k;        /* odd kernel size; zero "same" padding k/2, stride 1 (convlstm.py:12)  */
+  int32_t mode;     /* PlcMode                                                              */
+  int32_t has_bias; /* convlstm.py:13                                                       */
+} PlcCellDesc;
+
+/* ---- introspection ------------------------------------------------------------------- */
+int plc_abi_version(void);
+const char* plc_last_error(void);
+/* 1 if device `dev` can run this library (compute capability 10.x), else 0 */
+int plc_device_supported(int dev);
+
+/* ---- weights --------------------------------------------------------------------------
+ * Replaces: the implicit weight layout of nn.Conv2d at convlstm.py:8-14.
+ * `w_oihw` is the reference parameter `conv.weight` [4Ch, Cin+Ch, k, k] fp32 (device),
+ * x channels first then h channels; output channels in gate order i, f, o, g.            */
+size_t plc_packed_weight_bytes(const PlcCellDesc* d, int pack_kind);
+int plc_pack_weight(const PlcCellDesc* d, int pack_kind, const float* w_oihw, void* w_packed, void* stream);
+
+/* ---- forward cell step ------------------------------------------------------------------
+ * Replaces convlstm.py:17-28 (cat, conv, split, 3x sigmoid + tanh, c/h update) in ONE kernel.
+ *   x      [B,H,W,Cin]  (NULL iff Cin == 0)      h_prev [B,H,W,Ch]      c_prev [B,H,W,Ch]
+ *   bias   [4Ch] fp32 in reference order (NULL iff !has_bias)
+ *   h_out  [B,H,W,Ch]   c_out [B,H,W,Ch]   (must not alias h_prev / c_prev may alias c_out)
+ *   gates_out: optional [B,H,W,4Ch] (i,f,o,g activations, mode dtype for x) or NULL.
+ * dtypes: PLC_MODE_BF16_TC: x,h bf16, c fp32.  PLC_MODE_FP32: all fp32.                     */
+int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                 const void* w_packed_fwd, const float* bias, void* h_out, void* c_out, void* gates_out,
+                 void* stream);
+
+/* ---- backward (BPTT) cell step -----------------------------------------------------------
+ * Replaces autograd of convlstm.py:17-28: recomputes the gates from the
+ * saved (x, h_prev, c_prev), forms dZ, then dgrad and wgrad.
+ *   dh      [B,H,W,Ch]  gradient w.r.t. h_out, dtype of h
+ *   dh2     [B,H,W,Ch]  optional second contribution, added to dh inside the kernel (NULL = none):
+ *                       in BPTT h_t feeds both step t+1 of the same layer and the layer above.
+ *   dc_next [B,H,W,Ch]  gradient w.r.t. c_out, fp32 (NULL = zeros)
+ *   dx      [B,H,W,Cin] out (NULL = not needed), dtype of x
+ *   dh_prev [B,H,W,Ch]  out, dtype of h;   dc_prev [B,H,W,Ch] out fp32 (may alias dc_next)
+ *   dW_acc  [4Ch, Cin+Ch, k, k] fp32, reference layout, ACCUMULATED into (+=) across steps
+ *   db_acc  [4Ch] fp32, accumulated (NULL iff !has_bias)
+ *   workspace: plc_bwd_workspace_bytes(d) bytes of scratch (holds dZ).                          */
+size_t plc_bwd_workspace_bytes(const PlcCellDesc* d);
+int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                 const void* w_packed_fwd, const void* w_packed_dgrad, const float* bias, const void* dh,
+                 const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc, float* db_acc,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- layout helpers (HBM-bound elementwise kernels) ---------------------------------------
+ * The reference keeps NCHW fp32 tensors (generator.py:156-160).  These convert between that and
+ * the NHWC working layout at sequence entry / exit.  `C_dst >= C_src` zero-pads channels.       */
+int plc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C_src, int C_dst, int H, int W,
+                              void* stream);
+int plc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int C, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLC_H_ */

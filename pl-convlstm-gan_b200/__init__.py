@@ -1,0 +1,6 @@
+"""B200-native ConvLSTM recurrence: host-side mirror of the reference nn.Module API over libplc.so.
+
+Import name: ``plconv`` (this directory's name has hyphens; ``plconv/__init__.py`` aliases it).
+"""
+from . import _lib, build, functional  # noqa: F401
+from ._lib import PLC_MODE_BF16_TC, PLC_MODE_FP32  # noqa: F401

@@ -1,0 +1,73 @@
+"""ctypes binding of libplc.so (C ABI declared in include/plc.h).
+
+There is deliberately NO fallback: if the library cannot be built/loaded, or a call returns a
+non-zero status, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libplc.so")
+
+PLC_MODE_BF16_TC = 0
+PLC_MODE_FP32 = 1
+PLC_PACK_FWD = 0
+PLC_PACK_DGRAD = 1
+
+
+class PlcCellDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "H", "W", "Cin", "Ch", "k", "mode", "has_bias")]
+
+
+_vp, _sz, _int = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+_dp = ctypes.POINTER(PlcCellDesc)
+
+# name -> (restype, argtypes); must list every symbol include/plc.h declares (tests check this)
+SIGNATURES = {
+    "plc_abi_version": (_int, []),
+    "plc_last_error": (ctypes.c_char_p, []),
+    "plc_device_supported": (_int, [_int]),
+    "plc_packed_weight_bytes": (_sz, [_dp, _int]),
+    "plc_pack_weight": (_int, [_dp, _int, _vp, _vp, _vp]),
+    "plc_cell_fwd": (_int, [_dp] + [_vp] * 9),
+    "plc_bwd_workspace_bytes": (_sz, [_dp]),
+    "plc_cell_bwd": (_int, [_dp] + [_vp] * 15 + [_sz, _vp]),
+    "plc_nchw_f32_to_nhwc_bf16": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),
+    "plc_nhwc_bf16_to_nchw_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load (building first if needed and possible) libplc.so.  Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise RuntimeError(f"{LIB_PATH} is missing: run `python __graft_entry__.py build`")
+            from . import build as _build
+            _build.build()
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI and the binding drift apart
+            fn.restype = res
+            fn.argtypes = args
+        if lib.plc_abi_version() != 1:
+            raise RuntimeError("libplc.so ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().plc_last_error()
+        raise RuntimeError(f"{what} failed (status {status}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,389 @@
+// Implicit-GEMM "same" convolution on the 5th-gen tensor cores (tcgen05 + TMEM), fed by TMA,
+// with the ConvLSTM gate math fused into the epilogue.
+//
+//   D[pixel, n] = sum_{src, tap, c}  A_src[pixel + tap_offset, c] * Wp[n, (src, tap, c)]
+//
+// * M side: one CTA tile = 128 output pixels = a (th x tw) patch of one image (tw*th = 128).
+//   For every filter tap the A operand is ONE 4-D TMA box [64 ch, tw, th, 1] of the NHWC source,
+//   shifted by the tap offset; out-of-bounds rows/cols are zero-filled by TMA, which IS the
+//   reference's zero "same" padding (convlstm.py:12).  No im2col buffer, no torch.cat: x and h
+//   are two tensor maps walked in the weight's in-channel order (x first, then h; convlstm.py:17).
+// * N side: N_TILE = 4 * CH_TILE columns = gates (i,f,o,g) of CH_TILE hidden channels, packed so
+//   the four gates of one channel sit in the same TMEM lane -> the epilogue thread that owns a
+//   pixel has i,f,o,g for its channels and applies convlstm.py:21-27 without leaving the SM.
+// * K side: blocks of 64 bf16 (=128 B, one SWIZZLE_128B atom row) ordered (src, tap, chunk).
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer          (smem ring: kStages x {A 16 KB, B N_TILE*128 B})
+//   warp 1 lane 0 : tcgen05.mma issuer    (accumulators double-buffered in TMEM: 2 x N_TILE cols)
+//   warp 2        : TMEM alloc / dealloc
+//   warps 4..7    : epilogue (tcgen05.ld -> gate math -> global), overlapped with the next tile's MMAs
+#pragma once
+#include "plc_ptx.cuh"
+
+namespace plc {
+
+enum : int { EPI_LSTM_FWD = 0, EPI_LSTM_BWD_GATES = 1, EPI_PLAIN = 2 };
+
+struct ConvTcParams {
+  // geometry
+  int B, H, W;
+  int ksize, pad;
+  int tw, th, tw_log2;       // tile = th x tw pixels, tw*th == 128, tw power of two
+  int tiles_x, tiles_y;      // per image
+  int num_m_tiles, num_n_tiles, num_tiles;
+  int chunks0, chunks1;      // 64-channel K chunks of source 0 / source 1
+  int num_kb;                // ksize^2 * (chunks0 + chunks1)
+  // LSTM epilogues
+  int Ch;                    // hidden channels
+  int Cin;                   // EPI_PLAIN: first Cin output columns go to out0, the rest to out1
+  const float* bias;         // [4Ch] reference order or nullptr
+  const float* c_prev;       // [M, Ch] fp32
+  float* c_out;              // [M, Ch] fp32                       (FWD)
+  __nv_bfloat16* h_out;      // [M, Ch] bf16                       (FWD)
+  __nv_bfloat16* gates_out;  // [M, 4Ch] bf16 or nullptr           (FWD)
+  const __nv_bfloat16* dh;   // [M, Ch] bf16                       (BWD_GATES)
+  const __nv_bfloat16* dh2;  // [M, Ch] bf16 or nullptr, added     (BWD_GATES)
+  const float* dc_next;      // [M, Ch] fp32 or nullptr            (BWD_GATES)
+  float* dc_prev;            // [M, Ch] fp32                       (BWD_GATES)
+  __nv_bfloat16* dz;         // [M, 4Ch] bf16, reference gate order (BWD_GATES)
+  __nv_bfloat16* out0;       // [M, Cin] bf16 or nullptr           (PLAIN)
+  __nv_bfloat16* out1;       // [M, Ntot-Cin] bf16 or nullptr      (PLAIN)
+  int n_total;               // PLAIN: total valid output columns
+};
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes
+constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
+
+template <int N_TILE>
+struct ConvTcCfg {
+  static constexpr int kBBytes = N_TILE * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kAuxBytes = 4096 + 256;  // bias (<= 1024 floats) + barriers
+  static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - kAuxBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;
+  static constexpr int kTmemCols = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64) ? 64 : (2 * N_TILE <= 128) ? 128
+                                   : (2 * N_TILE <= 256) ? 256 : 512;
+  static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128");
+  static_assert(kStages >= 2, "need at least a double buffer");
+};
+
+__device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int& n_tile, int& b, int& y0, int& x0) {
+  n_tile = tile % p.num_n_tiles;
+  int m_tile = tile / p.num_n_tiles;
+  int tx = m_tile % p.tiles_x;
+  int r = m_tile / p.tiles_x;
+  int ty = r % p.tiles_y;
+  b = r / p.tiles_y;
+  y0 = ty * p.th;
+  x0 = tx * p.tw;
+}
+
+template <int N_TILE, int EPI>
+__global__ void __launch_bounds__(256, 1)
+conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap tmap_a0,
+                     const __grid_constant__ CUtensorMap tmap_a1, const __grid_constant__ CUtensorMap tmap_b) {
+  using Cfg = ConvTcCfg<N_TILE>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int CH_TILE = N_TILE / 4;
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  float* bias_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + 4096);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + kStages;            // [kStages]
+  uint64_t* tmem_full = bars + 2 * kStages;        // [2]
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;   // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a0);
+    tma_prefetch_desc(&tmap_a1);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_ptr_s, Cfg::kTmemCols);
+  if (EPI != EPI_PLAIN) {
+    for (int i = threadIdx.x; i < 4 * p.Ch; i += blockDim.x) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================================== TMA producer
+    uint32_t stage = 0, phase = 0;
+    const int kk = p.ksize * p.ksize;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int n_tile, b, y0, x0;
+      decode_tile(p, tile, n_tile, b, y0, x0);
+      int kb = 0;
+      for (int src = 0; src < 2; ++src) {
+        const int chunks = src ? p.chunks1 : p.chunks0;
+        const CUtensorMap* tm = src ? &tmap_a1 : &tmap_a0;
+        if (chunks == 0) continue;
+        for (int tap = 0; tap < kk; ++tap) {
+          const int dy = tap / p.ksize - p.pad;
+          const int dx = tap % p.ksize - p.pad;
+          for (int ck = 0; ck < chunks; ++ck, ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(smem_a + stage * kABytes, tm, &full_bar[stage], ck * kBlockK, x0 + dx, y0 + dy, b);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBlockK, n_tile * N_TILE);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(kTileM, N_TILE, 0, 0);
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * N_TILE;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * kABytes), 0, 1024);
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // +32 bytes per UMMA_K=16 inside the 128-byte swizzle atom (descriptor units of 16 B)
+          umma_bf16<1>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit<1>(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (kb == p.num_kb - 1) umma_commit<1>(&tmem_full[as]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue
+    const int q = warp - 4;  // TMEM lane quadrant == warp_idx % 4
+    const int row = q * 32 + lane;
+    const int ty = row >> p.tw_log2;
+    const int tx = row & (p.tw - 1);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      int n_tile, b, y0, x0;
+      decode_tile(p, tile, n_tile, b, y0, x0);
+      const int y = y0 + ty, x = x0 + tx;
+      const bool valid = (y < p.H) && (x < p.W);
+      const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * N_TILE;
+
+      if constexpr (EPI == EPI_LSTM_FWD || EPI == EPI_LSTM_BWD_GATES) {
+        const int ch0 = n_tile * CH_TILE;
+#pragma unroll 1
+        for (int cc = 0; cc < CH_TILE / 16; ++cc) {
+          uint32_t vi[16], vf[16], vo[16], vg[16];
+          tmem_ld16(t_acc + 0 * CH_TILE + cc * 16, vi);
+          tmem_ld16(t_acc + 1 * CH_TILE + cc * 16, vf);
+          tmem_ld16(t_acc + 2 * CH_TILE + cc * 16, vo);
+          tmem_ld16(t_acc + 3 * CH_TILE + cc * 16, vg);
+          tmem_ld_wait();
+          if (valid) {
+            const int chb = ch0 + cc * 16;
+            const size_t off = pix * p.Ch + chb;
+            float cp[16];
+            {
+              const float4* src = reinterpret_cast<const float4*>(p.c_prev + off);
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                float4 t = __ldg(src + v);
+                cp[4 * v + 0] = t.x; cp[4 * v + 1] = t.y; cp[4 * v + 2] = t.z; cp[4 * v + 3] = t.w;
+              }
+            }
+            if constexpr (EPI == EPI_LSTM_FWD) {
+              float cn[16];
+              uint32_t hp[8];
+              uint32_t gi[8], gf[8], go[8], gg[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                float hv[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int jj = j + u;
+                  const float ig = sigmoid_fast(__uint_as_float(vi[jj]) + bias_s[0 * p.Ch + chb + jj]);
+                  const float fg = sigmoid_fast(__uint_as_float(vf[jj]) + bias_s[1 * p.Ch + chb + jj]);
+                  const float og = sigmoid_fast(__uint_as_float(vo[jj]) + bias_s[2 * p.Ch + chb + jj]);
+                  const float gt = tanh_fast(__uint_as_float(vg[jj]) + bias_s[3 * p.Ch + chb + jj]);
+                  const float c2 = fmaf(fg, cp[jj], ig * gt);          // convlstm.py:26
+                  cn[jj] = c2;
+                  hv[u] = og * tanh_fast(c2);                          // convlstm.py:27
+                  vi[jj] = __float_as_uint(ig); vf[jj] = __float_as_uint(fg);
+                  vo[jj] = __float_as_uint(og); vg[jj] = __float_as_uint(gt);
+                }
+                hp[j >> 1] = pack_bf16x2(hv[0], hv[1]);
+              }
+              float4* cdst = reinterpret_cast<float4*>(p.c_out + off);
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                cdst[v] = make_float4(cn[4 * v], cn[4 * v + 1], cn[4 * v + 2], cn[4 * v + 3]);
+              uint4* hdst = reinterpret_cast<uint4*>(p.h_out + off);
+              hdst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+              hdst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+              if (p.gates_out) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  gi[j] = pack_bf16x2(__uint_as_float(vi[2 * j]), __uint_as_float(vi[2 * j + 1]));
+                  gf[j] = pack_bf16x2(__uint_as_float(vf[2 * j]), __uint_as_float(vf[2 * j + 1]));
+                  go[j] = pack_bf16x2(__uint_as_float(vo[2 * j]), __uint_as_float(vo[2 * j + 1]));
+                  gg[j] = pack_bf16x2(__uint_as_float(vg[2 * j]), __uint_as_float(vg[2 * j + 1]));
+                }
+                __nv_bfloat16* gbase = p.gates_out + pix * (4 * p.Ch) + chb;
+                uint4* d0 = reinterpret_cast<uint4*>(gbase + 0 * p.Ch);
+                uint4* d1 = reinterpret_cast<uint4*>(gbase + 1 * p.Ch);
+                uint4* d2 = reinterpret_cast<uint4*>(gbase + 2 * p.Ch);
+                uint4* d3 = reinterpret_cast<uint4*>(gbase + 3 * p.Ch);
+                d0[0] = make_uint4(gi[0], gi[1], gi[2], gi[3]); d0[1] = make_uint4(gi[4], gi[5], gi[6], gi[7]);
+                d1[0] = make_uint4(gf[0], gf[1], gf[2], gf[3]); d1[1] = make_uint4(gf[4], gf[5], gf[6], gf[7]);
+                d2[0] = make_uint4(go[0], go[1], go[2], go[3]); d2[1] = make_uint4(go[4], go[5], go[6], go[7]);
+                d3[0] = make_uint4(gg[0], gg[1], gg[2], gg[3]); d3[1] = make_uint4(gg[4], gg[5], gg[6], gg[7]);
+              }
+            } else {  // EPI_LSTM_BWD_GATES : SURVEY.md section 3.3
+              float dhv[16], dcn[16], dcp[16];
+              {
+                const uint4* s = reinterpret_cast<const uint4*>(p.dh + off);
+                uint4 a = __ldg(s), bq = __ldg(s + 1);
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+                  dhv[2 * j] = __low2float(t); dhv[2 * j + 1] = __high2float(t);
+                }
+                if (p.dh2) {
+                  const uint4* s2 = reinterpret_cast<const uint4*>(p.dh2 + off);
+                  uint4 a2 = __ldg(s2), b2 = __ldg(s2 + 1);
+                  const uint32_t w2[8] = {a2.x, a2.y, a2.z, a2.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w2[j]);
+                    dhv[2 * j] += __low2float(t); dhv[2 * j + 1] += __high2float(t);
+                  }
+                }
+              }
+              if (p.dc_next) {
+                const float4* s = reinterpret_cast<const float4*>(p.dc_next + off);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                  float4 t = __ldg(s + v);
+                  dcn[4 * v] = t.x; dcn[4 * v + 1] = t.y; dcn[4 * v + 2] = t.z; dcn[4 * v + 3] = t.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dcn[j] = 0.f;
+              }
+              uint32_t zi[8], zf[8], zo[8], zg[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                float di_[2], df_[2], do_[2], dg_[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int jj = j + u;
+                  const float ig = sigmoid_fast(__uint_as_float(vi[jj]) + bias_s[0 * p.Ch + chb + jj]);
+                  const float fg = sigmoid_fast(__uint_as_float(vf[jj]) + bias_s[1 * p.Ch + chb + jj]);
+                  const float og = sigmoid_fast(__uint_as_float(vo[jj]) + bias_s[2 * p.Ch + chb + jj]);
+                  const float gt = tanh_fast(__uint_as_float(vg[jj]) + bias_s[3 * p.Ch + chb + jj]);
+                  const float c2 = fmaf(fg, cp[jj], ig * gt);
+                  const float tc = tanh_fast(c2);
+                  const float dh_ = dhv[jj];
+                  const float dc = fmaf(dh_ * og, 1.f - tc * tc, dcn[jj]);
+                  dcp[jj] = dc * fg;
+                  di_[u] = dc * gt * ig * (1.f - ig);
+                  df_[u] = dc * cp[jj] * fg * (1.f - fg);
+                  do_[u] = dh_ * tc * og * (1.f - og);
+                  dg_[u] = dc * ig * (1.f - gt * gt);
+                }
+                zi[j >> 1] = pack_bf16x2(di_[0], di_[1]);
+                zf[j >> 1] = pack_bf16x2(df_[0], df_[1]);
+                zo[j >> 1] = pack_bf16x2(do_[0], do_[1]);
+                zg[j >> 1] = pack_bf16x2(dg_[0], dg_[1]);
+              }
+              float4* dcd = reinterpret_cast<float4*>(p.dc_prev + off);
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                dcd[v] = make_float4(dcp[4 * v], dcp[4 * v + 1], dcp[4 * v + 2], dcp[4 * v + 3]);
+              __nv_bfloat16* zb = p.dz + pix * (4 * p.Ch) + chb;
+              uint4* d0 = reinterpret_cast<uint4*>(zb + 0 * p.Ch);
+              uint4* d1 = reinterpret_cast<uint4*>(zb + 1 * p.Ch);
+              uint4* d2 = reinterpret_cast<uint4*>(zb + 2 * p.Ch);
+              uint4* d3 = reinterpret_cast<uint4*>(zb + 3 * p.Ch);
+              d0[0] = make_uint4(zi[0], zi[1], zi[2], zi[3]); d0[1] = make_uint4(zi[4], zi[5], zi[6], zi[7]);
+              d1[0] = make_uint4(zf[0], zf[1], zf[2], zf[3]); d1[1] = make_uint4(zf[4], zf[5], zf[6], zf[7]);
+              d2[0] = make_uint4(zo[0], zo[1], zo[2], zo[3]); d2[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
+              d3[0] = make_uint4(zg[0], zg[1], zg[2], zg[3]); d3[1] = make_uint4(zg[4], zg[5], zg[6], zg[7]);
+            }
+          }
+        }
+      } else {  // EPI_PLAIN: D -> bf16, columns [0,Cin) -> out0, [Cin, n_total) -> out1
+#pragma unroll 1
+        for (int cc = 0; cc < N_TILE / 16; ++cc) {
+          uint32_t v[16];
+          tmem_ld16(t_acc + cc * 16, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              const int n0 = n_tile * N_TILE + cc * 16 + hlf * 8;
+              if (n0 < p.n_total) {
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(v[hlf * 8 + 0]), __uint_as_float(v[hlf * 8 + 1]));
+                o.y = pack_bf16x2(__uint_as_float(v[hlf * 8 + 2]), __uint_as_float(v[hlf * 8 + 3]));
+                o.z = pack_bf16x2(__uint_as_float(v[hlf * 8 + 4]), __uint_as_float(v[hlf * 8 + 5]));
+                o.w = pack_bf16x2(__uint_as_float(v[hlf * 8 + 6]), __uint_as_float(v[hlf * 8 + 7]));
+                if (n0 < p.Cin) {
+                  if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pix * p.Cin + n0) = o;
+                } else {
+                  if (p.out1) *reinterpret_cast<uint4*>(p.out1 + pix * (p.n_total - p.Cin) + (n0 - p.Cin)) = o;
+                }
+              }
+            }
+          }
+        }
+      }
+      // release this accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace plc

@@ -1,0 +1,559 @@
+// C ABI of libplc.so (declared in include/plc.h): descriptor validation, weight packing, tensor-map
+// construction and kernel launches.  No torch types, no persistent device allocations.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/plc.h"
+#include "conv_igemm_tc.cuh"
+#include "conv_simt.cuh"
+#include "wgrad_tc.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define PLC_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) return fail(PLC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+// NHWC bf16 activation [B,H,W,C] as a 4-D tensor map; box = [64 ch, tw, th, 1], SWIZZLE_128B.
+int make_tmap_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int tw, int th) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled(act B=%d H=%d W=%d C=%d box=%dx%d) -> %d", B, H, W, C, tw, th,
+                (int)r);
+  return PLC_OK;
+}
+
+// row-major bf16 matrix [rows, cols] (cols contiguous); box = [box_cols, box_rows], SWIZZLE_128B.
+int make_tmap_mat(CUtensorMap* tm, const void* ptr, long rows, long cols, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled(mat %ldx%ld box=%dx%d) -> %d", rows, cols, box_rows, box_cols,
+                (int)r);
+  return PLC_OK;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int check_desc(const PlcCellDesc* d) {
+  if (!d) return fail(PLC_ERR_BAD_DESC, "null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Ch <= 0 || d->Cin < 0)
+    return fail(PLC_ERR_BAD_DESC, "bad sizes B=%d H=%d W=%d Cin=%d Ch=%d", d->B, d->H, d->W, d->Cin, d->Ch);
+  if (d->k <= 0 || (d->k % 2) == 0)
+    return fail(PLC_ERR_BAD_DESC, "kernel size %d must be odd (reference padding k//2 breaks even k, convlstm.py:12)",
+                d->k);
+  if (d->mode != PLC_MODE_BF16_TC && d->mode != PLC_MODE_FP32) return fail(PLC_ERR_BAD_DESC, "bad mode %d", d->mode);
+  if ((long long)d->B * d->H * d->W >= (1ll << 31)) return fail(PLC_ERR_UNSUPPORTED, "B*H*W must be < 2^31");
+  if (d->mode == PLC_MODE_BF16_TC) {
+    if (d->Cin % 8) return fail(PLC_ERR_ALIGNMENT, "bf16 mode needs Cin %% 8 == 0 (got %d): pad channels", d->Cin);
+    if (d->Ch % 16) return fail(PLC_ERR_ALIGNMENT, "bf16 mode needs Ch %% 16 == 0 (got %d)", d->Ch);
+    if (d->Ch > 256) return fail(PLC_ERR_UNSUPPORTED, "bf16 mode supports Ch <= 256 (got %d)", d->Ch);
+    if (d->k > 7) return fail(PLC_ERR_UNSUPPORTED, "bf16 mode supports k <= 7 (got %d)", d->k);
+  }
+  return PLC_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------ tensor-core tiling choices
+struct TcGeom {
+  int ch_tile, n_tile;       // LSTM: N_TILE = 4*CH_TILE
+  int tw, th, tw_log2, tiles_x, tiles_y;
+};
+
+int pick_ch_tile(int Ch) {
+  const int cands[4] = {64, 48, 32, 16};
+  for (int c : cands)
+    if (Ch % c == 0) return c;
+  return 16;
+}
+
+void pick_spatial_tile(int H, int W, TcGeom* g) {
+  long best = -1;
+  for (int l2 = 7; l2 >= 0; --l2) {
+    const int tw = 1 << l2, th = 128 >> l2;
+    const long area = (long)cdiv(W, tw) * tw * cdiv(H, th) * th;
+    if (best < 0 || area < best) {
+      best = area;
+      g->tw = tw; g->th = th; g->tw_log2 = l2;
+    }
+  }
+  g->tiles_x = cdiv(W, g->tw);
+  g->tiles_y = cdiv(H, g->th);
+}
+
+int pick_plain_n_tile(int n_total) {
+  if (n_total <= 64) return 64;
+  if (n_total <= 128) return 128;
+  if (n_total <= 192) return 192;
+  if (n_total <= 256) return 256;
+  // several N tiles: prefer the candidate with the least padding
+  int best = 256, best_pad = cdiv(n_total, 256) * 256 - n_total;
+  const int cands[3] = {192, 128, 64};
+  for (int c : cands) {
+    const int pad = cdiv(n_total, c) * c - n_total;
+    if (pad < best_pad) { best = c; best_pad = pad; }
+  }
+  return best;
+}
+
+// ------------------------------------------------------------------ bf16 packing kernels
+// forward image Wp[n'][k'] : n' = slice*N_TILE + gate*CH_TILE + j ; k' = kb*64 + jj, kb = (src, tap, chunk)
+__global__ void pack_w_tc_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Ch,
+                                     int ksize, int ch_tile, int chunks0, int chunks1) {
+  const int kk = ksize * ksize, ctot = Cin + Ch;
+  const int ktot = kk * (chunks0 + chunks1) * 64, ntot = 4 * Ch, n_tile = 4 * ch_tile;
+  const size_t total = static_cast<size_t>(ntot) * ktot;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int kp = idx % ktot, np = idx / ktot;
+    const int slice = np / n_tile, r = np % n_tile, gate = r / ch_tile, j = r % ch_tile;
+    const int o = gate * Ch + slice * ch_tile + j;
+    int kb = kp >> 6;
+    const int jj = kp & 63;
+    int ic = -1, tap = 0;
+    if (kb < kk * chunks0) {
+      tap = kb / chunks0;
+      const int c = (kb % chunks0) * 64 + jj;
+      if (c < Cin) ic = c;
+    } else {
+      kb -= kk * chunks0;
+      tap = kb / chunks1;
+      const int c = (kb % chunks1) * 64 + jj;
+      if (c < Ch) ic = Cin + c;
+    }
+    float v = 0.f;
+    if (ic >= 0) v = w[(static_cast<size_t>(o) * ctot + ic) * kk + tap];
+    out[idx] = __float2bfloat16(v);
+  }
+}
+// dgrad image Wd[c][k'] : rows c in [0, Cin+Ch) ; k' = (tap', chunk of dZ channel n)*64 + jj, flipped taps
+__global__ void pack_w_tc_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Ch,
+                                       int ksize, int chunksz) {
+  const int kk = ksize * ksize, ctot = Cin + Ch;
+  const int ktot = kk * chunksz * 64;
+  const size_t total = static_cast<size_t>(ctot) * ktot;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int kp = idx % ktot, c = idx / ktot;
+    const int kb = kp >> 6, jj = kp & 63;
+    const int tap = kb / chunksz;
+    const int n = (kb % chunksz) * 64 + jj;
+    float v = 0.f;
+    if (n < 4 * Ch) {
+      const int fy = ksize - 1 - tap / ksize, fx = ksize - 1 - tap % ksize;
+      v = w[(static_cast<size_t>(n) * ctot + c) * kk + fy * ksize + fx];
+    }
+    out[idx] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------ layout kernels
+// src [B, Cs, H*W] fp32  ->  dst [B, H*W, Cd] bf16 (channels >= Cs zero-filled); 32x32 smem transpose
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cs,
+                                             int Cd, int HW) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pp = p0 + threadIdx.x;
+    t[i][threadIdx.x] = (c < Cs && pp < HW) ? src[(static_cast<size_t>(b) * Cs + c) * HW + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, c = c0 + threadIdx.x;
+    if (pp < HW && c < Cd) dst[(static_cast<size_t>(b) * HW + pp) * Cd + c] = __float2bfloat16(t[threadIdx.x][i]);
+  }
+}
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C,
+                                             int HW) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (pp < HW && c < C) ? __bfloat162float(src[(static_cast<size_t>(b) * HW + pp) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pp = p0 + threadIdx.x;
+    if (c < C && pp < HW) dst[(static_cast<size_t>(b) * C + c) * HW + pp] = t[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------ tensor-core launches
+template <int EPI>
+int launch_conv_tc(int n_tile, const plc::ConvTcParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
+                   const CUtensorMap& b, cudaStream_t st) {
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+#define PLC_LAUNCH_TC(NT)                                                                                        \
+  case NT: {                                                                                                     \
+    auto kfn = plc::conv_igemm_tc_kernel<NT, EPI>;                                                               \
+    PLC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, plc::ConvTcCfg<NT>::kSmemBytes)); \
+    kfn<<<grid, 256, plc::ConvTcCfg<NT>::kSmemBytes, st>>>(p, a0, a1, b);                                        \
+    break;                                                                                                       \
+  }
+  switch (n_tile) {
+    PLC_LAUNCH_TC(64)
+    PLC_LAUNCH_TC(128)
+    PLC_LAUNCH_TC(192)
+    PLC_LAUNCH_TC(256)
+    default:
+      return fail(PLC_ERR_UNSUPPORTED, "no tensor-core kernel for N_TILE=%d", n_tile);
+  }
+#undef PLC_LAUNCH_TC
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+void fill_geom(const PlcCellDesc* d, const TcGeom& g, plc::ConvTcParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->B = d->B; p->H = d->H; p->W = d->W;
+  p->ksize = d->k; p->pad = d->k / 2;
+  p->tw = g.tw; p->th = g.th; p->tw_log2 = g.tw_log2;
+  p->tiles_x = g.tiles_x; p->tiles_y = g.tiles_y;
+  p->num_m_tiles = d->B * g.tiles_x * g.tiles_y;
+  p->Ch = d->Ch; p->Cin = d->Cin;
+}
+
+int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p) {
+  g->ch_tile = pick_ch_tile(d->Ch);
+  g->n_tile = 4 * g->ch_tile;
+  pick_spatial_tile(d->H, d->W, g);
+  fill_geom(d, *g, p);
+  p->num_n_tiles = d->Ch / g->ch_tile;
+  p->num_tiles = p->num_m_tiles * p->num_n_tiles;
+  p->chunks0 = cdiv(d->Cin, 64);
+  p->chunks1 = cdiv(d->Ch, 64);
+  p->num_kb = d->k * d->k * (p->chunks0 + p->chunks1);
+  return PLC_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int plc_abi_version(void) { return PLC_ABI_VERSION; }
+
+const char* plc_last_error(void) { return g_err.c_str(); }
+
+int plc_device_supported(int dev) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return major == 10 ? 1 : 0;
+}
+
+size_t plc_packed_weight_bytes(const PlcCellDesc* d, int pack_kind) {
+  if (check_desc(d) != PLC_OK) return 0;
+  const size_t kk = static_cast<size_t>(d->k) * d->k;
+  if (d->mode == PLC_MODE_FP32) return kk * (d->Cin + d->Ch) * 4 * d->Ch * sizeof(float);
+  if (pack_kind == PLC_PACK_FWD) {
+    const size_t ktot = kk * (cdiv(d->Cin, 64) + cdiv(d->Ch, 64)) * 64;
+    return static_cast<size_t>(4) * d->Ch * ktot * 2;
+  }
+  if (pack_kind == PLC_PACK_DGRAD) {
+    const size_t ktot = kk * cdiv(4 * d->Ch, 64) * 64;
+    return static_cast<size_t>(d->Cin + d->Ch) * ktot * 2;
+  }
+  fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
+  return 0;
+}
+
+int plc_pack_weight(const PlcCellDesc* d, int pack_kind, const float* w_oihw, void* w_packed, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!w_oihw || !w_packed) return fail(PLC_ERR_NULL_ARG, "plc_pack_weight: null pointer");
+  if (pack_kind != PLC_PACK_FWD && pack_kind != PLC_PACK_DGRAD) return fail(PLC_ERR_BAD_DESC, "bad pack kind");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 256, blocks = 148 * 4;
+  if (d->mode == PLC_MODE_FP32) {
+    if (pack_kind == PLC_PACK_FWD)
+      plc::pack_w_f32_fwd_kernel<<<blocks, threads, 0, st>>>(w_oihw, static_cast<float*>(w_packed), d->Cin, d->Ch, d->k);
+    else
+      plc::pack_w_f32_dgrad_kernel<<<blocks, threads, 0, st>>>(w_oihw, static_cast<float*>(w_packed), d->Cin, d->Ch,
+                                                               d->k);
+  } else {
+    if (!aligned16(w_packed)) return fail(PLC_ERR_ALIGNMENT, "w_packed must be 16-byte aligned");
+    if (pack_kind == PLC_PACK_FWD)
+      pack_w_tc_fwd_kernel<<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), d->Cin, d->Ch,
+                                                       d->k, pick_ch_tile(d->Ch), cdiv(d->Cin, 64), cdiv(d->Ch, 64));
+    else
+      pack_w_tc_dgrad_kernel<<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), d->Cin, d->Ch,
+                                                         d->k, cdiv(4 * d->Ch, 64));
+  }
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                 const void* w_packed_fwd, const float* bias, void* h_out, void* c_out, void* gates_out,
+                 void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if ((d->Cin > 0 && !x) || !h_prev || !c_prev || !w_packed_fwd || !h_out || !c_out)
+    return fail(PLC_ERR_NULL_ARG, "plc_cell_fwd: null pointer");
+  if (d->has_bias && !bias) return fail(PLC_ERR_NULL_ARG, "plc_cell_fwd: has_bias set but bias is null");
+  if (h_out == h_prev) return fail(PLC_ERR_BAD_DESC, "h_out must not alias h_prev (halo reads)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  if (d->mode == PLC_MODE_FP32) {
+    plc::ConvSimtParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = d->B; p.H = d->H; p.W = d->W; p.M = d->B * d->H * d->W;
+    p.ksize = d->k; p.pad = d->k / 2;
+    p.C0 = d->Cin; p.C1 = d->Ch;
+    p.K = d->k * d->k * (d->Cin + d->Ch);
+    p.N = 4 * d->Ch; p.Ch = d->Ch; p.Cin = d->Cin;
+    p.src0 = static_cast<const float*>(x); p.src1 = static_cast<const float*>(h_prev);
+    p.w = static_cast<const float*>(w_packed_fwd);
+    p.bias = d->has_bias ? bias : nullptr;
+    p.c_prev = static_cast<const float*>(c_prev);
+    p.c_out = static_cast<float*>(c_out); p.h_out = static_cast<float*>(h_out);
+    p.gates_out = static_cast<float*>(gates_out);
+    dim3 grid(cdiv(p.M, plc::SBM), cdiv(p.N, plc::SBN));
+    plc::conv_simt_kernel<plc::SEPI_LSTM_FWD><<<grid, 256, 0, st>>>(p);
+    PLC_CUDA(cudaGetLastError());
+    return PLC_OK;
+  }
+
+  if (!aligned16(x) || !aligned16(h_prev) || !aligned16(c_prev) || !aligned16(w_packed_fwd) || !aligned16(h_out) ||
+      !aligned16(c_out) || !aligned16(gates_out))
+    return fail(PLC_ERR_ALIGNMENT, "plc_cell_fwd: all device pointers must be 16-byte aligned");
+  TcGeom g;
+  plc::ConvTcParams p;
+  lstm_tc_setup(d, &g, &p);
+  p.bias = d->has_bias ? bias : nullptr;
+  p.c_prev = static_cast<const float*>(c_prev);
+  p.c_out = static_cast<float*>(c_out);
+  p.h_out = static_cast<__nv_bfloat16*>(h_out);
+  p.gates_out = static_cast<__nv_bfloat16*>(gates_out);
+  CUtensorMap ta0, ta1, tb;
+  if ((rc = make_tmap_act(&ta1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th))) return rc;
+  if (d->Cin > 0) {
+    if ((rc = make_tmap_act(&ta0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th))) return rc;
+  } else {
+    ta0 = ta1;
+  }
+  if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile))) return rc;
+  return launch_conv_tc<plc::EPI_LSTM_FWD>(g.n_tile, p, ta0, ta1, tb, st);
+}
+
+size_t plc_bwd_workspace_bytes(const PlcCellDesc* d) {
+  if (check_desc(d) != PLC_OK) return 0;
+  const size_t m = static_cast<size_t>(d->B) * d->H * d->W;
+  return m * 4 * d->Ch * (d->mode == PLC_MODE_FP32 ? 4 : 2);
+}
+
+int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                 const void* w_packed_fwd, const void* w_packed_dgrad, const float* bias, const void* dh,
+                 const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc,
+                 float* db_acc, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if ((d->Cin > 0 && !x) || !h_prev || !c_prev || !w_packed_fwd || !dh || !dc_prev || !workspace)
+    return fail(PLC_ERR_NULL_ARG, "plc_cell_bwd: null pointer");
+  if ((dx || dh_prev) && !w_packed_dgrad) return fail(PLC_ERR_NULL_ARG, "plc_cell_bwd: dgrad image missing");
+  if (d->has_bias && !bias) return fail(PLC_ERR_NULL_ARG, "plc_cell_bwd: has_bias set but bias is null");
+  if (workspace_bytes < plc_bwd_workspace_bytes(d))
+    return fail(PLC_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, plc_bwd_workspace_bytes(d));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int M = d->B * d->H * d->W;
+  const int kk = d->k * d->k;
+
+  if (d->mode == PLC_MODE_FP32) {
+    // 1) recompute gates, dZ + dc_prev
+    plc::ConvSimtParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = d->B; p.H = d->H; p.W = d->W; p.M = M;
+    p.ksize = d->k; p.pad = d->k / 2;
+    p.C0 = d->Cin; p.C1 = d->Ch; p.K = kk * (d->Cin + d->Ch);
+    p.N = 4 * d->Ch; p.Ch = d->Ch; p.Cin = d->Cin;
+    p.src0 = static_cast<const float*>(x); p.src1 = static_cast<const float*>(h_prev);
+    p.w = static_cast<const float*>(w_packed_fwd);
+    p.bias = d->has_bias ? bias : nullptr;
+    p.c_prev = static_cast<const float*>(c_prev);
+    p.dh = static_cast<const float*>(dh); p.dh2 = static_cast<const float*>(dh2);
+    p.dc_next = dc_next; p.dc_prev = dc_prev;
+    p.dz = static_cast<float*>(workspace);
+    dim3 grid(cdiv(M, plc::SBM), cdiv(p.N, plc::SBN));
+    plc::conv_simt_kernel<plc::SEPI_LSTM_BWD_GATES><<<grid, 256, 0, st>>>(p);
+    PLC_CUDA(cudaGetLastError());
+    // 2) dgrad
+    if (dx || dh_prev) {
+      plc::ConvSimtParams q;
+      memset(&q, 0, sizeof(q));
+      q.B = d->B; q.H = d->H; q.W = d->W; q.M = M;
+      q.ksize = d->k; q.pad = d->k / 2;
+      q.C0 = 4 * d->Ch; q.C1 = 0; q.K = kk * 4 * d->Ch;
+      q.N = d->Cin + d->Ch; q.Ch = d->Ch; q.Cin = d->Cin;
+      q.src0 = static_cast<const float*>(workspace);
+      q.w = static_cast<const float*>(w_packed_dgrad);
+      q.out0 = static_cast<float*>(dx); q.out1 = static_cast<float*>(dh_prev);
+      dim3 g2(cdiv(M, plc::SBM), cdiv(q.N, plc::SBN));
+      plc::conv_simt_kernel<plc::SEPI_PLAIN><<<g2, 256, 0, st>>>(q);
+      PLC_CUDA(cudaGetLastError());
+    }
+    // 3) wgrad (+ bias grad)
+    if (dW_acc) {
+      plc::WgradParams w;
+      memset(&w, 0, sizeof(w));
+      w.B = d->B; w.H = d->H; w.W = d->W; w.M = M;
+      w.ksize = d->k; w.pad = d->k / 2;
+      w.C0 = d->Cin; w.C1 = d->Ch; w.K = kk * (d->Cin + d->Ch); w.N = 4 * d->Ch;
+      w.src0 = x; w.src1 = h_prev; w.dz = workspace; w.dW = dW_acc; w.db = d->has_bias ? db_acc : nullptr;
+      const int tiles = cdiv(w.N, plc::SBN) * cdiv(w.K, plc::SBM);
+      int splits = cdiv(sm_count() * 4, tiles);
+      if (splits < 1) splits = 1;
+      int ppb = cdiv(cdiv(M, splits), plc::SBK) * plc::SBK;
+      if (ppb < plc::SBK) ppb = plc::SBK;
+      w.pix_per_block = ppb;
+      dim3 g3(cdiv(w.N, plc::SBN), cdiv(w.K, plc::SBM), cdiv(M, ppb));
+      plc::wgrad_simt_kernel<float><<<g3, 256, 0, st>>>(w);
+      PLC_CUDA(cudaGetLastError());
+    }
+    return PLC_OK;
+  }
+
+  // ---------------- bf16 tensor-core mode
+  if (!aligned16(x) || !aligned16(h_prev) || !aligned16(c_prev) || !aligned16(w_packed_fwd) ||
+      !aligned16(w_packed_dgrad) || !aligned16(dh) || !aligned16(dh2) || !aligned16(dc_next) || !aligned16(dx) ||
+      !aligned16(dh_prev) || !aligned16(dc_prev) || !aligned16(workspace))
+    return fail(PLC_ERR_ALIGNMENT, "plc_cell_bwd: all device pointers must be 16-byte aligned");
+  TcGeom g;
+  plc::ConvTcParams p;
+  lstm_tc_setup(d, &g, &p);
+  // 1) gate recompute (same mainloop as the forward) + dZ / dc_prev epilogue
+  p.bias = d->has_bias ? bias : nullptr;
+  p.c_prev = static_cast<const float*>(c_prev);
+  p.dh = static_cast<const __nv_bfloat16*>(dh);
+  p.dh2 = static_cast<const __nv_bfloat16*>(dh2);
+  p.dc_next = dc_next;
+  p.dc_prev = dc_prev;
+  p.dz = static_cast<__nv_bfloat16*>(workspace);
+  CUtensorMap ta0, ta1, tb;
+  if ((rc = make_tmap_act(&ta1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th))) return rc;
+  if (d->Cin > 0) {
+    if ((rc = make_tmap_act(&ta0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th))) return rc;
+  } else {
+    ta0 = ta1;
+  }
+  if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile))) return rc;
+  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, p, ta0, ta1, tb, st))) return rc;
+
+  // 2) dgrad: conv of dZ (4Ch channels) with the flipped/transposed image -> dx, dh_prev
+  if (dx || dh_prev) {
+    plc::ConvTcParams q;
+    fill_geom(d, g, &q);
+    const int n_total = d->Cin + d->Ch;
+    const int nt = pick_plain_n_tile(n_total);
+    q.num_n_tiles = cdiv(n_total, nt);
+    q.num_tiles = q.num_m_tiles * q.num_n_tiles;
+    q.chunks0 = cdiv(4 * d->Ch, 64);
+    q.chunks1 = 0;
+    q.num_kb = kk * q.chunks0;
+    q.n_total = n_total;
+    q.out0 = static_cast<__nv_bfloat16*>(dx);
+    q.out1 = static_cast<__nv_bfloat16*>(dh_prev);
+    CUtensorMap tz, tbd;
+    if ((rc = make_tmap_act(&tz, workspace, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th))) return rc;
+    if ((rc = make_tmap_mat(&tbd, w_packed_dgrad, n_total, (long)q.num_kb * 64, 64, nt))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, q, tz, tz, tbd, st))) return rc;
+  }
+
+  // 3) wgrad + bias grad
+  if (dW_acc) {
+    if ((rc = plc::launch_wgrad_tc(d, x, h_prev, workspace, dW_acc, d->has_bias ? db_acc : nullptr, sm_count(), st)))
+      return fail(rc, "wgrad launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  return PLC_OK;
+}
+
+int plc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C_src, int C_dst, int H, int W,
+                              void* stream) {
+  if (!src || !dst) return fail(PLC_ERR_NULL_ARG, "null pointer");
+  if (B <= 0 || C_src <= 0 || C_dst < C_src || H <= 0 || W <= 0) return fail(PLC_ERR_BAD_DESC, "bad sizes");
+  dim3 grid(cdiv(H * W, 32), cdiv(C_dst, 32), B), block(32, 8);
+  nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), C_src, C_dst, H * W);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+int plc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int C, int H, int W, void* stream) {
+  if (!src || !dst) return fail(PLC_ERR_NULL_ARG, "null pointer");
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(PLC_ERR_BAD_DESC, "bad sizes");
+  dim3 grid(cdiv(H * W, 32), cdiv(C, 32), B), block(32, 8);
+  nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), dst, C, H * W);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+}  // extern "C"

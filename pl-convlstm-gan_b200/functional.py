@@ -1,0 +1,173 @@
+"""Tensor-level wrappers over the C ABI (torch is plumbing: device memory + current stream).
+
+Working layout: NHWC-contiguous tensors of shape [B, H, W, C].
+  bf16 tensor-core mode : x, h bf16; c fp32.     fp32 validation mode: everything fp32.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import PLC_MODE_BF16_TC, PLC_MODE_FP32, PLC_PACK_DGRAD, PLC_PACK_FWD, PlcCellDesc
+
+Tensor = torch.Tensor
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: this library has no CPU path")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous NHWC [B,H,W,C]")
+
+
+def make_desc(B: int, H: int, W: int, Cin: int, Ch: int, k: int, mode: int, has_bias: bool) -> PlcCellDesc:
+    return PlcCellDesc(B, H, W, Cin, Ch, k, mode, 1 if has_bias else 0)
+
+
+@dataclass
+class PackedWeights:
+    """Kernel-ready images of one cell's `conv.weight` (+ the fp32 bias in reference order)."""
+    fwd: Tensor
+    dgrad: Optional[Tensor]
+    bias: Optional[Tensor]
+    mode: int
+    Cin: int
+    Ch: int
+    k: int
+
+
+def pack_weights(weight: Tensor, bias: Optional[Tensor], Cin: int, Ch: int, k: int, mode: int,
+                 with_dgrad: bool = False, cin_pad: Optional[int] = None) -> PackedWeights:
+    """weight: reference `conv.weight` [4Ch, Cin+Ch, k, k] (any float dtype, CUDA).
+
+    cin_pad: pad the x-channel block with zero columns up to this many channels (bf16 mode needs
+    Cin % 8 == 0; the activations are padded the same way by the caller)."""
+    lib = _lib.load()
+    assert weight.shape == (4 * Ch, Cin + Ch, k, k), (tuple(weight.shape), Cin, Ch, k)
+    w = weight.detach().to(torch.float32)
+    if cin_pad is not None and cin_pad != Cin:
+        wp = torch.zeros(4 * Ch, cin_pad + Ch, k, k, device=w.device, dtype=torch.float32)
+        wp[:, :Cin] = w[:, :Cin]
+        wp[:, cin_pad:] = w[:, Cin:]
+        w, Cin = wp, cin_pad
+    w = w.contiguous()
+    d = make_desc(1, 1, 1, Cin, Ch, k, mode, bias is not None)
+    out = {}
+    for kind, want in ((PLC_PACK_FWD, True), (PLC_PACK_DGRAD, with_dgrad)):
+        if not want:
+            out[kind] = None
+            continue
+        nbytes = lib.plc_packed_weight_bytes(ctypes.byref(d), kind)
+        if nbytes == 0:
+            _lib.check(-1, "plc_packed_weight_bytes")
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        _lib.check(lib.plc_pack_weight(ctypes.byref(d), kind, _ptr(w), _ptr(buf), _stream()), "plc_pack_weight")
+        out[kind] = buf
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    return PackedWeights(out[PLC_PACK_FWD], out[PLC_PACK_DGRAD], b, mode, Cin, Ch, k)
+
+
+def _act_dtype(mode: int):
+    return torch.bfloat16 if mode == PLC_MODE_BF16_TC else torch.float32
+
+
+def cell_forward(x: Optional[Tensor], h: Tensor, c: Tensor, pw: PackedWeights,
+                 h_out: Optional[Tensor] = None, c_out: Optional[Tensor] = None,
+                 gates_out: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """One fused cell step (convlstm.py:16-28).  NHWC tensors; returns (h_next, c_next)."""
+    lib = _lib.load()
+    B, H, W, Ch = h.shape
+    adt = _act_dtype(pw.mode)
+    _require_cuda(h, "h"); _require_cuda(c, "c")
+    if h.dtype != adt or c.dtype != torch.float32:
+        raise RuntimeError(f"dtype mismatch: h {h.dtype} (want {adt}), c {c.dtype} (want float32)")
+    if pw.Cin > 0:
+        _require_cuda(x, "x")
+        if x.dtype != adt or tuple(x.shape) != (B, H, W, pw.Cin):
+            raise RuntimeError(f"x must be {adt} [B,H,W,{pw.Cin}], got {x.dtype} {tuple(x.shape)}")
+    if Ch != pw.Ch or tuple(c.shape) != (B, H, W, Ch):
+        raise RuntimeError("state shape mismatch")
+    if h_out is None:
+        h_out = torch.empty_like(h)
+    if c_out is None:
+        c_out = torch.empty_like(c)
+    d = make_desc(B, H, W, pw.Cin, Ch, pw.k, pw.mode, pw.bias is not None)
+    _lib.check(lib.plc_cell_fwd(ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h), _ptr(c), _ptr(pw.fwd),
+                                _ptr(pw.bias), _ptr(h_out), _ptr(c_out), _ptr(gates_out), _stream()),
+               "plc_cell_fwd")
+    return h_out, c_out
+
+
+def bwd_workspace(B: int, H: int, W: int, pw: PackedWeights, device) -> Tensor:
+    lib = _lib.load()
+    d = make_desc(B, H, W, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)
+    return torch.empty(lib.plc_bwd_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8, device=device)
+
+
+def cell_backward(x: Optional[Tensor], h_prev: Tensor, c_prev: Tensor, pw: PackedWeights, dh: Tensor,
+                  dh2: Optional[Tensor], dc_next: Optional[Tensor], dW_acc: Optional[Tensor],
+                  db_acc: Optional[Tensor], need_dx: bool = True, workspace: Optional[Tensor] = None,
+                  dx: Optional[Tensor] = None, dh_prev: Optional[Tensor] = None,
+                  dc_prev: Optional[Tensor] = None):
+    """BPTT of one cell step: returns (dx, dh_prev, dc_prev); dW_acc/db_acc are += in place.
+
+    dW_acc is fp32 in the reference layout [4Ch, Cin+Ch, k, k] (Cin = pw.Cin, i.e. the padded count)."""
+    lib = _lib.load()
+    B, H, W, Ch = h_prev.shape
+    if pw.dgrad is None:
+        raise RuntimeError("weights were packed without the dgrad image (with_dgrad=True)")
+    if workspace is None:
+        workspace = bwd_workspace(B, H, W, pw, h_prev.device)
+    if dx is None and need_dx and pw.Cin > 0:
+        dx = torch.empty_like(x)
+    if dh_prev is None:
+        dh_prev = torch.empty_like(h_prev)
+    if dc_prev is None:
+        dc_prev = torch.empty_like(c_prev)
+    d = make_desc(B, H, W, pw.Cin, Ch, pw.k, pw.mode, pw.bias is not None)
+    _lib.check(lib.plc_cell_bwd(ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h_prev), _ptr(c_prev),
+                                _ptr(pw.fwd), _ptr(pw.dgrad), _ptr(pw.bias), _ptr(dh), _ptr(dh2), _ptr(dc_next),
+                                _ptr(dx), _ptr(dh_prev), _ptr(dc_prev), _ptr(dW_acc), _ptr(db_acc),
+                                _ptr(workspace), workspace.numel(), _stream()),
+               "plc_cell_bwd")
+    return dx, dh_prev, dc_prev
+
+
+def nchw_to_nhwc(src: Tensor, mode: int, c_pad: Optional[int] = None) -> Tensor:
+    """Reference layout [B,C,H,W] fp32 -> working layout [B,H,W,C'] (bf16 in TC mode, zero-padded to c_pad)."""
+    B, C, H, W = src.shape
+    cd = C if c_pad is None else c_pad
+    if mode == PLC_MODE_FP32:
+        out = src.to(torch.float32).permute(0, 2, 3, 1)
+        if cd != C:
+            out = torch.nn.functional.pad(out, (0, cd - C))
+        return out.contiguous()
+    lib = _lib.load()
+    s = src.to(torch.float32).contiguous()
+    out = torch.empty(B, H, W, cd, dtype=torch.bfloat16, device=src.device)
+    _lib.check(lib.plc_nchw_f32_to_nhwc_bf16(_ptr(s), _ptr(out), B, C, cd, H, W, _stream()), "plc_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_to_nchw(src: Tensor) -> Tensor:
+    """Working layout [B,H,W,C] -> reference layout [B,C,H,W] fp32."""
+    B, H, W, C = src.shape
+    if src.dtype == torch.float32:
+        return src.permute(0, 3, 1, 2).contiguous()
+    lib = _lib.load()
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=src.device)
+    _lib.check(lib.plc_nhwc_bf16_to_nchw_f32(_ptr(src.contiguous()), _ptr(out), B, C, H, W, _stream()),
+               "plc_nhwc_bf16_to_nchw_f32")
+    return out

@@ -1,0 +1,215 @@
+"""GPU parity: the CUDA cell step (through the C ABI) vs the CPU oracle and the reference goldens.
+
+Tolerances (north_star): bf16 tensor-core mode <= 1e-2 relative (per-step h/c), fp32 validation
+mode <= 1e-5.  "relative" = max |err| / max |ref| over the tensor (bf16 h has 2^-9 rounding).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files, load_golden
+from oracle import convlstm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2
+FP32_TOL = 1e-5
+
+
+def _plconv():
+    import plconv
+    from plconv import functional as F
+    return plconv, F
+
+
+def rel_err(got: torch.Tensor, ref: torch.Tensor) -> float:
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    return float((got - ref).abs().max() / (ref.abs().max() + 1e-30))
+
+
+def report(name, got, ref):
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    err = (got - ref).abs()
+    idx = np.unravel_index(int(err.argmax()), err.shape)
+    return (f"{name}: rel={float(err.max() / (ref.abs().max() + 1e-30)):.3e} max_abs={float(err.max()):.3e} at {idx} "
+            f"got={float(got[idx]):.5f} ref={float(ref[idx]):.5f} frac>1e-2={(err > 1e-2).double().mean():.4f} "
+            f"nan={int(torch.isnan(got).sum())}")
+
+
+def nhwc(t, dtype, dev, c_pad=None):
+    """[B,C,H,W] cpu tensor -> [B,H,W,C'] device tensor"""
+    t = t.permute(0, 2, 3, 1)
+    if c_pad is not None and c_pad != t.shape[-1]:
+        t = torch.nn.functional.pad(t, (0, c_pad - t.shape[-1]))
+    return t.contiguous().to(device=dev, dtype=dtype)
+
+
+def nchw(t):
+    return t.detach().float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def pad8(c):
+    return (c + 7) // 8 * 8
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def run_cell(mode, x, h, c, w, b, dev):
+    """x,h,c NCHW fp32 cpu; w OIHW; returns (h2, c2) NCHW fp32 cpu via the CUDA path."""
+    plconv, F = _plconv()
+    B, cin, H, W = x.shape if x is not None else (h.shape[0], 0, h.shape[2], h.shape[3])
+    ch = h.shape[1]
+    k = w.shape[-1]
+    if mode == plconv.PLC_MODE_BF16_TC:
+        cp = pad8(cin)
+        adt = torch.bfloat16
+    else:
+        cp = cin
+        adt = torch.float32
+    pw = F.pack_weights(w.to(dev), None if b is None else b.to(dev), cin, ch, k, mode, cin_pad=cp)
+    xd = nhwc(x, adt, dev, cp) if cin else None
+    hd = nhwc(h, adt, dev)
+    cd = nhwc(c, torch.float32, dev)
+    h2, c2 = F.cell_forward(xd, hd, cd, pw)
+    torch.cuda.synchronize()
+    return nchw(h2), nchw(c2)
+
+
+@pytest.mark.parametrize("path", golden_files("cell_"), ids=os.path.basename)
+def test_fp32_mode_forward_vs_reference_golden(path, cuda_device):
+    plconv, _ = _plconv()
+    g = load_golden(path)
+    T = torch.from_numpy
+    h2, c2 = run_cell(plconv.PLC_MODE_FP32, T(g["x"]), T(g["h"]), T(g["c"]), T(g["weight"]), T(g["bias"]), cuda_device)
+    eh, ec = rel_err(h2, T(g["h_next"])), rel_err(c2, T(g["c_next"]))
+    assert eh < FP32_TOL and ec < FP32_TOL, report("h", h2, T(g["h_next"])) + " | " + report("c", c2, T(g["c_next"]))
+
+
+@pytest.mark.parametrize("path", golden_files("cell_"), ids=os.path.basename)
+def test_bf16_mode_forward_vs_reference_golden(path, cuda_device):
+    plconv, _ = _plconv()
+    g = load_golden(path)
+    T = torch.from_numpy
+    h2, c2 = run_cell(plconv.PLC_MODE_BF16_TC, T(g["x"]), T(g["h"]), T(g["c"]), T(g["weight"]), T(g["bias"]),
+                      cuda_device)
+    eh, ec = rel_err(h2, T(g["h_next"])), rel_err(c2, T(g["c_next"]))
+    assert eh < BF16_TOL and ec < BF16_TOL, report("h", h2, T(g["h_next"])) + " | " + report("c", c2, T(g["c_next"]))
+
+
+# (B, Cin, Ch, H, W, k)
+SHAPES = [
+    (1, 64, 64, 8, 16, 1),      # pure GEMM: one tile, one tap
+    (1, 64, 64, 8, 16, 3),      # one tile, 9 taps, halo entirely zero padding
+    (2, 64, 64, 16, 32, 3),     # several tiles with real halos
+    (1, 16, 16, 12, 15, 3),     # ragged W, channel chunks < 64 (TMA OOB fill in C)
+    (2, 8, 32, 9, 7, 5),        # k=5, odd sizes
+    (1, 128, 128, 16, 16, 3),   # 2 N tiles (Ch=128), 2 K chunks per source
+    (1, 32, 48, 10, 20, 3),     # CH_TILE=48
+    (3, 0, 32, 8, 8, 3),        # no input tensor (forecaster first layer)
+    (1, 72, 80, 6, 130, 3),     # W > 128, chunk tails, CH_TILE=16
+    (2, 64, 256, 8, 8, 3),      # Ch = 256: 4 N tiles
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "B%d_Cin%d_Ch%d_%dx%d_k%d" % s)
+@pytest.mark.parametrize("mode_name", ["bf16", "fp32"])
+def test_forward_vs_oracle(shape, mode_name, cuda_device):
+    plconv, _ = _plconv()
+    B, cin, ch, H, W, k = shape
+    mode = plconv.PLC_MODE_BF16_TC if mode_name == "bf16" else plconv.PLC_MODE_FP32
+    gen = torch.Generator().manual_seed(hash(shape) % (2 ** 31))
+    fan_in = (cin + ch) * k * k
+    w = (torch.rand(4 * ch, cin + ch, k, k, generator=gen) * 2 - 1) * (3.0 / fan_in) ** 0.5 * 2
+    b = torch.randn(4 * ch, generator=gen) * 0.5
+    x = torch.randn(B, cin, H, W, generator=gen) if cin else None
+    h = torch.randn(B, ch, H, W, generator=gen) * 0.5
+    c = torch.randn(B, ch, H, W, generator=gen)
+    if mode_name == "bf16":
+        # isolate kernel error from operand quantisation: the oracle sees the same bf16-rounded operands
+        xr, hr, wr = (None if x is None else bf16r(x)), bf16r(h), bf16r(w)
+        tol = BF16_TOL
+    else:
+        xr, hr, wr = x, h, w
+        tol = FP32_TOL
+    h_ref, c_ref = O.cell_forward(None if xr is None else xr.double(), hr.double(), c.double(), wr.double(), b.double())
+    h2, c2 = run_cell(mode, x, h, c, w, b, cuda_device)
+    eh, ec = rel_err(h2, h_ref), rel_err(c2, c_ref)
+    assert eh < tol and ec < tol, report("h", h2, h_ref) + " | " + report("c", c2, c_ref)
+
+
+def test_kat_zero_weights_gpu(cuda_device):
+    """W=0,b=0 => c'=0.5c, h'=0.5 tanh(0.5c); c=2 -> c'=1, h'=0.380797 (SURVEY 8c KAT)."""
+    plconv, _ = _plconv()
+    ch = 16
+    w = torch.zeros(4 * ch, 8 + ch, 3, 3)
+    x = torch.randn(1, 8, 5, 5)
+    h = torch.randn(1, ch, 5, 5)
+    c = torch.full((1, ch, 5, 5), 2.0)
+    for mode, tol in ((plconv.PLC_MODE_FP32, 1e-6), (plconv.PLC_MODE_BF16_TC, 4e-3)):
+        h2, c2 = run_cell(mode, x, h, c, w, torch.zeros(4 * ch), cuda_device)
+        assert (c2 - 1.0).abs().max() < tol
+        assert (h2 - 0.380797088).abs().max() < tol
+
+
+def test_errors_are_loud(cuda_device):
+    plconv, F = _plconv()
+    dev = cuda_device
+    w = torch.zeros(4 * 16, 8 + 16, 4, 4, device=dev)
+    with pytest.raises(RuntimeError, match="odd"):
+        F.pack_weights(w, None, 8, 16, 4, plconv.PLC_MODE_BF16_TC)
+    w = torch.zeros(4 * 12, 8 + 12, 3, 3, device=dev)
+    with pytest.raises(RuntimeError, match="Ch % 16"):
+        F.pack_weights(w, None, 8, 12, 3, plconv.PLC_MODE_BF16_TC)
+    # CPU tensors are refused: there is no CPU path
+    pw = F.pack_weights(torch.zeros(64, 24, 3, 3, device=dev), None, 8, 16, 3, plconv.PLC_MODE_FP32)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        F.cell_forward(torch.zeros(1, 4, 4, 8), torch.zeros(1, 4, 4, 16), torch.zeros(1, 4, 4, 16), pw)
+
+
+# ---------------------------------------------------------------------------------------- backward
+
+def run_cell_bwd(mode, x, h, c, w, b, gh, gc, dev):
+    plconv, F = _plconv()
+    B, cin, H, W = x.shape
+    ch = h.shape[1]
+    k = w.shape[-1]
+    bf = mode == plconv.PLC_MODE_BF16_TC
+    cp = pad8(cin) if bf else cin
+    adt = torch.bfloat16 if bf else torch.float32
+    pw = F.pack_weights(w.to(dev), b.to(dev), cin, ch, k, mode, with_dgrad=True, cin_pad=cp)
+    xd, hd, cd = nhwc(x, adt, dev, cp), nhwc(h, adt, dev), nhwc(c, torch.float32, dev)
+    dh, dc = nhwc(gh, adt, dev), nhwc(gc, torch.float32, dev)
+    dW = torch.zeros(4 * ch, cp + ch, k, k, device=dev)
+    db = torch.zeros(4 * ch, device=dev)
+    dx, dhp, dcp = F.cell_backward(xd, hd, cd, pw, dh, None, dc, dW, db)
+    torch.cuda.synchronize()
+    dWc = dW.cpu()
+    dW_ref_layout = torch.cat([dWc[:, :cin], dWc[:, cp:]], dim=1)
+    return nchw(dx)[:, :cin], nchw(dhp), nchw(dcp), dW_ref_layout, db.cpu()
+
+
+@pytest.mark.parametrize("path", golden_files("cell_"), ids=os.path.basename)
+@pytest.mark.parametrize("mode_name", ["fp32", "bf16"])
+def test_backward_vs_reference_autograd_golden(path, mode_name, cuda_device):
+    plconv, _ = _plconv()
+    g = load_golden(path)
+    T = torch.from_numpy
+    mode = plconv.PLC_MODE_BF16_TC if mode_name == "bf16" else plconv.PLC_MODE_FP32
+    # fp32 mode: 1e-5 on the elementwise-dominated outputs, 5e-5 on the long fp32 reductions (dW, db: sums
+    # over B*H*W pixels in a different order than ATen's).  bf16 mode: 2e-2 (bf16 dZ operand).
+    tol = {"fp32": dict(dx=2e-5, dh_prev=2e-5, dc_prev=1e-5, dW=5e-5, db=5e-5),
+           "bf16": dict(dx=2e-2, dh_prev=2e-2, dc_prev=1e-2, dW=2e-2, db=2e-2)}[mode_name]
+    dx, dhp, dcp, dW, db = run_cell_bwd(mode, T(g["x"]), T(g["h"]), T(g["c"]), T(g["weight"]), T(g["bias"]),
+                                        T(g["gh"]), T(g["gc"]), cuda_device)
+    msgs = []
+    for name, got in (("dx", dx), ("dh_prev", dhp), ("dc_prev", dcp), ("dW", dW), ("db", db)):
+        ref = T(g[name])
+        if rel_err(got, ref) >= tol[name]:
+            msgs.append(report(name, got, ref))
+    assert not msgs, " | ".join(msgs)
