@@ -1,0 +1,227 @@
+"""Host-side mirror of the reference nn.Module API for the ConvLSTM recurrence.
+
+* :class:`ConvLSTMCell` -- drop-in for ``src/models/convlstm.py:4-28``: same constructor
+  ``(input_dim, hidden_dim, kernel_size=3, bias=True)``, same ``hidden_dim`` attribute, same
+  ``conv.weight [4Ch, Cin+Ch, k, k]`` / ``conv.bias [4Ch]`` parameters (hence ``state_dict`` keys and the
+  default-init RNG stream), same ``forward(x, h_cur, c_cur) -> (h_next, c_next)`` on logical
+  ``[B, C, H, W]`` tensors.  ``forward(x, (h, c))`` is accepted too (north_star spelling).
+  The arithmetic runs in libplc.so (no cuDNN / ATen conv, no CPU path).
+* :class:`ConvLSTMStack` -- the stacked-cell T-loop of ``src/models/generator.py:156-171`` (zero initial
+  state, layer l consumes h of layer l-1 at the same step), generalised to L layers and kept in the NHWC
+  bf16 working layout between steps.
+* :class:`EncoderForecaster` -- north_star extension with no reference counterpart (spec:
+  oracle/convlstm_oracle.py:encoder_forecaster_forward).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import functional as F
+from ._lib import PLC_MODE_BF16_TC, PLC_MODE_FP32
+
+Tensor = torch.Tensor
+
+_MODES = {"bf16": PLC_MODE_BF16_TC, "fp32": PLC_MODE_FP32}
+
+
+def _pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+class _CellStepFn(torch.autograd.Function):
+    """One cell step on working-layout (NHWC) tensors, differentiable (backward = plc_cell_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, h, c, weight, bias, cell):
+        pw = cell._packed(need_dgrad=torch.is_grad_enabled())
+        h2, c2 = F.cell_forward(x, h, c, pw)
+        ctx.cell = cell
+        ctx.pw = pw
+        ctx.has_x = x is not None
+        ctx.x_needs_grad = x is not None and x.requires_grad
+        ctx.save_for_backward(x, h, c)
+        return h2, c2
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        x, h, c = ctx.saved_tensors
+        cell, pw = ctx.cell, ctx.pw
+        if pw.dgrad is None:
+            pw = cell._packed(need_dgrad=True)
+        B, H, W, Ch = h.shape
+        if dh is None:
+            dh = torch.zeros_like(h)
+        dh = dh.contiguous()
+        dc = None if dc is None else dc.contiguous()
+        dW = torch.zeros(4 * Ch, pw.Cin + Ch, pw.k, pw.k, device=h.device, dtype=torch.float32)
+        db = torch.zeros(4 * Ch, device=h.device, dtype=torch.float32) if pw.bias is not None else None
+        dx, dh_prev, dc_prev = F.cell_backward(x if ctx.has_x else None, h, c, pw, dh, None, dc, dW, db,
+                                               need_dx=ctx.x_needs_grad)
+        cin = cell.input_dim
+        if pw.Cin != cin:  # drop the zero-padded x channels
+            dW = torch.cat([dW[:, :cin], dW[:, pw.Cin:]], dim=1)
+        gw = dW.to(cell.conv.weight.dtype)
+        gb = None if db is None else db.to(cell.conv.bias.dtype)
+        return (dx if ctx.x_needs_grad else None), dh_prev, dc_prev, gw, gb, None
+
+
+class ConvLSTMCell(nn.Module):
+    """Drop-in for the reference ``ConvLSTMCell`` (convlstm.py:4-28), computed by libplc.so.
+
+    mode: "bf16" (tcgen05 tensor cores, fp32 accumulate/state; <=1e-2 rel. vs reference) or
+          "fp32" (validation mode; <=1e-5).
+    """
+
+    def __init__(self, input_dim: int, hidden_dim: int, kernel_size: int = 3, bias: bool = True,
+                 mode: str = "bf16"):
+        super().__init__()
+        if mode not in _MODES:
+            raise ValueError(f"mode must be one of {list(_MODES)}")
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim                     # convlstm.py:7
+        self.kernel_size = kernel_size
+        self.mode = mode
+        # Parameter holder only -- identical to convlstm.py:8-14 so that state_dict keys, shapes and the
+        # default init are the reference's.  It is never *called*.
+        if input_dim + hidden_dim > 0:
+            self.conv = nn.Conv2d(input_dim + hidden_dim, 4 * hidden_dim, kernel_size,
+                                  padding=kernel_size // 2, bias=bias)
+        self._pack_cache = None
+
+    # -- packed-weight cache, invalidated when the parameters change (optimizer step, load_state_dict, .to())
+    def _packed(self, need_dgrad: bool) -> F.PackedWeights:
+        w, b = self.conv.weight, self.conv.bias
+        key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version), self.mode, str(w.device))
+        pc = self._pack_cache
+        if pc is not None and pc[0] == key and (pc[1].dgrad is not None or not need_dgrad):
+            return pc[1]
+        mode = _MODES[self.mode]
+        cin_pad = _pad8(self.input_dim) if mode == PLC_MODE_BF16_TC else self.input_dim
+        pw = F.pack_weights(w, b, self.input_dim, self.hidden_dim, self.kernel_size, mode,
+                            with_dgrad=need_dgrad, cin_pad=cin_pad)
+        self._pack_cache = (key, pw)
+        return pw
+
+    @property
+    def working_cin(self) -> int:
+        return _pad8(self.input_dim) if self.mode == "bf16" else self.input_dim
+
+    @property
+    def act_dtype(self):
+        return torch.bfloat16 if self.mode == "bf16" else torch.float32
+
+    def step_nhwc(self, x: Optional[Tensor], h: Tensor, c: Tensor) -> Tuple[Tensor, Tensor]:
+        """Working-layout step: x [B,H,W,working_cin] / h [B,H,W,Ch] in act_dtype, c fp32.  Differentiable."""
+        needs_grad = torch.is_grad_enabled() and (
+            self.conv.weight.requires_grad or h.requires_grad or c.requires_grad or (x is not None and x.requires_grad))
+        if needs_grad:
+            return _CellStepFn.apply(x, h, c, self.conv.weight, self.conv.bias, self)
+        return F.cell_forward(x, h, c, self._packed(need_dgrad=False))
+
+    def _to_working(self, t: Tensor, channels: int, dtype) -> Tensor:
+        # logical [B,C,H,W] (any strides) -> NHWC contiguous [B,H,W,C'] ; differentiable torch ops (plumbing)
+        t = t.permute(0, 2, 3, 1)
+        if channels != t.shape[-1]:
+            t = torch.nn.functional.pad(t, (0, channels - t.shape[-1]))
+        return t.to(dtype).contiguous()
+
+    def forward(self, x: Tensor, h_cur, c_cur: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        """convlstm.py:16-28.  Logical [B,C,H,W] in, ``(h_next, c_next)`` logical [B,C,H,W] out (dtype of
+        ``h_cur``, channels_last strides)."""
+        if c_cur is None:
+            h_cur, c_cur = h_cur                         # forward(x, (h, c)) spelling
+        if not h_cur.is_cuda:
+            raise RuntimeError("ConvLSTMCell (plconv) has no CPU path: move the module and inputs to a CUDA device")
+        if self.kernel_size % 2 == 0:
+            raise RuntimeError("kernel_size must be odd (the reference's padding k//2 breaks even k)")
+        out_dtype = h_cur.dtype
+        xw = self._to_working(x, self.working_cin, self.act_dtype) if self.input_dim > 0 else None
+        hw = self._to_working(h_cur, self.hidden_dim, self.act_dtype)
+        cw = self._to_working(c_cur, self.hidden_dim, torch.float32)
+        h2, c2 = self.step_nhwc(xw, hw, cw)
+        # back to the logical NCHW shape (a channels_last-strided view; no copy beyond the dtype cast)
+        return h2.to(out_dtype).permute(0, 3, 1, 2), c2.to(out_dtype).permute(0, 3, 1, 2)
+
+
+class ConvLSTMStack(nn.Module):
+    """L stacked cells run over T steps (generator.py:156-171 generalised).
+
+    ``cells[0] = ConvLSTMCell(input_dim, hidden_dims[0])``, ``cells[l] = ConvLSTMCell(hidden_dims[l-1],
+    hidden_dims[l])`` -- for ``hidden_dims=[a, b]`` and ``input_dim=a`` this is exactly the reference's
+    ``cell1``/``cell2`` wiring (generator.py:57-58).
+    """
+
+    def __init__(self, input_dim: int, hidden_dims: Sequence[int], kernel_size: int = 3, bias: bool = True,
+                 mode: str = "bf16"):
+        super().__init__()
+        self.input_dim = input_dim
+        self.hidden_dims = list(hidden_dims)
+        dims = [input_dim] + self.hidden_dims
+        self.cells = nn.ModuleList(
+            [ConvLSTMCell(dims[l], dims[l + 1], kernel_size, bias, mode) for l in range(len(self.hidden_dims))])
+        self.mode = mode
+
+    def zero_state(self, B: int, H: int, W: int, device) -> List[Tuple[Tensor, Tensor]]:
+        """generator.py:156-160: zeros, fp32 cell state (bf16 h in the working layout)."""
+        st = []
+        for cell in self.cells:
+            st.append((torch.zeros(B, H, W, cell.hidden_dim, device=device, dtype=cell.act_dtype),
+                       torch.zeros(B, H, W, cell.hidden_dim, device=device, dtype=torch.float32)))
+        return st
+
+    def run_nhwc(self, x_steps: Optional[Sequence[Tensor]], state=None, steps: Optional[int] = None):
+        """x_steps: per-step working-layout inputs [B,H,W,working_cin] (or None with ``steps`` for an
+        input-less first layer).  Returns (list of top-layer h per step, final state)."""
+        T = steps if x_steps is None else len(x_steps)
+        if state is None:
+            B, H, W, _ = x_steps[0].shape
+            state = self.zero_state(B, H, W, x_steps[0].device)
+        state = list(state)
+        outs = []
+        for t in range(T):                                # generator.py:164
+            inp = None if x_steps is None else x_steps[t]
+            for l, cell in enumerate(self.cells):         # generator.py:170-171
+                h, c = state[l]
+                h, c = cell.step_nhwc(inp, h, c)
+                state[l] = (h, c)
+                inp = h
+            outs.append(inp)
+        return outs, state
+
+    def forward(self, x_seq: Tensor, state=None):
+        """x_seq: logical [B, T, C, H, W] (fp32, reference layout).  Returns the top layer's h for every
+        step as logical [B, T, Ch_L, H, W] fp32, and the final working-layout state."""
+        if not x_seq.is_cuda:
+            raise RuntimeError("ConvLSTMStack (plconv) has no CPU path")
+        B, T, C, H, W = x_seq.shape
+        c0 = self.cells[0]
+        # one layout conversion for the whole sequence: [B,T,C,H,W] -> T x [B,H,W,C']
+        xs = x_seq.permute(1, 0, 3, 4, 2)
+        if c0.working_cin != C:
+            xs = torch.nn.functional.pad(xs, (0, c0.working_cin - C))
+        xs = xs.to(c0.act_dtype).contiguous()
+        outs, state = self.run_nhwc([xs[t] for t in range(T)], state)
+        out = torch.stack(outs, dim=1)                    # [B,T,H,W,Ch]
+        return out.to(torch.float32).permute(0, 1, 4, 2, 3), state
+
+
+class EncoderForecaster(nn.Module):
+    """Encoder-forecaster ConvLSTM (north_star extension; no reference counterpart -- parity is against
+    oracle.encoder_forecaster_forward only).  The forecaster's first layer has no input tensor."""
+
+    def __init__(self, input_dim: int, hidden_dims: Sequence[int], kernel_size: int = 3, t_out: int = 10,
+                 mode: str = "bf16"):
+        super().__init__()
+        self.t_out = t_out
+        self.encoder = ConvLSTMStack(input_dim, hidden_dims, kernel_size, True, mode)
+        self.forecaster = ConvLSTMStack(0, hidden_dims, kernel_size, True, mode)
+
+    def forward(self, x_seq: Tensor, t_out: Optional[int] = None) -> Tensor:
+        t_out = self.t_out if t_out is None else t_out
+        _, state = self.encoder(x_seq)
+        outs, _ = self.forecaster.run_nhwc(None, state, steps=t_out)
+        out = torch.stack(outs, dim=1)
+        return out.to(torch.float32).permute(0, 1, 4, 2, 3)
