@@ -114,6 +114,18 @@ int plc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C_src, int
                               void* stream);
 int plc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int C, int H, int W, void* stream);
 
+/* ---- frame front-end / head (either side of the recurrence; SURVEY.md section 8f "next-1") -------
+ * plc_frontend_fwd replaces generator.py:166-168 + coordconv.py:3-10 per step:
+ *     x_t = relu(init_conv(add_coord_channels(frame_t)))
+ *   frames [N, Cf, H, W] fp32 NCHW (N = B or B*T); w_oihw = init_conv.weight [C, Cf+2, 3, 3]; bias [C] or NULL
+ *   out    [N, H, W, C_stride] NHWC, channels [0,C) written (bf16 in PLC_MODE_BF16_TC, fp32 in PLC_MODE_FP32)
+ * plc_head_fwd: 1x1 conv C -> 1 on the top layer's h (encoder-forecaster output head, repo-defined):
+ *   h [npix, C] NHWC (mode dtype), w [C] fp32, bias [1] or NULL, out [npix] fp32.                   */
+int plc_frontend_fwd(const float* frames, int N, int Cf, int H, int W, const float* w_oihw, const float* bias, int C,
+                     int C_stride, int mode, void* out, void* stream);
+int plc_head_fwd(const void* h, long npix, int C, const float* w, const float* bias, int mode, float* out,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

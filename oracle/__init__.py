@@ -20,4 +20,7 @@ from .convlstm_oracle import (  # noqa: F401
     stack_backward,
     encoder_forecaster_forward,
     conv2d_same,
+    add_coord_channels,
+    frontend_forward,
+    nowcast_forward,
 )

@@ -199,3 +199,26 @@ def encoder_forecaster_forward(x_seq: Tensor, enc_w, enc_b, fc_w, fc_b, t_out: i
     _, state = stack_forward(x_seq, enc_w, enc_b)
     out, state = stack_forward(None, fc_w, fc_b, state=state, steps=t_out)
     return out, state
+
+
+def add_coord_channels(x: Tensor) -> Tensor:
+    """coordconv.py:3-10: append row / col ``linspace(0, 1)`` channels."""
+    b, _, hh, ww = x.shape
+    row = torch.linspace(0, 1, hh, dtype=x.dtype).view(1, 1, hh, 1).repeat(b, 1, 1, ww)
+    col = torch.linspace(0, 1, ww, dtype=x.dtype).view(1, 1, 1, ww).repeat(b, 1, hh, 1)
+    return torch.cat([x, row, col], dim=1)
+
+
+def frontend_forward(frame: Tensor, w_init: Tensor, b_init: Optional[Tensor]) -> Tensor:
+    """generator.py:166-168: ``x_t = relu(init_conv(add_coord_channels(frame_t)))``."""
+    return F.relu(F.conv2d(add_coord_channels(frame), w_init, b_init, padding=1))
+
+
+def nowcast_forward(frames: Tensor, w_init, b_init, enc_w, enc_b, fc_w, fc_b, w_head, b_head, t_out: int) -> Tensor:
+    """Encoder-forecaster generator (repo-defined spec, see :func:`encoder_forecaster_forward`):
+    frames [B,T_in,Cf,H,W] -> front-end per step -> encoder -> forecaster -> 1x1 head -> [B,T_out,1,H,W]."""
+    b, t_in = frames.shape[:2]
+    feats = torch.stack([frontend_forward(frames[:, t], w_init, b_init) for t in range(t_in)], dim=1)
+    h_top, _ = encoder_forecaster_forward(feats, enc_w, enc_b, fc_w, fc_b, t_out)
+    outs = [F.conv2d(h_top[:, t], w_head, b_head) for t in range(t_out)]
+    return torch.stack(outs, dim=1)

@@ -37,6 +37,8 @@ SIGNATURES = {
     "plc_cell_bwd": (_int, [_dp] + [_vp] * 15 + [_sz, _vp]),
     "plc_nchw_f32_to_nhwc_bf16": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),
     "plc_nhwc_bf16_to_nchw_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
+    "plc_frontend_fwd": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _int, _int, _int, _vp, _vp]),
+    "plc_head_fwd": (_int, [_vp, ctypes.c_long, _int, _vp, _vp, _int, _vp, _vp]),
 }
 
 _lock = threading.Lock()

@@ -13,6 +13,7 @@
 #include "../../include/plc.h"
 #include "conv_igemm_tc.cuh"
 #include "conv_simt.cuh"
+#include "frame_io.cuh"
 #include "wgrad_tc.cuh"
 
 namespace {
@@ -552,6 +553,48 @@ int plc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int C, int H, 
   dim3 grid(cdiv(H * W, 32), cdiv(C, 32), B), block(32, 8);
   nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(src), dst, C, H * W);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+int plc_frontend_fwd(const float* frames, int N, int Cf, int H, int W, const float* w_oihw, const float* bias, int C,
+                     int C_stride, int mode, void* out, void* stream) {
+  if (!frames || !w_oihw || !out) return fail(PLC_ERR_NULL_ARG, "plc_frontend_fwd: null pointer");
+  if (N <= 0 || Cf <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || C > 256 || C_stride < C || C_stride % 8)
+    return fail(PLC_ERR_BAD_DESC, "plc_frontend_fwd: need C %% 8 == 0, C <= 256, C_stride >= C (got C=%d stride=%d)", C,
+                C_stride);
+  if (H > 65535 || N > 65535) return fail(PLC_ERR_UNSUPPORTED, "plc_frontend_fwd: H and N must be <= 65535");
+  if (!aligned16(out)) return fail(PLC_ERR_ALIGNMENT, "plc_frontend_fwd: out must be 16-byte aligned");
+  dim3 grid(cdiv(W, 32), H, N), block(32, C / 8);
+  const size_t smem = (static_cast<size_t>(Cf + 2) * 9 * C + C) * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == PLC_MODE_BF16_TC) {
+    PLC_CUDA(cudaFuncSetAttribute(plc::frontend_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    plc::frontend_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(frames, w_oihw, bias, static_cast<__nv_bfloat16*>(out),
+                                                                  Cf, H, W, C, C_stride);
+  } else {
+    PLC_CUDA(cudaFuncSetAttribute(plc::frontend_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    plc::frontend_kernel<float><<<grid, block, smem, st>>>(frames, w_oihw, bias, static_cast<float*>(out), Cf, H, W, C,
+                                                          C_stride);
+  }
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+int plc_head_fwd(const void* h, long npix, int C, const float* w, const float* bias, int mode, float* out,
+                 void* stream) {
+  if (!h || !w || !out) return fail(PLC_ERR_NULL_ARG, "plc_head_fwd: null pointer");
+  if (npix <= 0 || C <= 0 || C % 8) return fail(PLC_ERR_BAD_DESC, "plc_head_fwd: need C %% 8 == 0");
+  if (!aligned16(h)) return fail(PLC_ERR_ALIGNMENT, "plc_head_fwd: h must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((npix + threads - 1) / threads);
+  if (mode == PLC_MODE_BF16_TC)
+    plc::head_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(h), w, bias, out,
+                                                               (size_t)npix, C);
+  else
+    plc::head_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(h), w, bias, out, (size_t)npix, C);
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;
 }

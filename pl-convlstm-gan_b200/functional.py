@@ -171,3 +171,39 @@ def nhwc_to_nchw(src: Tensor) -> Tensor:
     _lib.check(lib.plc_nhwc_bf16_to_nchw_f32(_ptr(src.contiguous()), _ptr(out), B, C, H, W, _stream()),
                "plc_nhwc_bf16_to_nchw_f32")
     return out
+
+
+def frontend_forward(frames: Tensor, weight: Tensor, bias: Optional[Tensor], mode: int,
+                     c_stride: Optional[int] = None, out: Optional[Tensor] = None) -> Tensor:
+    """relu(init_conv(add_coord_channels(frames))) (generator.py:166-168): frames [N,Cf,H,W] fp32 ->
+    features [N,H,W,c_stride] in the working layout (channels >= C untouched / zero)."""
+    lib = _lib.load()
+    N, Cf, H, W = frames.shape
+    C = weight.shape[0]
+    assert tuple(weight.shape) == (C, Cf + 2, 3, 3), tuple(weight.shape)
+    cs = C if c_stride is None else c_stride
+    _require_cuda(frames, "frames")
+    if frames.dtype != torch.float32:
+        raise RuntimeError("frames must be float32")
+    if out is None:
+        out = (torch.zeros if cs != C else torch.empty)(N, H, W, cs, dtype=_act_dtype(mode), device=frames.device)
+    w = weight.detach().to(torch.float32).contiguous()
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    _lib.check(lib.plc_frontend_fwd(_ptr(frames), N, Cf, H, W, _ptr(w), _ptr(b), C, cs, mode, _ptr(out), _stream()),
+               "plc_frontend_fwd")
+    return out
+
+
+def head_forward(h: Tensor, weight: Tensor, bias: Optional[Tensor], mode: int, out: Optional[Tensor] = None) -> Tensor:
+    """1x1 conv C -> 1 over working-layout h [..., C]; returns fp32 [...] (one value per pixel)."""
+    lib = _lib.load()
+    C = h.shape[-1]
+    npix = h.numel() // C
+    _require_cuda(h, "h")
+    w = weight.detach().to(torch.float32).reshape(-1).contiguous()
+    assert w.numel() == C
+    b = None if bias is None else bias.detach().to(torch.float32).reshape(-1).contiguous()
+    if out is None:
+        out = torch.empty(h.shape[:-1], dtype=torch.float32, device=h.device)
+    _lib.check(lib.plc_head_fwd(_ptr(h), npix, C, _ptr(w), _ptr(b), mode, _ptr(out), _stream()), "plc_head_fwd")
+    return out

@@ -1,0 +1,111 @@
+"""Preallocated inference rollout of the encoder-forecaster generator (BASELINE.json configs[1]).
+
+frames [B,T_in,Cf,H,W] fp32 -> front-end conv (generator.py:166-168) -> encoder ConvLSTM stack over T_in
+steps (generator.py:156-171 wiring) -> forecaster stack over T_out steps (input-less first layer) -> 1x1 head ->
+frames [T_out,B,H,W] fp32.  All state lives in buffers allocated once; one cell step = one kernel launch.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import functional as F
+from .nn import ConvLSTMStack, _MODES
+
+Tensor = torch.Tensor
+
+
+class NowcastGenerator(nn.Module):
+    """Encoder-forecaster generator (north_star extension; parity vs the repo's own eager spec in the tests,
+    not vs the reference, which has no such model).
+
+    Parameter names follow the reference where a counterpart exists: ``init_conv`` (generator.py:50-55),
+    ``encoder.cells[l].conv`` / ``forecaster.cells[l].conv`` (ConvLSTMCell.conv)."""
+
+    def __init__(self, in_channels: int = 1, hidden_dims: Sequence[int] = (64, 64), kernel_size: int = 3,
+                 t_in: int = 10, t_out: int = 10, mode: str = "bf16"):
+        super().__init__()
+        self.in_channels, self.hidden_dims = in_channels, list(hidden_dims)
+        self.t_in, self.t_out, self.mode = t_in, t_out, mode
+        hd0 = self.hidden_dims[0]
+        self.init_conv = nn.Conv2d(in_channels + 2, hd0, 3, padding=1)      # parameter holder
+        self.encoder = ConvLSTMStack(hd0, self.hidden_dims, kernel_size, True, mode)
+        self.forecaster = ConvLSTMStack(0, self.hidden_dims, kernel_size, True, mode)
+        self.head = nn.Conv2d(self.hidden_dims[-1], 1, 1)                   # parameter holder
+
+    def cell_flops_per_sequence(self, H: int, W: int) -> float:
+        """Algorithmic FLOPs (2*M*N*K of every gate conv) for ONE sequence through encoder + forecaster."""
+        tot = 0.0
+        for stack, steps in ((self.encoder, self.t_in), (self.forecaster, self.t_out)):
+            for cell in stack.cells:
+                k = cell.kernel_size
+                tot += steps * 2.0 * H * W * (cell.input_dim + cell.hidden_dim) * k * k * 4 * cell.hidden_dim
+        return tot
+
+
+class NowcastRunner:
+    """Inference engine for :class:`NowcastGenerator` with every buffer preallocated."""
+
+    def __init__(self, model: NowcastGenerator, B: int, H: int, W: int, device):
+        self.m, self.B, self.H, self.W, self.dev = model, B, H, W, device
+        self.mode = _MODES[model.mode]
+        adt = torch.bfloat16 if model.mode == "bf16" else torch.float32
+        hd = model.hidden_dims
+        L = len(hd)
+        self.feat = torch.zeros(model.t_in * B, H, W, model.encoder.cells[0].working_cin, dtype=adt, device=device)
+        # per layer: two h buffers (ping-pong; halo reads forbid in-place) and one c buffer (in-place is safe)
+        self.h = [[torch.zeros(B, H, W, hd[l], dtype=adt, device=device) for _ in range(2)] for l in range(L)]
+        self.c = [torch.zeros(B, H, W, hd[l], dtype=torch.float32, device=device) for l in range(L)]
+        self.h_top = torch.zeros(model.t_out, B, H, W, hd[-1], dtype=adt, device=device)
+        self.out = torch.zeros(model.t_out, B, H, W, dtype=torch.float32, device=device)
+        self.enc_pw = [c._packed(False) for c in model.encoder.cells]
+        self.fc_pw = [c._packed(False) for c in model.forecaster.cells]
+        self.cell_launches_per_run = L * (model.t_in + model.t_out)
+        self.launches_per_run = 1 + self.cell_launches_per_run + 1
+
+    def _cell(self, pw, x, h_prev, c, h_out, events):
+        if events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        F.cell_forward(x, h_prev, c, pw, h_out=h_out, c_out=c)
+        if events is not None:
+            e1.record()
+            events.append((e0, e1, pw))
+
+    @torch.no_grad()
+    def run(self, frames: Tensor, events: Optional[List] = None) -> Tensor:
+        """frames [B,T_in,Cf,H,W] fp32 on device.  Returns predicted frames [T_out,B,H,W] fp32 (device buffer).
+        ``events``: optional list collecting (start_event, end_event, packed_weights) per cell launch."""
+        m, B, L = self.m, self.B, len(self.c)
+        T_in, T_out = m.t_in, m.t_out
+        # [B,T,Cf,H,W] -> [T*B,Cf,H,W]: front-end for all steps in one launch
+        fr = frames.transpose(0, 1).reshape(T_in * B, m.in_channels, self.H, self.W).contiguous()
+        F.frontend_forward(fr, m.init_conv.weight, m.init_conv.bias, self.mode, c_stride=self.feat.shape[-1],
+                           out=self.feat)
+        for l in range(L):                                   # generator.py:156-160: zero initial state
+            self.h[l][0].zero_()
+            self.c[l].zero_()
+        cur = [0] * L
+        for t in range(T_in):                                # generator.py:164
+            x = self.feat[t * B:(t + 1) * B]
+            for l in range(L):                               # generator.py:170-171
+                dst = self.h[l][cur[l] ^ 1]
+                self._cell(self.enc_pw[l], x, self.h[l][cur[l]], self.c[l], dst, events)
+                cur[l] ^= 1
+                x = dst
+        for t in range(T_out):
+            x = None                                         # forecaster layer 0 has no input tensor
+            for l in range(L):
+                if l == L - 1:                               # top layer writes straight into the output ring
+                    src = self.h[l][cur[l]] if t == 0 else self.h_top[t - 1]
+                    dst = self.h_top[t]
+                    self._cell(self.fc_pw[l], x, src, self.c[l], dst, events)
+                else:
+                    dst = self.h[l][cur[l] ^ 1]
+                    self._cell(self.fc_pw[l], x, self.h[l][cur[l]], self.c[l], dst, events)
+                    cur[l] ^= 1
+                x = dst
+        F.head_forward(self.h_top, m.head.weight, m.head.bias, self.mode, out=self.out)
+        return self.out

@@ -1,0 +1,105 @@
+"""GPU parity of multi-step rollouts: the stacked T-loop (generator.py:156-171) against the reference golden
+rollouts and the oracle; the encoder-forecaster generator against the repo-defined eager spec."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files, load_golden
+from oracle import convlstm_oracle as O
+from test_cell_gpu import rel_err, report
+
+pytestmark = pytest.mark.gpu
+
+
+def _build_stack(plconv, g, mode, dev):
+    hd0, hd1 = g["w1"].shape[0] // 4, g["w2"].shape[0] // 4
+    st = plconv.ConvLSTMStack(hd0, [hd0, hd1], 3, True, mode).to(dev)
+    with torch.no_grad():
+        st.cells[0].conv.weight.copy_(torch.from_numpy(g["w1"]))
+        st.cells[0].conv.bias.copy_(torch.from_numpy(g["b1"]))
+        st.cells[1].conv.weight.copy_(torch.from_numpy(g["w2"]))
+        st.cells[1].conv.bias.copy_(torch.from_numpy(g["b2"]))
+    return st
+
+
+@pytest.mark.parametrize("path", golden_files("rollout_"), ids=os.path.basename)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_stack_rollout_every_step_vs_reference_golden(path, mode, cuda_device):
+    """Every step's top-layer h against the reference's 2-cell T-loop (goldens from the unmodified reference)."""
+    import plconv
+    g = load_golden(path)
+    st = _build_stack(plconv, g, mode, cuda_device)
+    with torch.no_grad():
+        out, _ = st(torch.from_numpy(g["x_seq"]).to(cuda_device))
+    tol = 1e-5 if mode == "fp32" else 1e-2
+    ref = torch.from_numpy(g["h2"])
+    for t in range(ref.shape[1]):
+        assert rel_err(out[:, t], ref[:, t]) < tol, f"t={t} " + report("h2", out[:, t], ref[:, t])
+
+
+@pytest.mark.parametrize("path", golden_files("rollout_"), ids=os.path.basename)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_stack_bptt_vs_reference_autograd_golden(path, mode, cuda_device):
+    """Full BPTT (autograd over plc_cell_bwd) against the reference's autograd: dx for every step, dW/db."""
+    import plconv
+    g = load_golden(path)
+    st = _build_stack(plconv, g, mode, cuda_device)
+    x = torch.from_numpy(g["x_seq"]).to(cuda_device).requires_grad_()
+    out, _ = st(x)
+    (out * torch.from_numpy(g["d_out"]).to(cuda_device)).sum().backward()
+    tol = 1e-4 if mode == "fp32" else 3e-2   # T-step accumulation of bf16 dZ / dh operands
+    got = {"dx_seq": x.grad, "dW1": st.cells[0].conv.weight.grad, "db1": st.cells[0].conv.bias.grad,
+           "dW2": st.cells[1].conv.weight.grad, "db2": st.cells[1].conv.bias.grad}
+    bad = [report(k, v, torch.from_numpy(g[k])) for k, v in got.items() if rel_err(v, torch.from_numpy(g[k])) >= tol]
+    assert not bad, " | ".join(bad)
+
+
+def test_dropin_cell_module_matches_reference_api(cuda_device):
+    """ConvLSTMCell keeps the reference surface: ctor, hidden_dim, conv.weight/bias keys, forward(x,h,c)->(h,c),
+    and the forward(x,(h,c)) spelling; NCHW fp32 in, NCHW-shaped out."""
+    import plconv
+    g = load_golden(golden_files("cell_b2_c16_h32")[0])
+    cell = plconv.ConvLSTMCell(16, 32, kernel_size=3, bias=True, mode="fp32").to(cuda_device)
+    assert cell.hidden_dim == 32
+    assert sorted(cell.state_dict().keys()) == ["conv.bias", "conv.weight"]
+    assert tuple(cell.conv.weight.shape) == (128, 48, 3, 3)
+    cell.load_state_dict({"conv.weight": torch.from_numpy(g["weight"]), "conv.bias": torch.from_numpy(g["bias"])})
+    x, h, c = (torch.from_numpy(g[k]).to(cuda_device) for k in ("x", "h", "c"))
+    h2, c2 = cell(x, h, c)
+    assert h2.shape == h.shape and c2.shape == c.shape and h2.dtype == torch.float32
+    assert rel_err(h2, torch.from_numpy(g["h_next"])) < 1e-5 and rel_err(c2, torch.from_numpy(g["c_next"])) < 1e-5
+    h3, c3 = cell(x, (h, c))
+    assert torch.equal(h3, h2) and torch.equal(c3, c2)
+    # packed-weight cache must follow parameter updates (optimizer step / load_state_dict)
+    with torch.no_grad():
+        cell.conv.weight.mul_(0.0)
+        cell.conv.bias.mul_(0.0)
+    h4, c4 = cell(x, h, c)
+    assert rel_err(c4, 0.5 * c) < 1e-6
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_nowcast_generator_vs_eager_spec(mode, cuda_device):
+    """Encoder-forecaster generator (repo-defined spec; NOT a reference model): frames in -> frames out."""
+    import plconv
+    torch.manual_seed(5)
+    B, T_in, T_out, H, W, hd = 2, 3, 4, 12, 20, [16, 32]
+    model = plconv.NowcastGenerator(1, hd, 3, T_in, T_out, mode).to(cuda_device)
+    frames = torch.rand(B, T_in, 1, H, W)
+    runner = plconv.NowcastRunner(model, B, H, W, cuda_device)
+    out = runner.run(frames.to(cuda_device)).cpu()             # [T_out,B,H,W]
+    sd = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    enc_w = [sd[f"encoder.cells.{l}.conv.weight"] for l in range(2)]
+    enc_b = [sd[f"encoder.cells.{l}.conv.bias"] for l in range(2)]
+    fc_w = [sd[f"forecaster.cells.{l}.conv.weight"] for l in range(2)]
+    fc_b = [sd[f"forecaster.cells.{l}.conv.bias"] for l in range(2)]
+    ref = O.nowcast_forward(frames.double(), sd["init_conv.weight"], sd["init_conv.bias"], enc_w, enc_b, fc_w, fc_b,
+                            sd["head.weight"], sd["head.bias"], T_out)       # [B,T_out,1,H,W]
+    ref = ref[:, :, 0].transpose(0, 1)
+    tol = 2e-5 if mode == "fp32" else 2e-2
+    assert rel_err(out, ref) < tol, report("frames", out, ref)
+    # running twice from the same input is idempotent (state is re-zeroed: generator.py:156-160)
+    out2 = runner.run(frames.to(cuda_device)).cpu()
+    assert torch.equal(out, out2)
