@@ -132,10 +132,10 @@ int pick_ch_tile(int Ch) {
   return 16;
 }
 
-void pick_spatial_tile(int H, int W, TcGeom* g) {
+void pick_spatial_tile(int H, int W, TcGeom* g, int pixels_log2 = 7) {
   long best = -1;
-  for (int l2 = 7; l2 >= 0; --l2) {
-    const int tw = 1 << l2, th = 128 >> l2;
+  for (int l2 = pixels_log2; l2 >= 0; --l2) {
+    const int tw = 1 << l2, th = (1 << pixels_log2) >> l2;
     const long area = (long)cdiv(W, tw) * tw * cdiv(H, th) * th;
     if (best < 0 || area < best) {
       best = area;
@@ -290,6 +290,55 @@ int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p) {
   p->chunks0 = cdiv(d->Cin, 64);
   p->chunks1 = cdiv(d->Ch, 64);
   p->num_kb = d->k * d->k * (p->chunks0 + p->chunks1);
+  return PLC_OK;
+}
+
+// wgrad on the tensor cores + bias-gradient column sum (bf16 mode)
+int launch_wgrad_tc(const PlcCellDesc* d, const void* x, const void* h_prev, const void* dz, float* dW, float* db,
+                    cudaStream_t st) {
+  int rc;
+  TcGeom g;
+  pick_spatial_tile(d->H, d->W, &g, 6);   // 64-pixel blocks
+  plc::WgradTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B; p.H = d->H; p.W = d->W;
+  p.ksize = d->k; p.pad = d->k / 2;
+  p.tw = g.tw; p.th = g.th; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y;
+  p.PB = d->B * g.tiles_x * g.tiles_y;
+  p.chunks0 = cdiv(d->Cin, 64); p.chunks1 = cdiv(d->Ch, 64);
+  p.CB = d->k * d->k * (p.chunks0 + p.chunks1);
+  p.num_groups = cdiv(p.CB, plc::kWgMaxGB);
+  p.GB = cdiv(p.CB, p.num_groups);
+  p.n_tiles = cdiv(4 * d->Ch, 128);
+  const int tiles = p.n_tiles * p.num_groups;
+  int S = sm_count() / tiles;
+  if (S < 1) S = 1;
+  if (S > p.PB) S = p.PB;
+  p.S = S;
+  p.C0 = d->Cin; p.C1 = d->Ch; p.N4 = 4 * d->Ch; p.Ctot = d->Cin + d->Ch;
+  p.dW = dW;
+  CUtensorMap tz, t0, t1;
+  if ((rc = make_tmap_act(&tz, dz, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th))) return rc;
+  if ((rc = make_tmap_act(&t1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th))) return rc;
+  if (d->Cin > 0) {
+    if ((rc = make_tmap_act(&t0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th))) return rc;
+  } else {
+    t0 = t1;
+  }
+  PLC_CUDA(cudaFuncSetAttribute(plc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plc::kWgSmemBytes));
+  plc::wgrad_tc_kernel<<<tiles * S, 256, plc::kWgSmemBytes, st>>>(p, tz, t0, t1);
+  PLC_CUDA(cudaGetLastError());
+  if (db) {
+    const int M = d->B * d->H * d->W, N4 = 4 * d->Ch, pairs = N4 / 2;
+    const int rstep = pairs >= 256 ? 1 : 256 / pairs;
+    const int threads = pairs * rstep;
+    int blocks = sm_count() * 4;
+    int rpb = cdiv(M, blocks);
+    if (rpb < 64) rpb = 64;
+    blocks = cdiv(M, rpb);
+    plc::colsum_bf16_kernel<<<blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(dz), db, M, N4, rpb);
+    PLC_CUDA(cudaGetLastError());
+  }
   return PLC_OK;
 }
 
@@ -530,8 +579,7 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
 
   // 3) wgrad + bias grad
   if (dW_acc) {
-    if ((rc = plc::launch_wgrad_tc(d, x, h_prev, workspace, dW_acc, d->has_bias ? db_acc : nullptr, sm_count(), st)))
-      return fail(rc, "wgrad launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if ((rc = launch_wgrad_tc(d, x, h_prev, workspace, dW_acc, d->has_bias ? db_acc : nullptr, st))) return rc;
   }
   return PLC_OK;
 }
@@ -565,7 +613,8 @@ int plc_frontend_fwd(const float* frames, int N, int Cf, int H, int W, const flo
                 C_stride);
   if (H > 65535 || N > 65535) return fail(PLC_ERR_UNSUPPORTED, "plc_frontend_fwd: H and N must be <= 65535");
   if (!aligned16(out)) return fail(PLC_ERR_ALIGNMENT, "plc_frontend_fwd: out must be 16-byte aligned");
-  dim3 grid(cdiv(W, 32), H, N), block(32, C / 8);
+  const int G = C / 8, P = G >= 256 ? 1 : 256 / G;
+  dim3 grid(cdiv(W, P), H, N), block(G, P);
   const size_t smem = (static_cast<size_t>(Cf + 2) * 9 * C + C) * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mode == PLC_MODE_BF16_TC) {
@@ -590,10 +639,20 @@ int plc_head_fwd(const void* h, long npix, int C, const float* w, const float* b
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((npix + threads - 1) / threads);
-  if (mode == PLC_MODE_BF16_TC)
-    plc::head_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(h), w, bias, out,
-                                                               (size_t)npix, C);
-  else
+  if (mode == PLC_MODE_BF16_TC) {
+    const __nv_bfloat16* hb = static_cast<const __nv_bfloat16*>(h);
+    const int G = C / 8;
+    const unsigned cb = static_cast<unsigned>(((size_t)npix * G + threads - 1) / threads);
+    switch (G) {
+      case 1: plc::head_kernel_bf16_coalesced<1><<<cb, threads, 0, st>>>(hb, w, bias, out, (size_t)npix); break;
+      case 2: plc::head_kernel_bf16_coalesced<2><<<cb, threads, 0, st>>>(hb, w, bias, out, (size_t)npix); break;
+      case 4: plc::head_kernel_bf16_coalesced<4><<<cb, threads, 0, st>>>(hb, w, bias, out, (size_t)npix); break;
+      case 8: plc::head_kernel_bf16_coalesced<8><<<cb, threads, 0, st>>>(hb, w, bias, out, (size_t)npix); break;
+      case 16: plc::head_kernel_bf16_coalesced<16><<<cb, threads, 0, st>>>(hb, w, bias, out, (size_t)npix); break;
+      case 32: plc::head_kernel_bf16_coalesced<32><<<cb, threads, 0, st>>>(hb, w, bias, out, (size_t)npix); break;
+      default: plc::head_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(hb, w, bias, out, (size_t)npix, C);
+    }
+  } else
     plc::head_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(h), w, bias, out, (size_t)npix, C);
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;

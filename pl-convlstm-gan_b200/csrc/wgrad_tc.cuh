@@ -1,30 +1,199 @@
-// Weight-gradient reduction for the bf16 mode:
-//   dW[o][i][ky][kx] += sum_pixels dZ[pix][o] * cat(x,h)[pix + (ky-pad, kx-pad)][i]      
+// Weight-gradient reduction on the tensor cores (bf16 mode):
+//   dW[n][i][ky][kx] += sum_pixels dZ[pix][n] * cat(x,h)[pix + (ky-pad, kx-pad)][i]        
 // accumulated in fp32 straight into the reference OIHW layout (`conv.weight.grad`).
+//
+// As a GEMM the reduction dimension is the PIXEL index, and both operands live in HBM pixel-major with
+// channels contiguous (NHWC) -- i.e. they are "MN-major" UMMA operands.  No transpose is materialised:
+//   A' = dZ^T   [M' = 128 gate-channels n, K' = 64 pixels]  <- TMA box [64 n, tw, th] of dZ      (x2 chunks)
+//   B' = src^T  [N' = 64*GB channels (tap,c), K' = 64 pixels] <- TMA box [64 c, tw, th] of x or h, SHIFTED by
+//        the tap offset; out-of-bounds pixels are zero-filled by TMA = the conv's zero padding.
+//   D  [128 x 64*GB] fp32 stays in TMEM while the CTA streams its share of the pixel blocks, then is
+//   red.add'ed into dW.  Output tiles (n_tile, column group) x S pixel-splits fill the SMs.
 #pragma once
 #include "../../include/plc.h"
-#include "conv_simt.cuh"
+#include "plc_ptx.cuh"
 
 namespace plc {
 
-inline int launch_wgrad_tc(const PlcCellDesc* d, const void* x, const void* h_prev, const void* dz, float* dW,
-                           float* db, int num_sms, cudaStream_t st) {
-  const int M = d->B * d->H * d->W;
-  WgradParams w;
-  memset(&w, 0, sizeof(w));
-  w.B = d->B; w.H = d->H; w.W = d->W; w.M = M;
-  w.ksize = d->k; w.pad = d->k / 2;
-  w.C0 = d->Cin; w.C1 = d->Ch; w.K = d->k * d->k * (d->Cin + d->Ch); w.N = 4 * d->Ch;
-  w.src0 = x; w.src1 = h_prev; w.dz = dz; w.dW = dW; w.db = db;
-  const int tiles = ((w.N + SBN - 1) / SBN) * ((w.K + SBM - 1) / SBM);
-  int splits = (num_sms * 4 + tiles - 1) / tiles;
-  if (splits < 1) splits = 1;
-  int ppb = (((M + splits - 1) / splits + SBK - 1) / SBK) * SBK;
-  if (ppb < SBK) ppb = SBK;
-  w.pix_per_block = ppb;
-  dim3 grid((w.N + SBN - 1) / SBN, (w.K + SBM - 1) / SBM, (M + ppb - 1) / ppb);
-  wgrad_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w);
-  return cudaGetLastError() == cudaSuccess ? PLC_OK : PLC_ERR_CUDA;
+struct WgradTcParams {
+  int B, H, W;
+  int ksize, pad;
+  int tw, th;                 // pixel block = th x tw = 64 pixels
+  int tiles_x, tiles_y, PB;   // PB = B*tiles_y*tiles_x pixel blocks
+  int chunks0, chunks1;       // 64-channel chunks of src0 (x) / src1 (h)
+  int CB, GB, num_groups;     // column blocks (src,tap,chunk); blocks per CTA; groups
+  int n_tiles, S;             // 128-row tiles of n = 4Ch; pixel splits
+  int C0, C1, N4, Ctot;       // true channel counts
+  float* dW;                  // [N4][Ctot][k][k]
+};
+
+constexpr int kWgPix = 64;                         // pixels per stage (UMMA K' = 4 x 16)
+constexpr int kWgBoxBytes = kWgPix * 128;          // one [64 px][64 ch] bf16 box = 8 KB
+constexpr int kWgMaxGB = 6;                        // N' <= 384 columns
+constexpr int kWgStageBytes = (2 + kWgMaxGB) * kWgBoxBytes;   // 64 KB
+constexpr int kWgStages = 3;
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 256 + 1024;
+constexpr int kWgTmemCols = 512;
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  // MN-major SWIZZLE_128B canonical layout ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units:
+  // 8 K-rows of 128 B per group (SBO = 1024 B), 64-element MN chunks LBO bytes apart.
+  return make_smem_desc(smem_addr, lbo_bytes, 1024);
+}
+
+__global__ void __launch_bounds__(256, 1)
+wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_dz,
+                const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kWgStages;
+  uint64_t* acc_bar = bars + 2 * kWgStages;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // job decomposition
+  int job = blockIdx.x;
+  const int s = job % p.S; job /= p.S;
+  const int group = job % p.num_groups;
+  const int n_tile = job / p.num_groups;
+  const int cb0 = group * p.GB;
+  const int nblk = min(p.GB, p.CB - cb0);     // column blocks of this CTA
+  const int kk = p.ksize * p.ksize;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_dz);
+    tma_prefetch_desc(&tmap_a0);
+    tma_prefetch_desc(&tmap_a1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_ptr_s, kWgTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const int my_blocks = (p.PB - s + p.S - 1) / p.S;   // pixel blocks s, s+S, ...
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================================== TMA producer
+    uint32_t stage = 0, phase = 0;
+    const uint32_t bytes = (2 + nblk) * kWgBoxBytes;
+    for (int i = 0; i < my_blocks; ++i) {
+      const int pb = s + i * p.S;
+      const int tx = pb % p.tiles_x;
+      const int r = pb / p.tiles_x;
+      const int ty = r % p.tiles_y;
+      const int b = r / p.tiles_y;
+      const int x0 = tx * p.tw, y0 = ty * p.th;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      mbar_arrive_expect_tx(&full_bar[stage], bytes);
+      uint8_t* st = smem + stage * kWgStageBytes;
+      tma_load_4d(st, &tmap_dz, &full_bar[stage], n_tile * 128, x0, y0, b);
+      tma_load_4d(st + kWgBoxBytes, &tmap_dz, &full_bar[stage], n_tile * 128 + 64, x0, y0, b);
+      for (int j = 0; j < nblk; ++j) {
+        int cb = cb0 + j;
+        const CUtensorMap* tm;
+        int tap, ck;
+        if (cb < kk * p.chunks0) { tm = &tmap_a0; tap = cb / p.chunks0; ck = cb % p.chunks0; }
+        else { cb -= kk * p.chunks0; tm = &tmap_a1; tap = cb / p.chunks1; ck = cb % p.chunks1; }
+        const int dy = tap / p.ksize - p.pad, dx = tap % p.ksize - p.pad;
+        tma_load_4d(st + (2 + j) * kWgBoxBytes, tm, &full_bar[stage], ck * 64, x0 + dx, y0 + dy, b);
+      }
+      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================================== MMA issuer
+    const int n_a = nblk < 4 ? nblk : 4;      // columns [0, 64*n_a)
+    const int n_b = nblk - n_a;               // columns [256, 256 + 64*n_b)
+    const uint32_t idesc_a = make_idesc_bf16(128, 64 * n_a, 1, 1);
+    const uint32_t idesc_b = make_idesc_bf16(128, 64 * (n_b > 0 ? n_b : 1), 1, 1);
+    uint32_t stage = 0, phase = 0;
+    for (int i = 0; i < my_blocks; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + stage * kWgStageBytes);
+#pragma unroll
+      for (int ks = 0; ks < kWgPix / 16; ++ks) {
+        // 16 pixels (K') = two 8-row groups = 2048 bytes further down every 64-channel chunk
+        const uint64_t adesc = make_smem_desc_mn(st + ks * 2048, kWgBoxBytes);
+        const uint64_t bdesc0 = make_smem_desc_mn(st + 2 * kWgBoxBytes + ks * 2048, kWgBoxBytes);
+        umma_bf16<1>(tmem_base, adesc, bdesc0, idesc_a, (i | ks) != 0);
+        if (n_b > 0) {
+          const uint64_t bdesc1 = make_smem_desc_mn(st + 6 * kWgBoxBytes + ks * 2048, kWgBoxBytes);
+          umma_bf16<1>(tmem_base + 256, adesc, bdesc1, idesc_b, (i | ks) != 0);
+        }
+      }
+      umma_commit<1>(&empty_bar[stage]);
+      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+    }
+    umma_commit<1>(acc_bar);
+  } else if (warp >= 4 && my_blocks > 0) {
+    // ===================================================================== epilogue: TMEM -> red.add into dW
+    const int q = warp - 4;
+    const int n = n_tile * 128 + q * 32 + lane;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int j = 0; j < nblk; ++j) {
+      int cb = cb0 + j;
+      int src, tap, ck;
+      if (cb < kk * p.chunks0) { src = 0; tap = cb / p.chunks0; ck = cb % p.chunks0; }
+      else { cb -= kk * p.chunks0; src = 1; tap = cb / p.chunks1; ck = cb % p.chunks1; }
+      const int csrc = src ? p.C1 : p.C0;
+      const int col = (j < 4) ? j * 64 : 256 + (j - 4) * 64;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[16];
+        tmem_ld16(t_row + col + cc * 16, v);
+        tmem_ld_wait();
+        if (n < p.N4) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int c = ck * 64 + cc * 16 + e;
+            if (c < csrc) {
+              const int ic = src ? p.C0 + c : c;
+              atomicAdd(p.dW + (static_cast<size_t>(n) * p.Ctot + ic) * kk + tap, __uint_as_float(v[e]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, kWgTmemCols);
+  }
+}
+
+// db[n] += sum_pixels dZ[pix][n]   (dZ bf16 [M, N4]); HBM-bound column sum.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dz, float* __restrict__ db,
+                                                          int M, int N4, int rows_per_block) {
+  // thread t handles channel pair (2*(t % (N4/2))) and row lane t / (N4/2)
+  const int pairs = N4 >> 1;
+  const int cp = threadIdx.x % pairs;
+  const int rl = threadIdx.x / pairs;
+  const int rstep = blockDim.x / pairs;
+  if (rl >= rstep) return;
+  const int m0 = blockIdx.x * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  for (int m = m0 + rl; m < m1; m += rstep) {
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(dz + static_cast<size_t>(m) * N4 + 2 * cp);
+    s0 += __low2float(v);
+    s1 += __high2float(v);
+  }
+  atomicAdd(db + 2 * cp, s0);
+  atomicAdd(db + 2 * cp + 1, s1);
 }
 
 }  // namespace plc
