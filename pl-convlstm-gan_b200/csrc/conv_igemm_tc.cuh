@@ -56,9 +56,11 @@ constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
 
-template <int N_TILE>
+template <int N_TILE, int kCta = 1>
 struct ConvTcCfg {
-  static constexpr int kBBytes = N_TILE * kBlockK * 2;
+  // cta_group::2: the CTA pair shares one 256 x N_TILE accumulator tile; each CTA stages its own 128 pixels of A
+  // and HALF of the B tile (N_TILE/2 packed-weight rows), so the per-SM operand feed drops from 48 to 32 KB / K-block.
+  static constexpr int kBBytes = (N_TILE / kCta) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kAuxBytes = 4096 + 256;  // bias (<= 1024 floats) + barriers
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - kAuxBytes;
@@ -67,13 +69,19 @@ struct ConvTcCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;
   static constexpr int kTmemCols = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64) ? 64 : (2 * N_TILE <= 128) ? 128
                                    : (2 * N_TILE <= 256) ? 256 : 512;
-  static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128");
+  static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128/256");
+  static_assert(kCta == 1 || kCta == 2, "cta_group is 1 or 2");
   static_assert(kStages >= 2, "need at least a double buffer");
 };
 
-__device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int& n_tile, int& b, int& y0, int& x0) {
+// tile -> (n_tile, image b, patch origin).  With kCta == 2 a "tile" is a PAIR tile: two adjacent 128-pixel m-tiles
+// (CTA rank r takes m_tile = 2*mpair + r; an odd tail m-tile decodes to b == B, which TMA zero-fills and the
+// epilogue masks).
+template <int kCta>
+__device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int rank, int& n_tile, int& b, int& y0,
+                                            int& x0) {
   n_tile = tile % p.num_n_tiles;
-  int m_tile = tile / p.num_n_tiles;
+  int m_tile = (tile / p.num_n_tiles) * kCta + rank;
   int tx = m_tile % p.tiles_x;
   int r = m_tile / p.tiles_x;
   int ty = r % p.tiles_y;
@@ -82,17 +90,25 @@ __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int
   x0 = tx * p.tw;
 }
 
-template <int N_TILE, int EPI>
-__global__ void __launch_bounds__(256, 1)
+// epilogue warps: the LSTM epilogues are MUFU/latency heavy (5 transcendentals per element) and must finish a tile
+// faster than the tensor core produces the next one -> two warps per TMEM lane quadrant, alternating 16-channel chunks.
+template <int EPI>
+constexpr int epi_warps() { return EPI == EPI_PLAIN ? 4 : 8; }
+template <int EPI>
+constexpr int conv_tc_threads() { return 128 + 32 * epi_warps<EPI>(); }
+
+template <int N_TILE, int EPI, int kCta>
+__global__ void __launch_bounds__(conv_tc_threads<EPI>(), 1)
 conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap tmap_a0,
                      const __grid_constant__ CUtensorMap tmap_a1, const __grid_constant__ CUtensorMap tmap_b) {
-  using Cfg = ConvTcCfg<N_TILE>;
+  using Cfg = ConvTcCfg<N_TILE, kCta>;
   constexpr int kStages = Cfg::kStages;
   constexpr int CH_TILE = N_TILE / 4;
 
+  constexpr int kEpiWarps = epi_warps<EPI>();
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B atoms need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // SWIZZLE_128B atoms need 1024-byte alignment (offset arithmetic keeps the pointer in the shared address space)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
   float* bias_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
@@ -105,6 +121,9 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = (kCta == 2) ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader (issues the MMAs)
+  const int tile0 = blockIdx.x / kCta, tile_step = gridDim.x / kCta;
+  const int num_tiles = (kCta == 2) ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a0);
@@ -118,16 +137,16 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], kEpiWarps * kCta);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<1>(tmem_ptr_s, Cfg::kTmemCols);
+  if (warp == 2) tmem_alloc<kCta>(tmem_ptr_s, Cfg::kTmemCols);
   if (EPI != EPI_PLAIN) {
     for (int i = threadIdx.x; i < 4 * p.Ch; i += blockDim.x) bias_s[i] = p.bias ? p.bias[i] : 0.f;
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -135,9 +154,9 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     // ===================================================================== TMA producer
     uint32_t stage = 0, phase = 0;
     const int kk = p.ksize * p.ksize;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       int n_tile, b, y0, x0;
-      decode_tile(p, tile, n_tile, b, y0, x0);
+      decode_tile<kCta>(p, tile, rank, n_tile, b, y0, x0);
       int kb = 0;
       for (int src = 0; src < 2; ++src) {
         const int chunks = src ? p.chunks1 : p.chunks0;
@@ -148,20 +167,29 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           const int dx = tap % p.ksize - p.pad;
           for (int ck = 0; ck < chunks; ++ck, ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_4d(smem_a + stage * kABytes, tm, &full_bar[stage], ck * kBlockK, x0 + dx, y0 + dy, b);
-            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBlockK, n_tile * N_TILE);
+            if constexpr (kCta == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_4d(smem_a + stage * kABytes, tm, &full_bar[stage], ck * kBlockK, x0 + dx, y0 + dy, b);
+              tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBlockK, n_tile * N_TILE);
+            } else {
+              // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there)
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              tma_load_4d_cg2(smem_u32(smem_a + stage * kABytes), tm, lead_bar, ck * kBlockK, x0 + dx, y0 + dy, b);
+              tma_load_2d_cg2(smem_u32(smem_b + stage * Cfg::kBBytes), &tmap_b, lead_bar, kb * kBlockK,
+                              n_tile * N_TILE + rank * (N_TILE / 2));
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================================== MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(kTileM, N_TILE, 0, 0);
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===================================================================== MMA issuer (leader CTA only)
+    constexpr uint32_t idesc = make_idesc_bf16(kTileM * kCta, N_TILE, 0, 0);
     uint32_t stage = 0, phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -175,27 +203,35 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           // +32 bytes per UMMA_K=16 inside the 128-byte swizzle atom (descriptor units of 16 B)
-          umma_bf16<1>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_bf16<kCta>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
         }
-        umma_commit<1>(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-        if (kb == p.num_kb - 1) umma_commit<1>(&tmem_full[as]);
+        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+        if constexpr (kCta == 1) {
+          umma_commit<1>(&empty_bar[stage]);
+          if (kb == p.num_kb - 1) umma_commit<1>(&tmem_full[as]);
+        } else {
+          umma_commit_mc2(&empty_bar[stage], 0b11);
+          if (kb == p.num_kb - 1) umma_commit_mc2(&tmem_full[as], 0b11);
+        }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
-    const int q = warp - 4;  // TMEM lane quadrant == warp_idx % 4
+    const int q = warp & 3;             // TMEM lane quadrant == warp_idx % 4
+    const int half = (warp - 4) >> 2;   // which of the kEpiWarps/4 warps of this quadrant
+    constexpr int kChunkStep = kEpiWarps / 4;
     const int row = q * 32 + lane;
     const int ty = row >> p.tw_log2;
     const int tx = row & (p.tw - 1);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       int n_tile, b, y0, x0;
-      decode_tile(p, tile, n_tile, b, y0, x0);
+      decode_tile<kCta>(p, tile, rank, n_tile, b, y0, x0);
       const int y = y0 + ty, x = x0 + tx;
-      const bool valid = (y < p.H) && (x < p.W);
+      const bool valid = (y < p.H) && (x < p.W) && (b < p.B);
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
@@ -204,7 +240,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       if constexpr (EPI == EPI_LSTM_FWD || EPI == EPI_LSTM_BWD_GATES) {
         const int ch0 = n_tile * CH_TILE;
 #pragma unroll 1
-        for (int cc = 0; cc < CH_TILE / 16; ++cc) {
+        for (int cc = half; cc < CH_TILE / 16; cc += kChunkStep) {
           uint32_t vi[16], vf[16], vo[16], vg[16];
           tmem_ld16(t_acc + 0 * CH_TILE + cc * 16, vi);
           tmem_ld16(t_acc + 1 * CH_TILE + cc * 16, vf);
@@ -214,6 +250,24 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           if (valid) {
             const int chb = ch0 + cc * 16;
             const size_t off = pix * p.Ch + chb;
+            {  // + bias (reference order: gate*Ch + channel), 16-byte smem broadcasts
+#pragma unroll
+              for (int v4 = 0; v4 < 4; ++v4) {
+                const float4 bi = *reinterpret_cast<const float4*>(bias_s + 0 * p.Ch + chb + 4 * v4);
+                const float4 bf = *reinterpret_cast<const float4*>(bias_s + 1 * p.Ch + chb + 4 * v4);
+                const float4 bo = *reinterpret_cast<const float4*>(bias_s + 2 * p.Ch + chb + 4 * v4);
+                const float4 bg = *reinterpret_cast<const float4*>(bias_s + 3 * p.Ch + chb + 4 * v4);
+                const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, bfa[4] = {bf.x, bf.y, bf.z, bf.w};
+                const float boa[4] = {bo.x, bo.y, bo.z, bo.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  vi[4 * v4 + e] = __float_as_uint(__uint_as_float(vi[4 * v4 + e]) + bia[e]);
+                  vf[4 * v4 + e] = __float_as_uint(__uint_as_float(vf[4 * v4 + e]) + bfa[e]);
+                  vo[4 * v4 + e] = __float_as_uint(__uint_as_float(vo[4 * v4 + e]) + boa[e]);
+                  vg[4 * v4 + e] = __float_as_uint(__uint_as_float(vg[4 * v4 + e]) + bga[e]);
+                }
+              }
+            }
             float cp[16];
             {
               const float4* src = reinterpret_cast<const float4*>(p.c_prev + off);
@@ -233,10 +287,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                   const int jj = j + u;
-                  const float ig = sigmoid_fast(__uint_as_float(vi[jj]) + bias_s[0 * p.Ch + chb + jj]);
-                  const float fg = sigmoid_fast(__uint_as_float(vf[jj]) + bias_s[1 * p.Ch + chb + jj]);
-                  const float og = sigmoid_fast(__uint_as_float(vo[jj]) + bias_s[2 * p.Ch + chb + jj]);
-                  const float gt = tanh_fast(__uint_as_float(vg[jj]) + bias_s[3 * p.Ch + chb + jj]);
+                  const float ig = sigmoid_fast(__uint_as_float(vi[jj]));
+                  const float fg = sigmoid_fast(__uint_as_float(vf[jj]));
+                  const float og = sigmoid_fast(__uint_as_float(vo[jj]));
+                  const float gt = tanh_fast(__uint_as_float(vg[jj]));
                   const float c2 = fmaf(fg, cp[jj], ig * gt);          // convlstm.py:26
                   cn[jj] = c2;
                   hv[u] = og * tanh_fast(c2);                          // convlstm.py:27
@@ -310,10 +364,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                   const int jj = j + u;
-                  const float ig = sigmoid_fast(__uint_as_float(vi[jj]) + bias_s[0 * p.Ch + chb + jj]);
-                  const float fg = sigmoid_fast(__uint_as_float(vf[jj]) + bias_s[1 * p.Ch + chb + jj]);
-                  const float og = sigmoid_fast(__uint_as_float(vo[jj]) + bias_s[2 * p.Ch + chb + jj]);
-                  const float gt = tanh_fast(__uint_as_float(vg[jj]) + bias_s[3 * p.Ch + chb + jj]);
+                  const float ig = sigmoid_fast(__uint_as_float(vi[jj]));
+                  const float fg = sigmoid_fast(__uint_as_float(vf[jj]));
+                  const float og = sigmoid_fast(__uint_as_float(vo[jj]));
+                  const float gt = tanh_fast(__uint_as_float(vg[jj]));
                   const float c2 = fmaf(fg, cp[jj], ig * gt);
                   const float tc = tanh_fast(c2);
                   const float dh_ = dhv[jj];
@@ -347,7 +401,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         }
       } else {  // EPI_PLAIN: D -> bf16, columns [0,Cin) -> out0, [Cin, n_total) -> out1
 #pragma unroll 1
-        for (int cc = 0; cc < N_TILE / 16; ++cc) {
+        for (int cc = half; cc < N_TILE / 16; cc += kChunkStep) {
           uint32_t v[16];
           tmem_ld16(t_acc + cc * 16, v);
           tmem_ld_wait();
@@ -374,15 +428,19 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (kCta == 1) mbar_arrive(&tmem_empty[as]);
+        else mbar_arrive_cluster(&tmem_empty[as], 0);   // the leader's barrier gates the next MMA into this stage
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  // pair: neither CTA may exit (or free TMEM) while the peer's MMAs / barrier arrives can still touch it
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc<kCta>(tmem_base, Cfg::kTmemCols);
   }
 }
 

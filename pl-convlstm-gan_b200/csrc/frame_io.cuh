@@ -23,13 +23,16 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<uint4*>(dst) = o;
 }
 
-// grid: (ceil(W/P), H, N); block: (G = C/8, P).  threadIdx.x = 8-channel group, threadIdx.y = pixel, so the
-// G lanes of one pixel write one contiguous C*sizeof(TOut) run (coalesced NHWC stores).
-// w: init_conv.weight [C, Cf+2, 3, 3] (reference OIHW), staged in smem as [tap*(Cf+2)+ci][C].
+// Persistent blocks: block (G = C/8, P); threadIdx.x = 8-channel group, threadIdx.y = pixel-quad lane.  Each thread
+// computes 8 output channels for 4 CONSECUTIVE x pixels (register blocking: one pair of 16-byte weight loads feeds
+// 32 FMAs), and the G lanes of one pixel write one contiguous C*sizeof(TOut) run (coalesced NHWC stores).
+// Weights are staged in smem ONCE per block (as [tap*(Cf+2)+ci][C]); the block grid-strides over pixel quads.
+// w: init_conv.weight [C, Cf+2, 3, 3] (reference OIHW).
+constexpr int kFrontPx = 4;
 template <typename TOut>
-__global__ void frontend_kernel(const float* __restrict__ frames, const float* __restrict__ w,
-                                const float* __restrict__ bias, TOut* __restrict__ out, int Cf, int H, int W, int C,
-                                int C_out_stride) {
+__global__ void __launch_bounds__(256) frontend_kernel(const float* __restrict__ frames, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, TOut* __restrict__ out, int N,
+                                                       int Cf, int H, int W, int C, int C_out_stride) {
   extern __shared__ float ws[];  // [(Cf+2)*9][C] + bias[C]
   const int cin = Cf + 2;
   const int nw = cin * 9 * C;
@@ -42,32 +45,63 @@ __global__ void frontend_kernel(const float* __restrict__ frames, const float* _
   float* bs = ws + nw;
   for (int i = tid; i < C; i += nthr) bs[i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const int x = blockIdx.x * blockDim.y + threadIdx.y, y = blockIdx.y, n = blockIdx.z;
-  if (x >= W) return;
   const int c0 = threadIdx.x * 8;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bs[c0 + j];
   const float inv_h = H > 1 ? 1.f / (H - 1) : 0.f, inv_w = W > 1 ? 1.f / (W - 1) : 0.f;
-  for (int tap = 0; tap < 9; ++tap) {
-    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;  // zero padding applies to the coord channels too
-    for (int ci = 0; ci < cin; ++ci) {
-      float v;
-      if (ci < Cf) v = __ldg(frames + ((static_cast<size_t>(n) * Cf + ci) * H + yy) * W + xx);
-      else if (ci == Cf) v = yy * inv_h;      // row channel: linspace(0,1,H)   (coordconv.py:7)
-      else v = xx * inv_w;                    // col channel: linspace(0,1,W)   (coordconv.py:8)
-      const float4* wr = reinterpret_cast<const float4*>(ws + (tap * cin + ci) * C + c0);
-      const float4 w0 = wr[0], w1 = wr[1];
-      acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-      acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-      acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-      acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+  const int qpr = (W + kFrontPx - 1) / kFrontPx;                     // quads per image row
+  const size_t nquads = static_cast<size_t>(N) * H * qpr;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.y;
+  for (size_t q = static_cast<size_t>(blockIdx.x) * blockDim.y + threadIdx.y; q < nquads; q += stride) {
+    const int x0 = static_cast<int>(q % qpr) * kFrontPx;
+    const size_t t = q / qpr;
+    const int y = static_cast<int>(t % H);
+    const size_t n = t / H;
+    float acc[kFrontPx][8];
+#pragma unroll
+    for (int px = 0; px < kFrontPx; ++px)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[px][j] = bs[c0 + j];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      if (yy < 0 || yy >= H) continue;     // zero padding (applies to the coord channels too)
+      for (int ci = 0; ci < cin; ++ci) {
+        float v[kFrontPx + 2];             // input values at x0-1 .. x0+kFrontPx
+#pragma unroll
+        for (int i = 0; i < kFrontPx + 2; ++i) {
+          const int xx = x0 - 1 + i;
+          float val = 0.f;
+          if (xx >= 0 && xx < W) {
+            if (ci < Cf) val = __ldg(frames + ((n * Cf + ci) * H + yy) * W + xx);
+            else if (ci == Cf) val = yy * inv_h;   // row channel: linspace(0,1,H)   (coordconv.py:7)
+            else val = xx * inv_w;                 // col channel: linspace(0,1,W)   (coordconv.py:8)
+          }
+          v[i] = val;
+        }
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4* wr = reinterpret_cast<const float4*>(ws + ((dy * 3 + dx) * cin + ci) * C + c0);
+          const float4 w0 = wr[0], w1 = wr[1];
+#pragma unroll
+          for (int px = 0; px < kFrontPx; ++px) {
+            const float a = v[px + dx];
+            acc[px][0] = fmaf(a, w0.x, acc[px][0]); acc[px][1] = fmaf(a, w0.y, acc[px][1]);
+            acc[px][2] = fmaf(a, w0.z, acc[px][2]); acc[px][3] = fmaf(a, w0.w, acc[px][3]);
+            acc[px][4] = fmaf(a, w1.x, acc[px][4]); acc[px][5] = fmaf(a, w1.y, acc[px][5]);
+            acc[px][6] = fmaf(a, w1.z, acc[px][6]); acc[px][7] = fmaf(a, w1.w, acc[px][7]);
+          }
+        }
+      }
+    }
+    const size_t pix0 = (n * H + y) * W + x0;
+#pragma unroll
+    for (int px = 0; px < kFrontPx; ++px) {
+      if (x0 + px < W) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[px][j] = fmaxf(acc[px][j], 0.f);   // F.relu (generator.py:168)
+        store8<TOut>(out + (pix0 + px) * C_out_stride + c0, acc[px]);
+      }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);   // F.relu (generator.py:168)
-  store8<TOut>(out + ((static_cast<size_t>(n) * H + y) * W + x) * C_out_stride + c0, acc);
 }
 
 // G = C/8 lanes per pixel (G a power of two <= 32): each lane reads 16 B, partial dot products are

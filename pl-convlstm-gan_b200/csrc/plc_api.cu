@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -246,17 +247,52 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ s
 }
 
 // ------------------------------------------------------------------ tensor-core launches
-template <int EPI>
-int launch_conv_tc(int n_tile, const plc::ConvTcParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
-                   const CUtensorMap& b, cudaStream_t st) {
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-#define PLC_LAUNCH_TC(NT)                                                                                        \
-  case NT: {                                                                                                     \
-    auto kfn = plc::conv_igemm_tc_kernel<NT, EPI>;                                                               \
-    PLC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, plc::ConvTcCfg<NT>::kSmemBytes)); \
-    kfn<<<grid, 256, plc::ConvTcCfg<NT>::kSmemBytes, st>>>(p, a0, a1, b);                                        \
-    break;                                                                                                       \
+// cta_group choice: a CTA pair (cta_group::2) halves the per-SM weight-tile traffic and wins once there are
+// enough 128-pixel tiles to keep all 74 pairs busy; tiny problems keep 148 independent CTAs.
+// PLC_CTA_GROUP=1|2 overrides (used by the benchmarks to A/B the two paths).
+int pick_cta_group(int num_m_tiles) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("PLC_CTA_GROUP");
+    forced = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
   }
+  if (forced) return forced;
+  return num_m_tiles >= 2 * sm_count() ? 2 : 1;
+}
+
+template <int NT, int EPI, int CTA>
+int launch_conv_tc_inst(const plc::ConvTcParams& p, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                        cudaStream_t st) {
+  using Cfg = plc::ConvTcCfg<NT, CTA>;
+  auto kfn = plc::conv_igemm_tc_kernel<NT, EPI, CTA>;
+  PLC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  const int tiles = CTA == 2 ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_tiles;
+  const int slots = sm_count() / CTA;
+  const int grid = (tiles < slots ? tiles : slots) * CTA;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(plc::conv_tc_threads<EPI>());
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PLC_CUDA(cudaLaunchKernelEx(&cfg, kfn, p, a0, a1, b));
+  return PLC_OK;
+}
+
+template <int EPI>
+int launch_conv_tc(int n_tile, int cta, const plc::ConvTcParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
+                   const CUtensorMap& b, cudaStream_t st) {
+#define PLC_LAUNCH_TC(NT)                                                                     \
+  case NT:                                                                                    \
+    return cta == 2 ? launch_conv_tc_inst<NT, EPI, 2>(p, a0, a1, b, st)                       \
+                    : launch_conv_tc_inst<NT, EPI, 1>(p, a0, a1, b, st);
   switch (n_tile) {
     PLC_LAUNCH_TC(64)
     PLC_LAUNCH_TC(128)
@@ -266,8 +302,6 @@ int launch_conv_tc(int n_tile, const plc::ConvTcParams& p, const CUtensorMap& a0
       return fail(PLC_ERR_UNSUPPORTED, "no tensor-core kernel for N_TILE=%d", n_tile);
   }
 #undef PLC_LAUNCH_TC
-  PLC_CUDA(cudaGetLastError());
-  return PLC_OK;
 }
 
 void fill_geom(const PlcCellDesc* d, const TcGeom& g, plc::ConvTcParams* p) {
@@ -451,8 +485,9 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   } else {
     ta0 = ta1;
   }
-  if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile))) return rc;
-  return launch_conv_tc<plc::EPI_LSTM_FWD>(g.n_tile, p, ta0, ta1, tb, st);
+  const int cta = pick_cta_group(p.num_m_tiles);
+  if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile / cta))) return rc;
+  return launch_conv_tc<plc::EPI_LSTM_FWD>(g.n_tile, cta, p, ta0, ta1, tb, st);
 }
 
 size_t plc_bwd_workspace_bytes(const PlcCellDesc* d) {
@@ -554,8 +589,9 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   } else {
     ta0 = ta1;
   }
-  if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile))) return rc;
-  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, p, ta0, ta1, tb, st))) return rc;
+  const int cta = pick_cta_group(p.num_m_tiles);
+  if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile / cta))) return rc;
+  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, st))) return rc;
 
   // 2) dgrad: conv of dZ (4Ch channels) with the flipped/transposed image -> dx, dh_prev
   if (dx || dh_prev) {
@@ -573,8 +609,8 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     q.out1 = static_cast<__nv_bfloat16*>(dh_prev);
     CUtensorMap tz, tbd;
     if ((rc = make_tmap_act(&tz, workspace, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th))) return rc;
-    if ((rc = make_tmap_mat(&tbd, w_packed_dgrad, n_total, (long)q.num_kb * 64, 64, nt))) return rc;
-    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, q, tz, tz, tbd, st))) return rc;
+    if ((rc = make_tmap_mat(&tbd, w_packed_dgrad, n_total, (long)q.num_kb * 64, 64, nt / cta))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tbd, st))) return rc;
   }
 
   // 3) wgrad + bias grad
@@ -611,20 +647,23 @@ int plc_frontend_fwd(const float* frames, int N, int Cf, int H, int W, const flo
   if (N <= 0 || Cf <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || C > 256 || C_stride < C || C_stride % 8)
     return fail(PLC_ERR_BAD_DESC, "plc_frontend_fwd: need C %% 8 == 0, C <= 256, C_stride >= C (got C=%d stride=%d)", C,
                 C_stride);
-  if (H > 65535 || N > 65535) return fail(PLC_ERR_UNSUPPORTED, "plc_frontend_fwd: H and N must be <= 65535");
   if (!aligned16(out)) return fail(PLC_ERR_ALIGNMENT, "plc_frontend_fwd: out must be 16-byte aligned");
   const int G = C / 8, P = G >= 256 ? 1 : 256 / G;
-  dim3 grid(cdiv(W, P), H, N), block(G, P);
+  if (G > 256) return fail(PLC_ERR_UNSUPPORTED, "plc_frontend_fwd: C must be <= 2048");
+  const size_t quads = static_cast<size_t>(N) * H * ((W + plc::kFrontPx - 1) / plc::kFrontPx);
+  const size_t groups = (quads + P - 1) / P;
+  const size_t max_blocks = static_cast<size_t>(sm_count()) * 8;
+  dim3 grid(static_cast<unsigned>(groups < max_blocks ? groups : max_blocks)), block(G, P);
   const size_t smem = (static_cast<size_t>(Cf + 2) * 9 * C + C) * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mode == PLC_MODE_BF16_TC) {
     PLC_CUDA(cudaFuncSetAttribute(plc::frontend_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     plc::frontend_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(frames, w_oihw, bias, static_cast<__nv_bfloat16*>(out),
-                                                                  Cf, H, W, C, C_stride);
+                                                                  N, Cf, H, W, C, C_stride);
   } else {
     PLC_CUDA(cudaFuncSetAttribute(plc::frontend_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    plc::frontend_kernel<float><<<grid, block, smem, st>>>(frames, w_oihw, bias, static_cast<float*>(out), Cf, H, W, C,
+    plc::frontend_kernel<float><<<grid, block, smem, st>>>(frames, w_oihw, bias, static_cast<float*>(out), N, Cf, H, W, C,
                                                           C_stride);
   }
   PLC_CUDA(cudaGetLastError());

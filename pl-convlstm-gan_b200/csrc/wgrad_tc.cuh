@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256, 1)
 wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_dz,
                 const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kWgStages;
@@ -84,30 +84,45 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
 
   if (warp == 0 && lane == 0) {
     // ===================================================================== TMA producer
+    // All per-column-block index math is hoisted: a single thread issues 2 + nblk TMA loads per stage and must
+    // stay well under the stage's MMA time.
+    int dxs[kWgMaxGB], dys[kWgMaxGB], cks[kWgMaxGB];
+    bool s1[kWgMaxGB];
+#pragma unroll
+    for (int j = 0; j < kWgMaxGB; ++j) {
+      int cb = cb0 + j, tap = 0, ck = 0;
+      bool is1 = false;
+      if (j < nblk) {
+        if (cb < kk * p.chunks0) { tap = cb / p.chunks0; ck = cb % p.chunks0; }
+        else { cb -= kk * p.chunks0; is1 = true; tap = cb / p.chunks1; ck = cb % p.chunks1; }
+      }
+      dys[j] = tap / p.ksize - p.pad; dxs[j] = tap % p.ksize - p.pad; cks[j] = ck * 64; s1[j] = is1;
+    }
     uint32_t stage = 0, phase = 0;
     const uint32_t bytes = (2 + nblk) * kWgBoxBytes;
+    // pixel block s + i*S, decoded incrementally
+    int tx = s % p.tiles_x, r0 = s / p.tiles_x;
+    int ty = r0 % p.tiles_y, b = r0 / p.tiles_y;
+    const int step_x = p.S % p.tiles_x, step_r = p.S / p.tiles_x;
+    const int step_y = step_r % p.tiles_y, step_b = step_r / p.tiles_y;
     for (int i = 0; i < my_blocks; ++i) {
-      const int pb = s + i * p.S;
-      const int tx = pb % p.tiles_x;
-      const int r = pb / p.tiles_x;
-      const int ty = r % p.tiles_y;
-      const int b = r / p.tiles_y;
       const int x0 = tx * p.tw, y0 = ty * p.th;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       mbar_arrive_expect_tx(&full_bar[stage], bytes);
       uint8_t* st = smem + stage * kWgStageBytes;
       tma_load_4d(st, &tmap_dz, &full_bar[stage], n_tile * 128, x0, y0, b);
       tma_load_4d(st + kWgBoxBytes, &tmap_dz, &full_bar[stage], n_tile * 128 + 64, x0, y0, b);
-      for (int j = 0; j < nblk; ++j) {
-        int cb = cb0 + j;
-        const CUtensorMap* tm;
-        int tap, ck;
-        if (cb < kk * p.chunks0) { tm = &tmap_a0; tap = cb / p.chunks0; ck = cb % p.chunks0; }
-        else { cb -= kk * p.chunks0; tm = &tmap_a1; tap = cb / p.chunks1; ck = cb % p.chunks1; }
-        const int dy = tap / p.ksize - p.pad, dx = tap % p.ksize - p.pad;
-        tma_load_4d(st + (2 + j) * kWgBoxBytes, tm, &full_bar[stage], ck * 64, x0 + dx, y0 + dy, b);
+#pragma unroll
+      for (int j = 0; j < kWgMaxGB; ++j) {
+        if (j < nblk)
+          tma_load_4d(st + (2 + j) * kWgBoxBytes, s1[j] ? &tmap_a1 : &tmap_a0, &full_bar[stage], cks[j], x0 + dxs[j],
+                      y0 + dys[j], b);
       }
       if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      // advance (tx, ty, b) by S pixel blocks without divisions
+      tx += step_x; ty += step_y; b += step_b;
+      if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+      if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================================================================== MMA issuer

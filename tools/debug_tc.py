@@ -58,7 +58,7 @@ if __name__ == "__main__":
     for n in names:
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", n], capture_output=True,
-                               text=True, timeout=120)
+                               text=True, timeout=int(os.environ.get("PLC_CASE_TIMEOUT", "120")))
             print(f"--- {n}: exit {r.returncode}")
             print(r.stdout[-3000:])
             if r.returncode:
