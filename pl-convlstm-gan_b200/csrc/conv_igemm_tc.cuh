@@ -119,7 +119,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   uint64_t* tmem_empty = bars + 2 * kStages + 2;   // [2]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int rank = (kCta == 2) ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader (issues the MMAs)
   const int tile0 = blockIdx.x / kCta, tile_step = gridDim.x / kCta;
@@ -150,13 +150,18 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp == 0 && lane == 0) {
+  // The producer and MMA-issuer loops run WARP-UNIFORM (all 32 lanes walk the loop, one elected lane issues):
+  // every loop value is then provably uniform, lives in uniform registers, and the per-K-block issue sequence
+  // stays far below the 512 cycles the tensor core needs for it (a lane-0-only loop cost ~750 cycles/K-block).
+  if (warp == 0) {
     // ===================================================================== TMA producer
     uint32_t stage = 0, phase = 0;
     const int kk = p.ksize * p.ksize;
+    const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b), full_base = smem_u32(full_bar);
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       int n_tile, b, y0, x0;
       decode_tile<kCta>(p, tile, rank, n_tile, b, y0, x0);
+      const int n_row = n_tile * N_TILE + rank * (N_TILE / kCta);
       int kb = 0;
       for (int src = 0; src < 2; ++src) {
         const int chunks = src ? p.chunks1 : p.chunks0;
@@ -167,26 +172,31 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           const int dx = tap % p.ksize - p.pad;
           for (int ck = 0; ck < chunks; ++ck, ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if constexpr (kCta == 1) {
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              tma_load_4d(smem_a + stage * kABytes, tm, &full_bar[stage], ck * kBlockK, x0 + dx, y0 + dy, b);
-              tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBlockK, n_tile * N_TILE);
-            } else {
-              // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there)
-              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-              const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-              tma_load_4d_cg2(smem_u32(smem_a + stage * kABytes), tm, lead_bar, ck * kBlockK, x0 + dx, y0 + dy, b);
-              tma_load_2d_cg2(smem_u32(smem_b + stage * Cfg::kBBytes), &tmap_b, lead_bar, kb * kBlockK,
-                              n_tile * N_TILE + rank * (N_TILE / 2));
+            if (elect_one()) {
+              const uint32_t a_dst = a_base + stage * kABytes, b_dst = b_base + stage * Cfg::kBBytes;
+              if constexpr (kCta == 1) {
+                mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                tma_load_4d_s(a_dst, tm, full_base + stage * 8, ck * kBlockK, x0 + dx, y0 + dy, b);
+                tma_load_2d_s(b_dst, &tmap_b, full_base + stage * 8, kb * kBlockK, n_row);
+              } else {
+                // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there)
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                const uint32_t lead_bar = mapa_u32(full_base + stage * 8, 0);
+                tma_load_4d_cg2(a_dst, tm, lead_bar, ck * kBlockK, x0 + dx, y0 + dy, b);
+                tma_load_2d_cg2(b_dst, &tmap_b, lead_bar, kb * kBlockK, n_row);
+              }
             }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (warp == 1 && rank == 0) {
     // ===================================================================== MMA issuer (leader CTA only)
     constexpr uint32_t idesc = make_idesc_bf16(kTileM * kCta, N_TILE, 0, 0);
+    const uint64_t adesc0 = make_smem_desc(smem_u32(smem_a), 0, 1024);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), 0, 1024);
     uint32_t stage = 0, phase = 0;
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
@@ -198,21 +208,25 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * kABytes), 0, 1024);
-        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes), 0, 1024);
+        if (elect_one()) {
+          // descriptor start-address field is in 16-byte units
+          const uint64_t adesc = adesc0 + stage * (kABytes >> 4);
+          const uint64_t bdesc = bdesc0 + stage * (Cfg::kBBytes >> 4);
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // +32 bytes per UMMA_K=16 inside the 128-byte swizzle atom (descriptor units of 16 B)
-          umma_bf16<kCta>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 bytes per UMMA_K=16 inside the 128-byte swizzle atom
+            umma_bf16<kCta>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (kCta == 1) {
+            umma_commit<1>(&empty_bar[stage]);
+            if (kb == p.num_kb - 1) umma_commit<1>(&tmem_full[as]);
+          } else {
+            umma_commit_mc2(&empty_bar[stage], 0b11);
+            if (kb == p.num_kb - 1) umma_commit_mc2(&tmem_full[as], 0b11);
+          }
         }
-        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-        if constexpr (kCta == 1) {
-          umma_commit<1>(&empty_bar[stage]);
-          if (kb == p.num_kb - 1) umma_commit<1>(&tmem_full[as]);
-        } else {
-          umma_commit_mc2(&empty_bar[stage], 0b11);
-          if (kb == p.num_kb - 1) umma_commit_mc2(&tmem_full[as], 0b11);
-        }
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }

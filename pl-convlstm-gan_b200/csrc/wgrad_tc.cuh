@@ -52,7 +52,7 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
   uint64_t* acc_bar = bars + 2 * kWgStages;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   // job decomposition
   int job = blockIdx.x;
   const int s = job % p.S; job /= p.S;
@@ -82,8 +82,8 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
   const uint32_t tmem_base = *tmem_ptr_s;
   const int my_blocks = (p.PB - s + p.S - 1) / p.S;   // pixel blocks s, s+S, ...
 
-  if (warp == 0 && lane == 0) {
-    // ===================================================================== TMA producer
+  if (warp == 0) {
+    // ===================================================================== TMA producer (warp-uniform loop)
     // All per-column-block index math is hoisted: a single thread issues 2 + nblk TMA loads per stage and must
     // stay well under the stage's MMA time.
     int dxs[kWgMaxGB], dys[kWgMaxGB], cks[kWgMaxGB];
@@ -108,24 +108,28 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
     for (int i = 0; i < my_blocks; ++i) {
       const int x0 = tx * p.tw, y0 = ty * p.th;
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      mbar_arrive_expect_tx(&full_bar[stage], bytes);
-      uint8_t* st = smem + stage * kWgStageBytes;
-      tma_load_4d(st, &tmap_dz, &full_bar[stage], n_tile * 128, x0, y0, b);
-      tma_load_4d(st + kWgBoxBytes, &tmap_dz, &full_bar[stage], n_tile * 128 + 64, x0, y0, b);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[stage], bytes);
+        const uint32_t st = smem_u32(smem) + stage * kWgStageBytes;
+        const uint32_t bar = smem_u32(&full_bar[stage]);
+        tma_load_4d_s(st, &tmap_dz, bar, n_tile * 128, x0, y0, b);
+        tma_load_4d_s(st + kWgBoxBytes, &tmap_dz, bar, n_tile * 128 + 64, x0, y0, b);
 #pragma unroll
-      for (int j = 0; j < kWgMaxGB; ++j) {
-        if (j < nblk)
-          tma_load_4d(st + (2 + j) * kWgBoxBytes, s1[j] ? &tmap_a1 : &tmap_a0, &full_bar[stage], cks[j], x0 + dxs[j],
-                      y0 + dys[j], b);
+        for (int j = 0; j < kWgMaxGB; ++j) {
+          if (j < nblk)
+            tma_load_4d_s(st + (2 + j) * kWgBoxBytes, s1[j] ? &tmap_a1 : &tmap_a0, bar, cks[j], x0 + dxs[j],
+                          y0 + dys[j], b);
+        }
       }
+      __syncwarp();
       if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       // advance (tx, ty, b) by S pixel blocks without divisions
       tx += step_x; ty += step_y; b += step_b;
       if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
       if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (warp-uniform loop)
     const int n_a = nblk < 4 ? nblk : 4;      // columns [0, 64*n_a)
     const int n_b = nblk - n_a;               // columns [256, 256 + 64*n_b)
     const uint32_t idesc_a = make_idesc_bf16(128, 64 * n_a, 1, 1);
@@ -134,7 +138,8 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
     for (int i = 0; i < my_blocks; ++i) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      const uint32_t st = smem_u32(smem + stage * kWgStageBytes);
+      const uint32_t st = smem_u32(smem) + stage * kWgStageBytes;
+      if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < kWgPix / 16; ++ks) {
         // 16 pixels (K') = two 8-row groups = 2048 bytes further down every 64-channel chunk
@@ -147,9 +152,11 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
         }
       }
       umma_commit<1>(&empty_bar[stage]);
+      if (i == my_blocks - 1) umma_commit<1>(acc_bar);
+      }
+      __syncwarp();
       if (++stage == kWgStages) { stage = 0; phase ^= 1; }
     }
-    umma_commit<1>(acc_bar);
   } else if (warp >= 4 && my_blocks > 0) {
     // ===================================================================== epilogue: TMEM -> red.add into dW
     const int q = warp - 4;
