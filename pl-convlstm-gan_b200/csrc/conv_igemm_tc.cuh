@@ -247,20 +247,52 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       const int y = y0 + ty, x = x0 + tx;
       const bool valid = (y < p.H) && (x < p.W) && (b < p.B);
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
+      // hand the accumulator stage back to the MMA warp as soon as this warp's last tcgen05.ld has landed
+      bool released = false;
+      auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCta == 1) mbar_arrive(&tmem_empty[as]);
+          else mbar_arrive_cluster(&tmem_empty[as], 0);   // the leader's barrier gates the next MMA into this stage
+        }
+        released = true;
+      };
+      constexpr int kLstmChunks = CH_TILE / 16;
+      constexpr int kMaxMine = (kLstmChunks + kChunkStep - 1) / kChunkStep;
+      // forward: fetch this thread's c_prev BEFORE waiting for the accumulator -> DRAM latency hides under the MMAs
+      float cpre[EPI == EPI_LSTM_FWD ? kMaxMine : 1][16];
+      if constexpr (EPI == EPI_LSTM_FWD) {
+#pragma unroll
+        for (int m = 0; m < kMaxMine; ++m) {
+          const int cc = half + m * kChunkStep;
+          if (valid && cc < kLstmChunks) {
+            const float4* src = reinterpret_cast<const float4*>(p.c_prev + pix * p.Ch + n_tile * CH_TILE + cc * 16);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const float4 t = __ldg(src + v);
+              cpre[m][4 * v + 0] = t.x; cpre[m][4 * v + 1] = t.y; cpre[m][4 * v + 2] = t.z; cpre[m][4 * v + 3] = t.w;
+            }
+          }
+        }
+      }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * N_TILE;
 
       if constexpr (EPI == EPI_LSTM_FWD || EPI == EPI_LSTM_BWD_GATES) {
         const int ch0 = n_tile * CH_TILE;
-#pragma unroll 1
-        for (int cc = half; cc < CH_TILE / 16; cc += kChunkStep) {
+#pragma unroll
+        for (int m = 0; m < kMaxMine; ++m) {
+          const int cc = half + m * kChunkStep;
+          if (cc >= kLstmChunks) break;
           uint32_t vi[16], vf[16], vo[16], vg[16];
           tmem_ld16(t_acc + 0 * CH_TILE + cc * 16, vi);
           tmem_ld16(t_acc + 1 * CH_TILE + cc * 16, vf);
           tmem_ld16(t_acc + 2 * CH_TILE + cc * 16, vo);
           tmem_ld16(t_acc + 3 * CH_TILE + cc * 16, vg);
           tmem_ld_wait();
+          if (cc + kChunkStep >= kLstmChunks) release();
           if (valid) {
             const int chb = ch0 + cc * 16;
             const size_t off = pix * p.Ch + chb;
@@ -283,7 +315,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
               }
             }
             float cp[16];
-            {
+            if constexpr (EPI == EPI_LSTM_FWD) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) cp[e] = cpre[m][e];
+            } else {
               const float4* src = reinterpret_cast<const float4*>(p.c_prev + off);
 #pragma unroll
               for (int v = 0; v < 4; ++v) {
@@ -419,6 +454,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           uint32_t v[16];
           tmem_ld16(t_acc + cc * 16, v);
           tmem_ld_wait();
+          if (cc + kChunkStep >= N_TILE / 16) release();
           if (valid) {
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
@@ -439,13 +475,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           }
         }
       }
-      // release this accumulator stage back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kCta == 1) mbar_arrive(&tmem_empty[as]);
-        else mbar_arrive_cluster(&tmem_empty[as], 0);   // the leader's barrier gates the next MMA into this stage
-      }
+      if (!released) release();   // warps without a chunk for this tile shape
     }
   }
 
