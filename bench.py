@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer = BASELINE configs[1] (default, the headline line); train = configs[2]-style recurrence "
+                         "training step (global batch 64 sharded over the ranks, strong scaling)")
     ap.add_argument("--cpu-sample", type=int, default=1, help="sequences per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -177,10 +180,98 @@ def committed_traffic():
     return None
 
 
+TRAIN = dict(global_batch=64, H=128, W=128, C=64, hidden=[64, 64], k=3, T=20)
+TRAIN_WORKLOAD = ("cfg3-style: 2-layer ConvLSTM (hidden [64,64], k3) recurrence training step, fwd + BPTT + grad "
+                  "all-reduce + clip + Adam, 128x128, T=20, global batch 64 sharded by batch")
+
+
+def run_train(args):
+    """Training-step throughput of the recurrence (forward rollout, BPTT through plc_cell_bwd, bucketed gradient
+    all-reduce overlapped with BPTT, clip 0.5, Adam) -- the reference order of trainer.py:290-315."""
+    import torch
+    import torch.distributed as dist
+    import plconv
+    from plconv.parallel import init_distributed, shard_batch
+    from plconv.training import TrainStep
+
+    rank, world, local = init_distributed()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = TRAIN
+    sl = shard_batch(cfg["global_batch"], rank, world)
+    B = sl.stop - sl.start
+    torch.manual_seed(1234)                       # identical weights on every rank
+    stack = plconv.ConvLSTMStack(cfg["C"], cfg["hidden"], cfg["k"], True, "bf16").to(dev)
+    torch.manual_seed(1234 + rank)
+    xs = [torch.relu(torch.randn(B, cfg["H"], cfg["W"], cfg["C"], device=dev)).to(torch.bfloat16)
+          for _ in range(cfg["T"])]
+    tgt = [torch.rand(B, cfg["H"], cfg["W"], cfg["hidden"][-1], device=dev).to(torch.bfloat16)
+           for _ in range(cfg["T"])]
+    step = TrainStep(stack, [c.parameters() for c in stack.cells], lr=5e-4, grad_clip_norm=0.5)
+
+    def forward_loss():
+        outs, _ = stack.run_nhwc(xs)
+        loss = 0.0
+        for o, t in zip(outs, tgt):
+            loss = loss + (o - t).float().pow(2).mean()
+        return loss / len(outs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    for _ in range(Wm):
+        step(forward_loss)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss = None
+    for _ in range(K):
+        loss = step(forward_loss)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        L = len(cfg["hidden"])
+        flops_fwd = sum(2.0 * cfg["H"] * cfg["W"] * (ci + ch) * cfg["k"] ** 2 * 4 * ch
+                        for ci, ch in zip([cfg["C"]] + cfg["hidden"][:-1], cfg["hidden"])) * cfg["T"]
+        seqs = cfg["global_batch"] * K
+        peak_sus, peak_burst, peak_src = measured_peaks()
+        algo_tf = 3.0 * flops_fwd * seqs / (ms * 1e-3) / 1e12 / world
+        print(json.dumps({
+            "metric": "recurrence_train_sequences_per_sec", "value": seqs / (ms * 1e-3), "unit": "sequences/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": TRAIN_WORKLOAD, "global_batch": cfg["global_batch"], "per_gpu_batch": B,
+                       "parallelism": f"dp{world} (batch shards + NCCL grad all-reduce overlapped with BPTT)",
+                       "l2": "inputs larger than L2"},
+            "gpu_launches": K * cfg["T"] * L * (1 + 5),
+            "loss": None if loss is None else float(loss),
+            "roofline": {"bound": "tensor", "achieved": algo_tf, "peak": peak_sus, "unit": "TFLOP/s",
+                         "frac": algo_tf / peak_sus, "peak_source": peak_src,
+                         "note": "whole-step algorithmic 3*F_fwd per GPU (gate recompute not counted)", "traffic": None},
+            "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.workload == "train":
+        run_train(args)
         return
 
     import torch
