@@ -351,6 +351,7 @@ int launch_wgrad_tc(const PlcCellDesc* d, const void* x, const void* h_prev, con
   p.S = S;
   p.C0 = d->Cin; p.C1 = d->Ch; p.N4 = 4 * d->Ch; p.Ctot = d->Cin + d->Ch;
   p.dW = dW;
+  p.db = db;
   CUtensorMap tz, t0, t1;
   if ((rc = make_tmap_act(&tz, dz, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th))) return rc;
   if ((rc = make_tmap_act(&t1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th))) return rc;
@@ -362,17 +363,6 @@ int launch_wgrad_tc(const PlcCellDesc* d, const void* x, const void* h_prev, con
   PLC_CUDA(cudaFuncSetAttribute(plc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plc::kWgSmemBytes));
   plc::wgrad_tc_kernel<<<tiles * S, 256, plc::kWgSmemBytes, st>>>(p, tz, t0, t1);
   PLC_CUDA(cudaGetLastError());
-  if (db) {
-    const int M = d->B * d->H * d->W, N4 = 4 * d->Ch, pairs = N4 / 2;
-    const int rstep = pairs >= 256 ? 1 : 256 / pairs;
-    const int threads = pairs * rstep;
-    int blocks = sm_count() * 4;
-    int rpb = cdiv(M, blocks);
-    if (rpb < 64) rpb = 64;
-    blocks = cdiv(M, rpb);
-    plc::colsum_bf16_kernel<<<blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(dz), db, M, N4, rpb);
-    PLC_CUDA(cudaGetLastError());
-  }
   return PLC_OK;
 }
 

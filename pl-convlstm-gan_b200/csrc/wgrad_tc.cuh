@@ -25,6 +25,7 @@ struct WgradTcParams {
   int n_tiles, S;             // 128-row tiles of n = 4Ch; pixel splits
   int C0, C1, N4, Ctot;       // true channel counts
   float* dW;                  // [N4][Ctot][k][k]
+  float* db;                  // [N4] or nullptr: bias gradient = dZ^T x ones, one extra N=16 MMA per K-step
 };
 
 constexpr int kWgPix = 64;                         // pixels per stage (UMMA K' = 4 x 16)
@@ -32,7 +33,9 @@ constexpr int kWgBoxBytes = kWgPix * 128;          // one [64 px][64 ch] bf16 bo
 constexpr int kWgMaxGB = 6;                        // N' <= 384 columns
 constexpr int kWgStageBytes = (2 + kWgMaxGB) * kWgBoxBytes;   // 64 KB
 constexpr int kWgStages = 3;
-constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 256 + 1024;
+constexpr int kWgOnesBytes = kWgBoxBytes;            // [64 px][64 ch] of bf16 1.0: B' operand of the db column
+constexpr int kWgDbCol = 384;                        // TMEM column of the db accumulator (16 columns)
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + kWgOnesBytes + 256 + 1024;
 constexpr int kWgTmemCols = 512;
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -46,7 +49,8 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
                 const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+  uint8_t* ones_s = smem + kWgStages * kWgStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones_s + kWgOnesBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kWgStages;
   uint64_t* acc_bar = bars + 2 * kWgStages;
@@ -76,6 +80,11 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_ptr_s, kWgTmemCols);
+  const bool do_db = (p.db != nullptr) && (group == 0);
+  if (do_db) {
+    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_s)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -150,6 +159,10 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
           const uint64_t bdesc1 = make_smem_desc_mn(st + 6 * kWgBoxBytes + ks * 2048, kWgBoxBytes);
           umma_bf16<1>(tmem_base + 256, adesc, bdesc1, idesc_b, (i | ks) != 0);
         }
+        if (do_db) {   // db[n] += sum over these 16 pixels of dZ[pix][n]  (all 16 result columns are equal)
+          const uint64_t odesc = make_smem_desc_mn(smem_u32(ones_s) + ks * 2048, kWgBoxBytes);
+          umma_bf16<1>(tmem_base + kWgDbCol, adesc, odesc, make_idesc_bf16(128, 16, 1, 1), (i | ks) != 0);
+        }
       }
       umma_commit<1>(&empty_bar[stage]);
       if (i == my_blocks - 1) umma_commit<1>(acc_bar);
@@ -164,6 +177,12 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if (do_db) {
+      uint32_t v[16];
+      tmem_ld16(t_row + kWgDbCol, v);
+      tmem_ld_wait();
+      if (n < p.N4) atomicAdd(p.db + n, __uint_as_float(v[0]));
+    }
     for (int j = 0; j < nblk; ++j) {
       int cb = cb0 + j;
       int src, tap, ck;
@@ -195,27 +214,6 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, kWgTmemCols);
   }
-}
-
-// db[n] += sum_pixels dZ[pix][n]   (dZ bf16 [M, N4]); HBM-bound column sum.
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dz, float* __restrict__ db,
-                                                          int M, int N4, int rows_per_block) {
-  // thread t handles channel pair (2*(t % (N4/2))) and row lane t / (N4/2)
-  const int pairs = N4 >> 1;
-  const int cp = threadIdx.x % pairs;
-  const int rl = threadIdx.x / pairs;
-  const int rstep = blockDim.x / pairs;
-  if (rl >= rstep) return;
-  const int m0 = blockIdx.x * rows_per_block;
-  const int m1 = min(M, m0 + rows_per_block);
-  float s0 = 0.f, s1 = 0.f;
-  for (int m = m0 + rl; m < m1; m += rstep) {
-    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(dz + static_cast<size_t>(m) * N4 + 2 * cp);
-    s0 += __low2float(v);
-    s1 += __high2float(v);
-  }
-  atomicAdd(db + 2 * cp, s0);
-  atomicAdd(db + 2 * cp + 1, s1);
 }
 
 }  // namespace plc

@@ -27,7 +27,7 @@ def time_fn(fn, iters=20, warm=5):
     return ts[len(ts) // 2], ts[0]
 
 
-def main():
+def main():  # noqa: C901
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     B, cin, ch, H, W, k = (int(a) for a in args[:6]) if len(args) >= 6 else (32, 64, 64, 128, 128, 3)
     dev = torch.device("cuda:0")
