@@ -24,3 +24,4 @@ from .convlstm_oracle import (  # noqa: F401
     frontend_forward,
     nowcast_forward,
 )
+from . import loss_oracle  # noqa: F401,E402

@@ -2,7 +2,8 @@
 
 Import name: ``plconv`` (this directory's name has hyphens; ``plconv/__init__.py`` aliases it).
 """
-from . import _lib, build, functional, nn, parallel, rollout, training  # noqa: F401
+from . import _lib, build, functional, generator, nn, parallel, rollout, training  # noqa: F401
+from .generator import Generator  # noqa: F401
 from .nn import ConvLSTMCell, ConvLSTMStack, EncoderForecaster  # noqa: F401
 from .rollout import NowcastGenerator, NowcastRunner  # noqa: F401
 from ._lib import PLC_MODE_BF16_TC, PLC_MODE_FP32  # noqa: F401

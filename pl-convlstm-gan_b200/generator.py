@@ -1,0 +1,145 @@
+"""Drop-in for the reference ``Generator`` (src/models/generator.py:31-205) built on the native ConvLSTM cells.
+
+Same constructor, same ``forward(rain_lr, dem, lu, input_grid_size=None)``, same parameter names, so a reference
+checkpoint (``best_model.pth['model_state_dict']``, trainer.py:410-417) loads unchanged:
+    init_conv.*, cell1.conv.*, cell2.conv.*, dem_attn.conv.{0,2}.*, lu_attn.conv.{0,2}.*,
+    upsample_blocks.{i}.conv.*, post_process.{0,2}.*
+The recurrence (cell1/cell2 over T steps, generator.py:156-171) runs in libplc.so.  The NON-recurrent body
+(front-end conv, PixelShuffle upsampling, DEM/LU gating, output head) is SURVEY.md section 8f "next-1": here it is plain
+PyTorch, restructured but arithmetically identical -- batched over T (it has no recurrence) and with the
+time-invariant attention gates hoisted out of the T loop (attention.py:13,26 depend only on static inputs).
+Like the reference, ``upsample_blocks`` are created on first forward (generator.py:129-130; SURVEY.md section 5 gotcha 1);
+call ``materialize(scale)`` before ``load_state_dict`` when loading a checkpoint into a fresh model.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .nn import ConvLSTMCell
+
+
+def _coord_channels(x: torch.Tensor) -> torch.Tensor:
+    """coordconv.py:3-10: append row and column linspace(0, 1) planes."""
+    b, _, h, w = x.shape
+    rows = torch.linspace(0, 1, h, device=x.device, dtype=x.dtype).view(1, 1, h, 1).expand(b, 1, h, w)
+    cols = torch.linspace(0, 1, w, device=x.device, dtype=x.dtype).view(1, 1, 1, w).expand(b, 1, h, w)
+    return torch.cat([x, rows, cols], dim=1)
+
+
+class _Gate(nn.Module):
+    """DEMAttention / LUAttention (attention.py:3-26): x * sigmoid(conv1x1(relu(conv3x3(static)))).
+    ``gate(static)`` returns the multiplicative map so callers can compute it once per forward."""
+
+    def __init__(self, channels: int, static_channels: int):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Conv2d(static_channels, channels // 2, 3, padding=1), nn.ReLU(inplace=True),
+                                  nn.Conv2d(channels // 2, channels, 1), nn.Sigmoid())
+
+    def gate(self, static: torch.Tensor) -> torch.Tensor:
+        return self.conv(static)
+
+    def forward(self, x, static):
+        return x * self.gate(static)
+
+
+class _Up2(nn.Module):
+    """UpsampleBlock (generator.py:10-28): conv3x3 C -> 4C, PixelShuffle(2), ReLU."""
+
+    def __init__(self, channels: int):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels * 4, 3, padding=1)
+
+    def forward(self, x):
+        return F.relu(F.pixel_shuffle(self.conv(x), 2))
+
+
+class Generator(nn.Module):
+    def __init__(self, in_channels: int = 1, dem_channels: int = 1, lu_channels: int = 0,
+                 hidden_dims: Sequence[int] = (32, 64), target_grid_size=None, scale_factor=None, mode: str = "bf16"):
+        super().__init__()
+        self.hidden_dims = list(hidden_dims)
+        self.lu_channels = lu_channels
+        self.target_grid_size = target_grid_size if target_grid_size is not None else None
+        self.scale_factor = None if target_grid_size is not None else scale_factor      # generator.py:38-48
+        self.target_size = None
+        hd0, hd1 = self.hidden_dims
+        self.init_conv = nn.Conv2d(in_channels + 2, hd0, 3, padding=1)                 # generator.py:50-55
+        self.cell1 = ConvLSTMCell(hd0, hd0, mode=mode)                                 # generator.py:57
+        self.cell2 = ConvLSTMCell(hd0, hd1, mode=mode)                                 # generator.py:58
+        self.dem_attn = _Gate(hd1, dem_channels)                                       # generator.py:60
+        self.lu_attn = _Gate(hd1, lu_channels)                                         # generator.py:61
+        self.upsample_blocks = None                                                    # generator.py:64 (lazy)
+        self.post_process = nn.Sequential(nn.Conv2d(hd1, 32, 3, padding=1), nn.ReLU(inplace=True),
+                                          nn.Conv2d(32, 1, 3, padding=1))              # generator.py:67-71
+
+    def materialize(self, scale_factor: int, device=None) -> float:
+        """Create the x2 upsample blocks for an integer scale (generator.py:73-92); returns the residual factor."""
+        blocks, f = [], int(scale_factor)
+        while f >= 2:
+            blocks.append(_Up2(self.hidden_dims[1]))
+            f //= 2
+        self.upsample_blocks = nn.ModuleList(blocks)
+        if device is not None:
+            self.upsample_blocks.to(device)
+        return scale_factor / (2 ** len(blocks)) if scale_factor > 1 else 1
+
+    def forward(self, rain_lr: torch.Tensor, dem: torch.Tensor, lu: torch.Tensor,
+                input_grid_size: Optional[Tuple[float, float]] = None) -> torch.Tensor:
+        B, T, C, H, W = rain_lr.shape
+        dev = rain_lr.device
+        # ---- target resolution (generator.py:106-126)
+        if self.target_grid_size is not None and input_grid_size is not None:
+            sw = input_grid_size[0] / self.target_grid_size[0]
+            sh = input_grid_size[1] / self.target_grid_size[1]
+            self.target_size = (int(H * sh), int(W * sw))
+            scale = max(sh, sw)
+        elif self.scale_factor is not None:
+            scale, self.target_size = self.scale_factor, None
+        else:
+            scale, self.target_size = 1, None
+        if self.upsample_blocks is None:
+            remaining = self.materialize(int(scale), dev)                               # generator.py:129-130
+        else:
+            remaining = scale / (2 ** len(self.upsample_blocks))
+        final_hw = self.target_size if self.target_size is not None else (int(H * scale), int(W * scale))
+        # ---- static maps, once per forward (generator.py:143-153); gates are time-invariant
+        dem_hr = F.interpolate(dem, size=final_hw, mode="bilinear", align_corners=False)
+        lu_hr = F.interpolate(lu, size=final_hw, mode="nearest")
+        gate = self.dem_attn.gate(dem_hr) * self.lu_attn.gate(lu_hr)                    # generator.py:198-199
+
+        # ---- front-end for all T frames at once (generator.py:166-168)
+        x = F.relu(self.init_conv(_coord_channels(rain_lr.reshape(B * T, C, H, W))))
+        hd0, hd1 = self.hidden_dims
+        c1, c2 = self.cell1, self.cell2
+        xw = x.view(B, T, hd0, H, W).permute(1, 0, 3, 4, 2)                             # [T,B,H,W,C]
+        if c1.working_cin != hd0:
+            xw = F.pad(xw, (0, c1.working_cin - hd0))
+        xw = xw.to(c1.act_dtype).contiguous()
+        # ---- the recurrence (generator.py:156-171): zero state, cell1 then cell2 per step, in libplc.so
+        h1 = torch.zeros(B, H, W, hd0, device=dev, dtype=c1.act_dtype)
+        s1 = torch.zeros(B, H, W, hd0, device=dev, dtype=torch.float32)
+        h2 = torch.zeros(B, H, W, hd1, device=dev, dtype=c2.act_dtype)
+        s2 = torch.zeros(B, H, W, hd1, device=dev, dtype=torch.float32)
+        pad2 = c2.working_cin - hd0
+        tops = []
+        for t in range(T):
+            h1, s1 = c1.step_nhwc(xw[t], h1, s1)
+            h2, s2 = c2.step_nhwc(h1 if pad2 == 0 else F.pad(h1, (0, pad2)), h2, s2)
+            tops.append(h2)
+        feat = torch.stack(tops, dim=1).reshape(B * T, H, W, hd1).permute(0, 3, 1, 2).to(torch.float32)
+
+        # ---- tail, batched over T (generator.py:173-203)
+        for blk in self.upsample_blocks:
+            feat = blk(feat)
+        if remaining > 1:
+            feat = F.interpolate(feat, scale_factor=remaining, mode="bilinear", align_corners=False)
+        if self.target_size is not None:
+            feat = F.interpolate(feat, size=self.target_size, mode="bilinear", align_corners=False)
+        hh, ww = feat.shape[-2:]
+        feat = (feat.view(B, T, hd1, hh, ww) * gate.unsqueeze(1)).view(B * T, hd1, hh, ww)
+        out = self.post_process(feat)
+        return out.view(B, T, 1, hh, ww)                                                # generator.py:205

@@ -107,3 +107,45 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ------------------------------------------------------------------------------------------------
+# Full Generator + CombinedLoss rollout: state_dict copied AFTER one warm-up forward
+# (lazy upsample blocks, generator.py:129-130), non-negative station values (log1p weights).
+def gen_generator(name, seed, B, T, H, W, hd, scale, lu_ch, n_st):
+    from src.models.generator import Generator
+    from src.losses.combined_loss import CombinedLoss
+    torch.manual_seed(seed)
+    gen = Generator(in_channels=1, dem_channels=1, lu_channels=lu_ch, hidden_dims=list(hd), scale_factor=scale)
+    rain = torch.rand(B, T, 1, H, W) * 5.0
+    dem = torch.rand(B, 1, H * scale, W * scale)
+    lu = torch.rand(B, lu_ch, H * scale, W * scale)
+    with torch.no_grad():
+        gen(rain, dem, lu)                        # warm-up: creates upsample_blocks
+    sd = {k: np32(v) for k, v in gen.state_dict().items()}
+    s_coords = torch.stack([torch.randint(0, H, (n_st,)), torch.randint(0, W, (n_st,))], dim=1)
+    s_vals = torch.rand(T, n_st) * 20.0
+    s_vals[0, 0] = float("nan")                   # missing observation (fenhe_dataset.py keeps NaN for gaps)
+    pred = gen(rain, dem, lu)
+    loss_mod = CombinedLoss()
+    total, parts = loss_mod(pred, rain, s_coords, s_vals, scale_factor=scale)
+    total.backward()
+    grads = {"grad." + k: np32(p.grad) for k, p in gen.named_parameters() if p.grad is not None}
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        rain=np32(rain), dem=np32(dem), lu=np32(lu), s_coords=s_coords.numpy().astype(np.int64), s_vals=np32(s_vals),
+        pred=np32(pred), loss_total=np32(total), loss_point=np32(parts["point"]),
+        loss_conserve=np32(parts["conserve"]), loss_smooth=np32(parts["smooth"]),
+        loss_temporal=np32(parts["temporal"]), scale=np.int32(scale), hidden_dims=np.array(hd, dtype=np.int32),
+        **{"sd." + k: v for k, v in sd.items()}, **grads)
+
+
+GENERATOR_CASES = [
+    ("generator_b2_t3_10x12_h16_32_x2", 301, 2, 3, 10, 12, (16, 32), 2, 5, 7),
+    ("generator_b1_t2_8x8_h16_16_x1", 302, 1, 2, 8, 8, (16, 16), 1, 3, 4),
+]
+
+if __name__ == "__main__":
+    for case in GENERATOR_CASES:
+        gen_generator(*case)
+    print("wrote", len(GENERATOR_CASES), "generator fixtures")

@@ -1,0 +1,74 @@
+"""Drop-in Generator (recurrence in libplc.so) vs the UNMODIFIED reference Generator + CombinedLoss goldens:
+reference state_dict loads unchanged; predicted frames, the four loss terms and the gradients match."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files, load_golden
+from oracle import loss_oracle as L
+from test_cell_gpu import rel_err, report
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    """The non-recurrent body runs in torch (cuDNN): keep it true fp32 so the comparison isolates the recurrence
+    (disable TF32 when comparing fp32 results on GPU)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _build(g, mode, dev):
+    import plconv
+    hd = [int(v) for v in g["hidden_dims"]]
+    lu_ch = g["lu"].shape[1]
+    gen = plconv.Generator(in_channels=1, dem_channels=1, lu_channels=lu_ch, hidden_dims=hd,
+                           scale_factor=int(g["scale"]), mode=mode)
+    gen.materialize(int(g["scale"]))
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    assert sorted(sd) == sorted(gen.state_dict().keys()), "state_dict keys differ from the reference"
+    gen.load_state_dict(sd)                      # reference checkpoint layout, unchanged
+    return gen.to(dev)
+
+
+@pytest.mark.parametrize("path", golden_files("generator_"), ids=os.path.basename)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_generator_rollout_and_loss_vs_reference(path, mode, cuda_device):
+    g = load_golden(path)
+    gen = _build(g, mode, cuda_device)
+    rain, dem, lu = (torch.from_numpy(g[k]).to(cuda_device) for k in ("rain", "dem", "lu"))
+    pred = gen(rain, dem, lu)
+    assert tuple(pred.shape) == g["pred"].shape
+    tol_pred = 2e-4 if mode == "fp32" else 2e-2
+    assert rel_err(pred, torch.from_numpy(g["pred"])) < tol_pred, report("pred", pred, torch.from_numpy(g["pred"]))
+    total, parts = L.combined_loss(pred.cpu(), torch.from_numpy(g["rain"]), torch.from_numpy(g["s_coords"]),
+                                   torch.from_numpy(g["s_vals"]), scale_factor=int(g["scale"]))
+    # rollout loss tolerance (north_star "within a stated tolerance"): 1e-4 relative in fp32 mode, 1e-2 in bf16 mode
+    tol = 1e-4 if mode == "fp32" else 1e-2
+    assert abs(float(total.detach()) - float(g["loss_total"])) <= tol * abs(float(g["loss_total"]))
+    for k in ("point", "conserve"):
+        assert abs(float(parts[k].detach()) - float(g["loss_" + k])) <= tol * abs(float(g["loss_" + k])) + 1e-6, k
+
+
+@pytest.mark.parametrize("path", golden_files("generator_b2"), ids=os.path.basename)
+def test_generator_gradients_vs_reference_autograd(path, cuda_device):
+    """loss.backward() through the drop-in (BPTT in plc_cell_bwd) reproduces the reference's parameter gradients."""
+    g = load_golden(path)
+    gen = _build(g, "fp32", cuda_device)
+    rain, dem, lu = (torch.from_numpy(g[k]).to(cuda_device) for k in ("rain", "dem", "lu"))
+    pred = gen(rain, dem, lu)
+    total, _ = L.combined_loss(pred, rain, torch.from_numpy(g["s_coords"]).to(cuda_device),
+                               torch.from_numpy(g["s_vals"]).to(cuda_device), scale_factor=int(g["scale"]))
+    total.backward()
+    bad = []
+    for name, p in gen.named_parameters():
+        ref = torch.from_numpy(g["grad." + name])
+        if rel_err(p.grad, ref) >= 2e-3:
+            bad.append(report(name, p.grad, ref))
+    assert not bad, " | ".join(bad)

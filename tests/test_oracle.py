@@ -157,3 +157,15 @@ def test_oracle_matches_live_reference_cell():
     hr, cr = cell(x, h, c)
     ho, co = O.cell_forward(x, h, c, cell.conv.weight.detach(), cell.conv.bias.detach())
     assert torch.allclose(hr, ho, atol=1e-6) and torch.allclose(cr, co, atol=1e-6)
+
+
+# ---- CombinedLoss restatement pinned by the reference's own loss values --------------------------------------
+@pytest.mark.parametrize("path", golden_files("generator_"), ids=os.path.basename)
+def test_loss_oracle_matches_reference_golden(path):
+    from oracle import loss_oracle as L
+    g = load_golden(path)
+    total, parts = L.combined_loss(T(g["pred"]), T(g["rain"]), T(g["s_coords"]), T(g["s_vals"]),
+                                   scale_factor=int(g["scale"]))
+    for k in ("point", "conserve", "smooth", "temporal"):
+        assert abs(float(parts[k]) - float(g["loss_" + k])) <= 1e-5 * max(1.0, abs(float(g["loss_" + k]))), k
+    assert abs(float(total) - float(g["loss_total"])) <= 1e-5 * abs(float(g["loss_total"]))
