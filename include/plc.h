@@ -107,6 +107,12 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
                  const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc, float* db_acc,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- debug ---------------------------------------------------------------------------------
+ * Developer aid (tools/kprof.py): when set to a zeroed device buffer of at least 148*16 uint64, the tensor-core conv
+ * kernels record per-CTA cycle counters (MMA warp total / waiting for TMEM / waiting for TMA, epilogue busy / idle).
+ * NULL (default) disables it.  Not part of the reference-facing surface.                                   */
+int plc_debug_set_prof(void* device_buf_u64);
+
 /* ---- layout helpers (HBM-bound elementwise kernels) ---------------------------------------
  * The reference keeps NCHW fp32 tensors (generator.py:156-160).  These convert between that and
  * the NHWC working layout at sequence entry / exit.  `C_dst >= C_src` zero-pads channels.       */

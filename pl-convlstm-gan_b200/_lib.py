@@ -10,7 +10,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libplc.so")
+LIB_PATH = os.environ.get("PLC_LIB") or os.path.join(HERE, "libplc.so")   # PLC_LIB: developer override
 
 PLC_MODE_BF16_TC = 0
 PLC_MODE_FP32 = 1
@@ -35,6 +35,7 @@ SIGNATURES = {
     "plc_cell_fwd": (_int, [_dp] + [_vp] * 9),
     "plc_bwd_workspace_bytes": (_sz, [_dp]),
     "plc_cell_bwd": (_int, [_dp] + [_vp] * 15 + [_sz, _vp]),
+    "plc_debug_set_prof": (_int, [_vp]),
     "plc_nchw_f32_to_nhwc_bf16": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),
     "plc_nhwc_bf16_to_nchw_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
     "plc_frontend_fwd": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _int, _int, _int, _vp, _vp]),

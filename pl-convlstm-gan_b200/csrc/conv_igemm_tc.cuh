@@ -50,23 +50,39 @@ struct ConvTcParams {
   __nv_bfloat16* out0;       // [M, Cin] bf16 or nullptr           (PLAIN)
   __nv_bfloat16* out1;       // [M, Ntot-Cin] bf16 or nullptr      (PLAIN)
   int n_total;               // PLAIN: total valid output columns
+  unsigned long long* prof;  // debug: per-CTA cycle counters [gridDim][16] or nullptr (plc_debug_set_prof)
 };
 
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
 
-template <int N_TILE, int kCta = 1>
+// Forward tiles with all 64 channels (N_TILE = 256) leave through shared memory + TMA tensor stores: the per-thread
+// NHWC stores (one pixel per lane -> 32 scattered 16/32-byte pieces per instruction) were THE epilogue bottleneck
+// (4300 of 10000 cycles per tile); staged, the stores are three bulk copies issued by one thread.
+template <int N_TILE, int EPI>
+constexpr bool tma_store_epilogue() {
+#ifdef PLC_NO_TMA_STORE
+  return false;
+#else
+  return EPI == 0 /*EPI_LSTM_FWD*/ && N_TILE == 256;
+#endif
+}
+
+template <int N_TILE, int kCta = 1, int EPI = 2>
 struct ConvTcCfg {
+  static constexpr bool kTmaStore = tma_store_epilogue<N_TILE, EPI>();
+  // staging: c' fp32 as two [128 px][32 ch] boxes (2 x 16 KB) + h' bf16 as one [128 px][64 ch] box (16 KB)
+  static constexpr int kStoreBytes = kTmaStore ? 3 * 16384 : 0;
   // cta_group::2: the CTA pair shares one 256 x N_TILE accumulator tile; each CTA stages its own 128 pixels of A
   // and HALF of the B tile (N_TILE/2 packed-weight rows), so the per-SM operand feed drops from 48 to 32 KB / K-block.
   static constexpr int kBBytes = (N_TILE / kCta) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kAuxBytes = 4096 + 256;  // bias (<= 1024 floats) + barriers
-  static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - kAuxBytes;
+  static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - kAuxBytes - kStoreBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kAuxBytes + 1024;
   static constexpr int kTmemCols = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64) ? 64 : (2 * N_TILE <= 128) ? 128
                                    : (2 * N_TILE <= 256) ? 256 : 512;
   static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128/256");
@@ -92,16 +108,20 @@ __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int
 
 // epilogue warps: the LSTM epilogues are MUFU/latency heavy (5 transcendentals per element) and must finish a tile
 // faster than the tensor core produces the next one -> two warps per TMEM lane quadrant, alternating 16-channel chunks.
+// The forward epilogue works in 8-channel granules with 16 warps (4 per quadrant, 4 per SM sub-partition): it is
+// latency bound (TMEM load -> bias -> 5 dependent MUFU/FMA chains per element), so thread-level parallelism is what
+// gets a 128 x 64-channel tile through in less than the 9216 cycles the tensor core needs for the next one.
 template <int EPI>
-constexpr int epi_warps() { return EPI == EPI_PLAIN ? 4 : 8; }
+constexpr int epi_warps() { return EPI == EPI_PLAIN ? 4 : (EPI == EPI_LSTM_FWD ? 16 : 8); }
 template <int EPI>
 constexpr int conv_tc_threads() { return 128 + 32 * epi_warps<EPI>(); }
 
 template <int N_TILE, int EPI, int kCta>
 __global__ void __launch_bounds__(conv_tc_threads<EPI>(), 1)
 conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap tmap_a0,
-                     const __grid_constant__ CUtensorMap tmap_a1, const __grid_constant__ CUtensorMap tmap_b) {
-  using Cfg = ConvTcCfg<N_TILE, kCta>;
+                     const __grid_constant__ CUtensorMap tmap_a1, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1) {
+  using Cfg = ConvTcCfg<N_TILE, kCta, EPI>;
   constexpr int kStages = Cfg::kStages;
   constexpr int CH_TILE = N_TILE / 4;
 
@@ -111,8 +131,9 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  float* bias_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + 4096);
+  uint8_t* stage_out = smem + kStages * Cfg::kStageBytes;                 // TMA-store staging (1024-aligned)
+  float* bias_s = reinterpret_cast<float*>(stage_out + Cfg::kStoreBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + Cfg::kStoreBytes + 4096);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + kStages;            // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages;        // [2]
@@ -143,7 +164,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   }
   if (warp == 2) tmem_alloc<kCta>(tmem_ptr_s, Cfg::kTmemCols);
   if (EPI != EPI_PLAIN) {
-    for (int i = threadIdx.x; i < 4 * p.Ch; i += blockDim.x) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    // forward: sigmoid(x + b) = 0.5 * tanh(0.5 * x + 0.5 * b) + 0.5 -> stage HALF the bias of the i, f, o gates so the
+    // bias add folds into the FFMA that scales the pre-activation
+    for (int i = threadIdx.x; i < 4 * p.Ch; i += blockDim.x)
+      bias_s[i] = (p.bias ? p.bias[i] : 0.f) * ((EPI == EPI_LSTM_FWD && i < 3 * p.Ch) ? 0.5f : 1.f);
   }
   tc_fence_before();
   if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
@@ -199,15 +223,20 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), 0, 1024);
     uint32_t stage = 0, phase = 0;
     int it = 0;
+    long long t_empty = 0, t_full = 0, t0 = clock64();
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      long long ta = p.prof ? clock64() : 0;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tc_fence_after();
+      if (p.prof) t_empty += clock64() - ta;
       const uint32_t d_tmem = tmem_base + as * N_TILE;
       for (int kb = 0; kb < p.num_kb; ++kb) {
+        long long tb = p.prof ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (p.prof) t_full += clock64() - tb;
         if (elect_one()) {
           // descriptor start-address field is in 16-byte units
           const uint64_t adesc = adesc0 + stage * (kABytes >> 4);
@@ -230,15 +259,22 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 16 + 0] = clock64() - t0;   // MMA warp: total
+      p.prof[blockIdx.x * 16 + 1] = t_empty;          //           waiting for the epilogue to free TMEM
+      p.prof[blockIdx.x * 16 + 2] = t_full;           //           waiting for TMA data
+      p.prof[blockIdx.x * 16 + 3] = it;               //           tiles
+    }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     const int q = warp & 3;             // TMEM lane quadrant == warp_idx % 4
-    const int half = (warp - 4) >> 2;   // which of the kEpiWarps/4 warps of this quadrant
+    const int half = (warp - 4) >> 2;   // which of the kEpiWarps/4 warps of this quadrant (a.k.a. wq)
     constexpr int kChunkStep = kEpiWarps / 4;
     const int row = q * 32 + lane;
     const int ty = row >> p.tw_log2;
     const int tx = row & (p.tw - 1);
     int it = 0;
+    long long epi_t0 = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -260,27 +296,136 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       };
       constexpr int kLstmChunks = CH_TILE / 16;
       constexpr int kMaxMine = (kLstmChunks + kChunkStep - 1) / kChunkStep;
+      constexpr int kGran = CH_TILE / 8;                                   // forward: 8-channel granules
+      constexpr int kMaxGran = (kGran + kChunkStep - 1) / kChunkStep;
       // forward: fetch this thread's c_prev BEFORE waiting for the accumulator -> DRAM latency hides under the MMAs
-      float cpre[EPI == EPI_LSTM_FWD ? kMaxMine : 1][16];
+      float cpre[EPI == EPI_LSTM_FWD ? kMaxGran : 1][8];
       if constexpr (EPI == EPI_LSTM_FWD) {
 #pragma unroll
-        for (int m = 0; m < kMaxMine; ++m) {
-          const int cc = half + m * kChunkStep;
-          if (valid && cc < kLstmChunks) {
-            const float4* src = reinterpret_cast<const float4*>(p.c_prev + pix * p.Ch + n_tile * CH_TILE + cc * 16);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const float4 t = __ldg(src + v);
-              cpre[m][4 * v + 0] = t.x; cpre[m][4 * v + 1] = t.y; cpre[m][4 * v + 2] = t.z; cpre[m][4 * v + 3] = t.w;
-            }
+        for (int m = 0; m < kMaxGran; ++m) {
+          const int g = half + m * kChunkStep;
+          if (valid && g < kGran) {
+            const float4* src = reinterpret_cast<const float4*>(p.c_prev + pix * p.Ch + n_tile * CH_TILE + g * 8);
+            const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
+            cpre[m][0] = t0.x; cpre[m][1] = t0.y; cpre[m][2] = t0.z; cpre[m][3] = t0.w;
+            cpre[m][4] = t1.x; cpre[m][5] = t1.y; cpre[m][6] = t1.z; cpre[m][7] = t1.w;
           }
         }
       }
+      long long te = (p.prof && warp == 4) ? clock64() : 0;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
+      if (p.prof && warp == 4 && lane == 0) {
+        const long long now = clock64();
+        p.prof[blockIdx.x * 16 + 4] += now - te;                    // epilogue warp 4: waiting for an accumulator
+        if (it > 0) p.prof[blockIdx.x * 16 + 5] += te - epi_t0;     //                  busy (previous tile's work)
+        epi_t0 = now;
+      }
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * N_TILE;
 
-      if constexpr (EPI == EPI_LSTM_FWD || EPI == EPI_LSTM_BWD_GATES) {
+      if constexpr (EPI == EPI_LSTM_FWD) {
+        const int ch0 = n_tile * CH_TILE;
+        const bool issuer = (warp == 4) && (lane == 0);
+        if constexpr (Cfg::kTmaStore) {
+          // staging buffer free again?  (the issuer's previous bulk stores have finished reading it)
+          if (issuer) tma_store_wait_read();
+          named_bar_sync(1, 32 * kEpiWarps);
+        }
+#pragma unroll
+        for (int m = 0; m < kMaxGran; ++m) {
+          const int g = half + m * kChunkStep;
+          if (g >= kGran) break;
+          uint32_t vi[8], vf[8], vo[8], vg[8];
+          tmem_ld8(t_acc + 0 * CH_TILE + g * 8, vi);
+          tmem_ld8(t_acc + 1 * CH_TILE + g * 8, vf);
+          tmem_ld8(t_acc + 2 * CH_TILE + g * 8, vo);
+          tmem_ld8(t_acc + 3 * CH_TILE + g * 8, vg);
+          const int chb = ch0 + g * 8;
+          // (half-)bias of this granule: smem reads issued before the TMEM wait so both latencies overlap
+          float bi[8], bf[8], bo[8], bg[8];
+          {
+            const float4* s0 = reinterpret_cast<const float4*>(bias_s + 0 * p.Ch + chb);
+            const float4* s1 = reinterpret_cast<const float4*>(bias_s + 1 * p.Ch + chb);
+            const float4* s2 = reinterpret_cast<const float4*>(bias_s + 2 * p.Ch + chb);
+            const float4* s3 = reinterpret_cast<const float4*>(bias_s + 3 * p.Ch + chb);
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              const float4 a = s0[v], b4 = s1[v], c4 = s2[v], d4 = s3[v];
+              bi[4 * v] = a.x; bi[4 * v + 1] = a.y; bi[4 * v + 2] = a.z; bi[4 * v + 3] = a.w;
+              bf[4 * v] = b4.x; bf[4 * v + 1] = b4.y; bf[4 * v + 2] = b4.z; bf[4 * v + 3] = b4.w;
+              bo[4 * v] = c4.x; bo[4 * v + 1] = c4.y; bo[4 * v + 2] = c4.z; bo[4 * v + 3] = c4.w;
+              bg[4 * v] = d4.x; bg[4 * v + 1] = d4.y; bg[4 * v + 2] = d4.z; bg[4 * v + 3] = d4.w;
+            }
+          }
+          tmem_ld_wait();
+          if (g + kChunkStep >= kGran) release();
+          if (valid) {
+            const size_t off = pix * p.Ch + chb;
+            float cn[8];
+            uint32_t hp[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              float hv[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int jj = j + u;
+                // convlstm.py:21-24 (bias already halved for the sigmoid gates)
+                const float ig = fmaf(tanh_fast(fmaf(__uint_as_float(vi[jj]), 0.5f, bi[jj])), 0.5f, 0.5f);
+                const float fg = fmaf(tanh_fast(fmaf(__uint_as_float(vf[jj]), 0.5f, bf[jj])), 0.5f, 0.5f);
+                const float og = fmaf(tanh_fast(fmaf(__uint_as_float(vo[jj]), 0.5f, bo[jj])), 0.5f, 0.5f);
+                const float gt = tanh_fast(__uint_as_float(vg[jj]) + bg[jj]);
+                const float c2 = fmaf(fg, cpre[m][jj], ig * gt);       // convlstm.py:26
+                cn[jj] = c2;
+                hv[u] = og * tanh_fast(c2);                            // convlstm.py:27
+                vi[jj] = __float_as_uint(ig); vf[jj] = __float_as_uint(fg);
+                vo[jj] = __float_as_uint(og); vg[jj] = __float_as_uint(gt);
+              }
+              hp[j >> 1] = pack_bf16x2(hv[0], hv[1]);
+            }
+            if constexpr (Cfg::kTmaStore) {
+              // SWIZZLE_128B staging: 16-byte chunk index XOR (row % 8) -> conflict-free st.shared.v4
+              const uint32_t sw = row & 7;
+              const uint32_t cb = smem_u32(stage_out) + (g >> 2) * 16384 + row * 128;
+              const uint32_t j0 = (g & 3) * 2;
+              st_shared_v4(cb + ((j0 ^ sw) << 4), __float_as_uint(cn[0]), __float_as_uint(cn[1]),
+                           __float_as_uint(cn[2]), __float_as_uint(cn[3]));
+              st_shared_v4(cb + (((j0 + 1) ^ sw) << 4), __float_as_uint(cn[4]), __float_as_uint(cn[5]),
+                           __float_as_uint(cn[6]), __float_as_uint(cn[7]));
+              st_shared_v4(smem_u32(stage_out) + 2 * 16384 + row * 128 + ((static_cast<uint32_t>(g) ^ sw) << 4), hp[0],
+                           hp[1], hp[2], hp[3]);
+            } else {
+              float4* cdst = reinterpret_cast<float4*>(p.c_out + off);
+              cdst[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+              cdst[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+              *reinterpret_cast<uint4*>(p.h_out + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            }
+            if (p.gates_out) {
+              __nv_bfloat16* gbase = p.gates_out + pix * (4 * p.Ch) + chb;
+#pragma unroll
+              for (int gate = 0; gate < 4; ++gate) {
+                const uint32_t* src = gate == 0 ? vi : gate == 1 ? vf : gate == 2 ? vo : vg;
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1]));
+                o.y = pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3]));
+                o.z = pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5]));
+                o.w = pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7]));
+                *reinterpret_cast<uint4*>(gbase + gate * p.Ch) = o;
+              }
+            }
+          }
+        }
+        if constexpr (Cfg::kTmaStore) {
+          fence_proxy_async_smem();               // my st.shared -> visible to the TMA (async proxy)
+          named_bar_sync(1, 32 * kEpiWarps);
+          if (issuer) {                           // OOB rows / images (ragged tiles, odd tail pair) are clipped by TMA
+            const uint32_t so = smem_u32(stage_out);
+            tma_store_4d(&tmap_o0, so, ch0, x0, y0, b);
+            tma_store_4d(&tmap_o0, so + 16384, ch0 + 32, x0, y0, b);
+            tma_store_4d(&tmap_o1, so + 2 * 16384, ch0, x0, y0, b);
+            tma_store_commit();
+          }
+        }
+      } else if constexpr (EPI == EPI_LSTM_BWD_GATES) {
         const int ch0 = n_tile * CH_TILE;
 #pragma unroll
         for (int m = 0; m < kMaxMine; ++m) {
@@ -476,6 +621,9 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         }
       }
       if (!released) release();   // warps without a chunk for this tile shape
+    }
+    if constexpr (Cfg::kTmaStore) {
+      if (warp == 4 && lane == 0) tma_store_wait_all();   // bulk stores complete before the CTA retires
     }
   }
 

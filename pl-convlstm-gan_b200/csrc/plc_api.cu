@@ -65,14 +65,17 @@ int sm_count() {
 }
 
 // NHWC bf16 activation [B,H,W,C] as a 4-D tensor map; box = [64 ch, tw, th, 1], SWIZZLE_128B.
-int make_tmap_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int tw, int th) {
+int make_tmap_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int tw, int th, int esize = 2,
+                  int box_c = 64) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t es = (cuuint64_t)esize;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)tw, (cuuint32_t)th, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -260,10 +263,15 @@ int pick_cta_group(int num_m_tiles) {
   return num_m_tiles >= 2 * sm_count() ? 2 : 1;
 }
 
+// debug cycle counters (tools/kprof.py): a caller-provided device buffer of 148*16 u64, zeroed by the caller
+unsigned long long* g_prof_buf = nullptr;
+
 template <int NT, int EPI, int CTA>
-int launch_conv_tc_inst(const plc::ConvTcParams& p, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                        cudaStream_t st) {
-  using Cfg = plc::ConvTcCfg<NT, CTA>;
+int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                        const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st) {
+  using Cfg = plc::ConvTcCfg<NT, CTA, EPI>;
+  plc::ConvTcParams p = p_in;
+  p.prof = g_prof_buf;
   auto kfn = plc::conv_igemm_tc_kernel<NT, EPI, CTA>;
   PLC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int tiles = CTA == 2 ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_tiles;
@@ -282,17 +290,18 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p, const CUtensorMap& a0, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PLC_CUDA(cudaLaunchKernelEx(&cfg, kfn, p, a0, a1, b));
+  PLC_CUDA(cudaLaunchKernelEx(&cfg, kfn, p, a0, a1, b, o0, o1));
   return PLC_OK;
 }
 
+// o0 / o1: output tensor maps of the TMA-store epilogue (forward, N_TILE = 256); ignored by the other instantiations
 template <int EPI>
 int launch_conv_tc(int n_tile, int cta, const plc::ConvTcParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
-                   const CUtensorMap& b, cudaStream_t st) {
+                   const CUtensorMap& b, const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st) {
 #define PLC_LAUNCH_TC(NT)                                                                     \
   case NT:                                                                                    \
-    return cta == 2 ? launch_conv_tc_inst<NT, EPI, 2>(p, a0, a1, b, st)                       \
-                    : launch_conv_tc_inst<NT, EPI, 1>(p, a0, a1, b, st);
+    return cta == 2 ? launch_conv_tc_inst<NT, EPI, 2>(p, a0, a1, b, o0, o1, st)               \
+                    : launch_conv_tc_inst<NT, EPI, 1>(p, a0, a1, b, o0, o1, st);
   switch (n_tile) {
     PLC_LAUNCH_TC(64)
     PLC_LAUNCH_TC(128)
@@ -477,7 +486,12 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   }
   const int cta = pick_cta_group(p.num_m_tiles);
   if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile / cta))) return rc;
-  return launch_conv_tc<plc::EPI_LSTM_FWD>(g.n_tile, cta, p, ta0, ta1, tb, st);
+  CUtensorMap to0 = ta1, to1 = ta1;
+  if (plc::tma_store_epilogue<256, plc::EPI_LSTM_FWD>() && g.n_tile == 256) {
+    if ((rc = make_tmap_act(&to0, c_out, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
+    if ((rc = make_tmap_act(&to1, h_out, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, 64))) return rc;
+  }
+  return launch_conv_tc<plc::EPI_LSTM_FWD>(g.n_tile, cta, p, ta0, ta1, tb, to0, to1, st);
 }
 
 size_t plc_bwd_workspace_bytes(const PlcCellDesc* d) {
@@ -581,7 +595,7 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   }
   const int cta = pick_cta_group(p.num_m_tiles);
   if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile / cta))) return rc;
-  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, st))) return rc;
+  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, ta1, ta1, st))) return rc;
 
   // 2) dgrad: conv of dZ (4Ch channels) with the flipped/transposed image -> dx, dh_prev
   if (dx || dh_prev) {
@@ -600,13 +614,18 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     CUtensorMap tz, tbd;
     if ((rc = make_tmap_act(&tz, workspace, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th))) return rc;
     if ((rc = make_tmap_mat(&tbd, w_packed_dgrad, n_total, (long)q.num_kb * 64, 64, nt / cta))) return rc;
-    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tbd, st))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tbd, tz, tz, st))) return rc;
   }
 
   // 3) wgrad + bias grad
   if (dW_acc) {
     if ((rc = launch_wgrad_tc(d, x, h_prev, workspace, dW_acc, d->has_bias ? db_acc : nullptr, st))) return rc;
   }
+  return PLC_OK;
+}
+
+int plc_debug_set_prof(void* device_buf_u64) {
+  g_prof_buf = static_cast<unsigned long long*>(device_buf_u64);
   return PLC_OK;
 }
 
