@@ -203,18 +203,13 @@ def run_train(args):
     torch.manual_seed(1234)                       # identical weights on every rank
     stack = plconv.ConvLSTMStack(cfg["C"], cfg["hidden"], cfg["k"], True, "bf16").to(dev)
     torch.manual_seed(1234 + rank)
-    xs = [torch.relu(torch.randn(B, cfg["H"], cfg["W"], cfg["C"], device=dev)).to(torch.bfloat16)
-          for _ in range(cfg["T"])]
-    tgt = [torch.rand(B, cfg["H"], cfg["W"], cfg["hidden"][-1], device=dev).to(torch.bfloat16)
-           for _ in range(cfg["T"])]
+    xs = torch.relu(torch.randn(cfg["T"], B, cfg["H"], cfg["W"], cfg["C"], device=dev)).to(torch.bfloat16)
+    tgt = torch.rand(cfg["T"], B, cfg["H"], cfg["W"], cfg["hidden"][-1], device=dev).to(torch.bfloat16)
     step = TrainStep(stack, [c.parameters() for c in stack.cells], lr=5e-4, grad_clip_norm=0.5)
 
     def forward_loss():
-        outs, _ = stack.run_nhwc(xs)
-        loss = 0.0
-        for o, t in zip(outs, tgt):
-            loss = loss + (o - t).float().pow(2).mean()
-        return loss / len(outs)
+        out, _ = stack.run_seq(xs)                 # fused rollout: one autograd node, explicit BPTT
+        return (out - tgt).float().pow(2).mean()
 
     def barrier():
         if world > 1:

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .nn import ConvLSTMCell
+from .nn import ConvLSTMCell, _StackRolloutFn
 
 
 def _coord_channels(x: torch.Tensor) -> torch.Tensor:
@@ -119,18 +119,16 @@ class Generator(nn.Module):
         if c1.working_cin != hd0:
             xw = F.pad(xw, (0, c1.working_cin - hd0))
         xw = xw.to(c1.act_dtype).contiguous()
-        # ---- the recurrence (generator.py:156-171): zero state, cell1 then cell2 per step, in libplc.so
-        h1 = torch.zeros(B, H, W, hd0, device=dev, dtype=c1.act_dtype)
-        s1 = torch.zeros(B, H, W, hd0, device=dev, dtype=torch.float32)
-        h2 = torch.zeros(B, H, W, hd1, device=dev, dtype=c2.act_dtype)
-        s2 = torch.zeros(B, H, W, hd1, device=dev, dtype=torch.float32)
-        pad2 = c2.working_cin - hd0
-        tops = []
-        for t in range(T):
-            h1, s1 = c1.step_nhwc(xw[t], h1, s1)
-            h2, s2 = c2.step_nhwc(h1 if pad2 == 0 else F.pad(h1, (0, pad2)), h2, s2)
-            tops.append(h2)
-        feat = torch.stack(tops, dim=1).reshape(B * T, H, W, hd1).permute(0, 3, 1, 2).to(torch.float32)
+        # ---- the recurrence (generator.py:156-171): zero state, cell1 then cell2 per step, in libplc.so;
+        #      one fused autograd node for all T steps (explicit BPTT in its backward)
+        zeros = [torch.zeros(B, H, W, hd0, device=dev, dtype=c1.act_dtype),
+                 torch.zeros(B, H, W, hd0, device=dev, dtype=torch.float32),
+                 torch.zeros(B, H, W, hd1, device=dev, dtype=c2.act_dtype),
+                 torch.zeros(B, H, W, hd1, device=dev, dtype=torch.float32)]
+        outs = _StackRolloutFn.apply([c1, c2], T, xw, *zeros, c1.conv.weight, c1.conv.bias, c2.conv.weight,
+                                     c2.conv.bias)
+        tops = outs[0]                                                                  # [T,B,H,W,hd1]
+        feat = tops.permute(1, 0, 4, 2, 3).reshape(B * T, hd1, H, W).to(torch.float32)
 
         # ---- tail, batched over T (generator.py:173-203)
         for blk in self.upsample_blocks:

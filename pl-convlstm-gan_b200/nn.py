@@ -146,6 +146,111 @@ class ConvLSTMCell(nn.Module):
         return h2.to(out_dtype).permute(0, 3, 1, 2), c2.to(out_dtype).permute(0, 3, 1, 2)
 
 
+class _StackRolloutFn(torch.autograd.Function):
+    """The whole stacked T-step rollout (generator.py:156-171) as ONE autograd node.
+
+    forward : T x L fused cell steps into preallocated state rings  h[l][0..T], c[l][0..T]  (index 0 = initial state).
+    backward: explicit BPTT -- per cell step one plc_cell_bwd with
+              dh = gradient from the layer above / the loss, dh2 = recurrent gradient from step t+1 (summed inside the
+              kernel), dW / db accumulated in place over all T steps.  No per-step autograd nodes, no per-step
+              allocations, gates recomputed from the saved (x, h_prev, c_prev).
+    Inputs : xs [T,B,H,W,Cin'] or None, then (h0_l, c0_l) per layer, then (weight_l, bias_l) per layer.
+    Outputs: top-layer h for every step [T,B,H,W,Ch_L], then final (h_l, c_l) per layer.
+    """
+
+    @staticmethod
+    def forward(ctx, cells, T, xs, *tensors):
+        L = len(cells)
+        states, params = tensors[:2 * L], tensors[2 * L:]
+        need_grad = torch.is_grad_enabled()
+        pws = [c._packed(need_dgrad=need_grad) for c in cells]
+        B, H, W, _ = states[0].shape
+        dev = states[0].device
+        hs, cs = [], []
+        for l, cell in enumerate(cells):
+            h_ring = torch.empty(T + 1, B, H, W, cell.hidden_dim, device=dev, dtype=cell.act_dtype)
+            c_ring = torch.empty(T + 1, B, H, W, cell.hidden_dim, device=dev, dtype=torch.float32)
+            h_ring[0].copy_(states[2 * l])
+            c_ring[0].copy_(states[2 * l + 1])
+            hs.append(h_ring)
+            cs.append(c_ring)
+        for t in range(T):                                   # generator.py:164
+            inp = None if xs is None else xs[t]
+            for l in range(L):                               # generator.py:170-171
+                F.cell_forward(inp, hs[l][t], cs[l][t], pws[l], h_out=hs[l][t + 1], c_out=cs[l][t + 1])
+                inp = hs[l][t + 1]
+        ctx.cells, ctx.T, ctx.pws = cells, T, pws
+        ctx.xs, ctx.hs, ctx.cs = xs, hs, cs
+        ctx.x_needs_grad = xs is not None and xs.requires_grad
+        ctx.state_needs_grad = [s.requires_grad for s in states]
+        outs = [hs[L - 1][1:]]
+        for l in range(L):
+            outs += [hs[l][T], cs[l][T]]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d_out, *d_final):
+        cells, T, xs, hs, cs = ctx.cells, ctx.T, ctx.xs, ctx.hs, ctx.cs
+        L = len(cells)
+        pws = [pw if pw.dgrad is not None else c._packed(need_dgrad=True) for pw, c in zip(ctx.pws, cells)]
+        B, H, W, _ = hs[0][0].shape
+        dev = hs[0].device
+        dW = [torch.zeros(4 * c.hidden_dim, pw.Cin + c.hidden_dim, pw.k, pw.k, device=dev) for c, pw in zip(cells, pws)]
+        db = [torch.zeros(4 * c.hidden_dim, device=dev) if pw.bias is not None else None for c, pw in zip(cells, pws)]
+        ws = [F.bwd_workspace(B, H, W, pw, dev) for pw in pws]
+        # recurrent carries: dh ping-pong (read as dh2 while the next dh_prev is written), dc in place
+        dh_buf = [[torch.empty_like(hs[l][0]) for _ in range(2)] for l in range(L)]
+        dc_buf = [torch.empty_like(cs[l][0]) for l in range(L)]
+        dx_buf = [torch.empty(B, H, W, pws[l].Cin, device=dev, dtype=cells[l].act_dtype) if pws[l].Cin else None
+                  for l in range(L)]
+        dh_carry = [None] * L
+        dc_carry = [None] * L
+        for l in range(L):
+            dhT, dcT = d_final[2 * l], d_final[2 * l + 1]
+            if dhT is not None:
+                dh_carry[l] = dhT.contiguous()
+            if dcT is not None:
+                dc_buf[l].copy_(dcT)
+                dc_carry[l] = dc_buf[l]
+        dxs = torch.empty_like(xs) if ctx.x_needs_grad else None
+        zero_top = None
+        flip = [0] * L
+        for t in reversed(range(T)):
+            d_above = None if d_out is None else d_out[t]
+            for l in reversed(range(L)):
+                x_in = (xs[t] if xs is not None else None) if l == 0 else hs[l - 1][t + 1]
+                dh, dh2 = d_above, dh_carry[l]
+                if dh is None:
+                    dh, dh2 = dh2, None
+                if dh is None:
+                    if zero_top is None or zero_top.shape != hs[l][0].shape:
+                        zero_top = torch.zeros_like(hs[l][0])
+                    dh = zero_top
+                if not dh.is_contiguous():
+                    dh = dh.contiguous()
+                need_dx = pws[l].Cin > 0 and (l > 0 or ctx.x_needs_grad)
+                out_dx = None
+                if need_dx:
+                    out_dx = dxs[t] if (l == 0) else dx_buf[l]
+                dst = dh_buf[l][flip[l]]
+                F.cell_backward(x_in, hs[l][t], cs[l][t], pws[l], dh, dh2, dc_carry[l], dW[l], db[l], need_dx=need_dx,
+                                workspace=ws[l], dx=out_dx, dh_prev=dst, dc_prev=dc_buf[l])
+                dh_carry[l], dc_carry[l] = dst, dc_buf[l]
+                flip[l] ^= 1
+                d_above = out_dx if l > 0 else None
+        grads = [None, None, dxs]
+        for l in range(L):
+            grads.append(dh_carry[l] if ctx.state_needs_grad[2 * l] else None)
+            grads.append(dc_carry[l] if ctx.state_needs_grad[2 * l + 1] else None)
+        for l, cell in enumerate(cells):
+            g = dW[l]
+            if pws[l].Cin != cell.input_dim:                 # drop zero-padded x channels
+                g = torch.cat([g[:, :cell.input_dim], g[:, pws[l].Cin:]], dim=1)
+            grads.append(g.to(cell.conv.weight.dtype))
+            grads.append(None if cell.conv.bias is None else db[l].to(cell.conv.bias.dtype))
+        return tuple(grads)
+
+
 class ConvLSTMStack(nn.Module):
     """L stacked cells run over T steps (generator.py:156-171 generalised).
 
@@ -191,6 +296,21 @@ class ConvLSTMStack(nn.Module):
             outs.append(inp)
         return outs, state
 
+    def run_seq(self, xs: Optional[Tensor], state=None, steps: Optional[int] = None):
+        """Fused rollout: xs [T,B,H,W,working_cin] (one contiguous tensor) or None with ``steps``.
+        Returns (top-layer h for every step [T,B,H,W,Ch_L], final state); one autograd node for the whole rollout."""
+        T = steps if xs is None else xs.shape[0]
+        if state is None:
+            _, B, H, W, _ = xs.shape
+            state = self.zero_state(B, H, W, xs.device)
+        flat_state = [t for hc in state for t in hc]
+        params = []
+        for c in self.cells:
+            params += [c.conv.weight, c.conv.bias]
+        outs = _StackRolloutFn.apply(list(self.cells), T, xs, *flat_state, *params)
+        final = [(outs[1 + 2 * l], outs[2 + 2 * l]) for l in range(len(self.cells))]
+        return outs[0], final
+
     def forward(self, x_seq: Tensor, state=None):
         """x_seq: logical [B, T, C, H, W] (fp32, reference layout).  Returns the top layer's h for every
         step as logical [B, T, Ch_L, H, W] fp32, and the final working-layout state."""
@@ -203,9 +323,8 @@ class ConvLSTMStack(nn.Module):
         if c0.working_cin != C:
             xs = torch.nn.functional.pad(xs, (0, c0.working_cin - C))
         xs = xs.to(c0.act_dtype).contiguous()
-        outs, state = self.run_nhwc([xs[t] for t in range(T)], state)
-        out = torch.stack(outs, dim=1)                    # [B,T,H,W,Ch]
-        return out.to(torch.float32).permute(0, 1, 4, 2, 3), state
+        out, state = self.run_seq(xs, state)              # [T,B,H,W,Ch]
+        return out.to(torch.float32).permute(1, 0, 4, 2, 3), state
 
 
 class EncoderForecaster(nn.Module):
@@ -222,6 +341,5 @@ class EncoderForecaster(nn.Module):
     def forward(self, x_seq: Tensor, t_out: Optional[int] = None) -> Tensor:
         t_out = self.t_out if t_out is None else t_out
         _, state = self.encoder(x_seq)
-        outs, _ = self.forecaster.run_nhwc(None, state, steps=t_out)
-        out = torch.stack(outs, dim=1)
-        return out.to(torch.float32).permute(0, 1, 4, 2, 3)
+        out, _ = self.forecaster.run_seq(None, state, steps=t_out)
+        return out.to(torch.float32).permute(1, 0, 4, 2, 3)
