@@ -132,6 +132,11 @@ int plc_frontend_fwd(const float* frames, int N, int Cf, int H, int W, const flo
 int plc_head_fwd(const void* h, long npix, int C, const float* w, const float* bias, int mode, float* out,
                  void* stream);
 
+/* backward of plc_head_fwd (bf16 mode): dh [npix, C] bf16 = dy * w;  dw_acc [C] += sum dy * h;  db_acc [1] += sum dy
+ * (db_acc may be NULL).  dy [npix] fp32.                                                                       */
+int plc_head_bwd(const void* h, long npix, int C, const float* w, const float* dy, void* dh, float* dw_acc,
+                 float* db_acc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

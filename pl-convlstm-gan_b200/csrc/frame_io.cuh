@@ -153,4 +153,51 @@ __global__ void head_kernel(const TIn* __restrict__ h, const float* __restrict__
   out[p] = acc;
 }
 
+// Backward of the 1x1 head: y[p] = sum_c h[p][c] * w[c] + b
+//   dh[p][c] = dy[p] * w[c]  (bf16, coalesced: G = C/8 lanes per pixel)
+//   dw[c]   += sum_p dy[p] * h[p][c],   db += sum_p dy[p]       (block partial sums -> atomics)
+template <int G>
+__global__ void __launch_bounds__(256) head_bwd_kernel_bf16(const __nv_bfloat16* __restrict__ h,
+                                                            const float* __restrict__ w, const float* __restrict__ dy,
+                                                            __nv_bfloat16* __restrict__ dh, float* __restrict__ dw,
+                                                            float* __restrict__ db, size_t npix) {
+  __shared__ float red[256 * 8];
+  const int g = threadIdx.x % G;
+  float wv[8], acc[8], bsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { wv[j] = __ldg(w + g * 8 + j); acc[j] = 0.f; }
+  const size_t stride = static_cast<size_t>(gridDim.x) * (blockDim.x / G);
+  for (size_t p = static_cast<size_t>(blockIdx.x) * (blockDim.x / G) + threadIdx.x / G; p < npix; p += stride) {
+    const float d = __ldg(dy + p);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(h + p * (G * 8) + g * 8));
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&u[j]);
+      acc[2 * j] = fmaf(d, __low2float(t), acc[2 * j]);
+      acc[2 * j + 1] = fmaf(d, __high2float(t), acc[2 * j + 1]);
+      const __nv_bfloat162 r = __floats2bfloat162_rn(d * wv[2 * j], d * wv[2 * j + 1]);
+      o[j] = *reinterpret_cast<const uint32_t*>(&r);
+    }
+    *reinterpret_cast<uint4*>(dh + p * (G * 8) + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    if (g == 0) bsum += d;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  // threads 0 .. C-1 reduce channel c = t over the blockDim/G pixel lanes
+  const int C = G * 8;
+  if (threadIdx.x < C) {
+    const int gg = threadIdx.x / 8, jj = threadIdx.x % 8;
+    float s = 0.f;
+    for (int l = 0; l < blockDim.x / G; ++l) s += red[(l * G + gg) * 8 + jj];
+    atomicAdd(dw + threadIdx.x, s);
+  }
+  if (db) {
+    for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    if ((threadIdx.x & 31) == 0 && bsum != 0.f) atomicAdd(db, bsum);
+  }
+}
+
 }  // namespace plc

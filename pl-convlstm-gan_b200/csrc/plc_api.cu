@@ -706,4 +706,22 @@ int plc_head_fwd(const void* h, long npix, int C, const float* w, const float* b
   return PLC_OK;
 }
 
+int plc_head_bwd(const void* h, long npix, int C, const float* w, const float* dy, void* dh, float* dw_acc,
+                 float* db_acc, void* stream) {
+  if (!h || !w || !dy || !dh || !dw_acc) return fail(PLC_ERR_NULL_ARG, "plc_head_bwd: null pointer");
+  const int G = C / 8;
+  if (npix <= 0 || C % 8 || (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32))
+    return fail(PLC_ERR_UNSUPPORTED, "plc_head_bwd: C must be 8, 16, 32, 64, 128 or 256 (got %d)", C);
+  if (!aligned16(h) || !aligned16(dh)) return fail(PLC_ERR_ALIGNMENT, "plc_head_bwd: h/dh must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* hb = static_cast<const __nv_bfloat16*>(h);
+  __nv_bfloat16* dhb = static_cast<__nv_bfloat16*>(dh);
+  const int blocks = sm_count() * 8;
+#define PLC_HB(GG) case GG: plc::head_bwd_kernel_bf16<GG><<<blocks, 256, 0, st>>>(hb, w, dy, dhb, dw_acc, db_acc, (size_t)npix); break;
+  switch (G) { PLC_HB(1) PLC_HB(2) PLC_HB(4) PLC_HB(8) PLC_HB(16) PLC_HB(32) }
+#undef PLC_HB
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
 }  // extern "C"

@@ -207,3 +207,40 @@ def head_forward(h: Tensor, weight: Tensor, bias: Optional[Tensor], mode: int, o
         out = torch.empty(h.shape[:-1], dtype=torch.float32, device=h.device)
     _lib.check(lib.plc_head_fwd(_ptr(h), npix, C, _ptr(w), _ptr(b), mode, _ptr(out), _stream()), "plc_head_fwd")
     return out
+
+
+class _HeadFn(torch.autograd.Function):
+    """Differentiable 1x1 head on working-layout h [..., C] -> fp32 [...] (plc_head_fwd / plc_head_bwd)."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, mode):
+        out = head_forward(h, weight, bias, mode)
+        ctx.save_for_backward(h, weight)
+        ctx.has_bias, ctx.mode = bias is not None, mode
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, weight = ctx.saved_tensors
+        lib = _lib.load()
+        C = h.shape[-1]
+        npix = h.numel() // C
+        if ctx.mode != PLC_MODE_BF16_TC:
+            w = weight.reshape(-1).to(torch.float32)
+            dyf = dy.to(torch.float32)
+            dh = dyf.unsqueeze(-1) * w
+            dw = (dyf.reshape(-1, 1) * h.reshape(-1, C).to(torch.float32)).sum(0)
+            return dh.to(h.dtype), dw.reshape(weight.shape).to(weight.dtype), (dyf.sum().reshape(1) if ctx.has_bias else None), None
+        dyc = dy.to(torch.float32).contiguous()
+        w = weight.detach().to(torch.float32).reshape(-1).contiguous()
+        dh = torch.empty_like(h)
+        dw = torch.zeros(C, dtype=torch.float32, device=h.device)
+        db = torch.zeros(1, dtype=torch.float32, device=h.device) if ctx.has_bias else None
+        _lib.check(lib.plc_head_bwd(_ptr(h), npix, C, _ptr(w), _ptr(dyc), _ptr(dh), _ptr(dw), _ptr(db), _stream()),
+                   "plc_head_bwd")
+        return dh, dw.reshape(weight.shape).to(weight.dtype), db, None
+
+
+def head(h: Tensor, weight: Tensor, bias: Optional[Tensor], mode: int) -> Tensor:
+    """Differentiable 1x1 head: h [..., C] (contiguous, working layout) -> fp32 [...]."""
+    return _HeadFn.apply(h.contiguous(), weight, bias, mode)

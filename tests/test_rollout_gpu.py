@@ -103,3 +103,24 @@ def test_nowcast_generator_vs_eager_spec(mode, cuda_device):
     # running twice from the same input is idempotent (state is re-zeroed: generator.py:156-160)
     out2 = runner.run(frames.to(cuda_device)).cpu()
     assert torch.equal(out, out2)
+
+
+def test_head_forward_backward_vs_torch(cuda_device):
+    """1x1 output head (repo-defined): plc_head_fwd / plc_head_bwd vs a plain fp32 torch restatement."""
+    import plconv
+    from plconv import functional as PF
+    torch.manual_seed(3)
+    h = torch.randn(2, 3, 9, 11, 64, device=cuda_device).to(torch.bfloat16).requires_grad_()
+    conv = torch.nn.Conv2d(64, 1, 1).to(cuda_device)
+    y = PF.head(h, conv.weight, conv.bias, plconv.PLC_MODE_BF16_TC)
+    gy = torch.randn_like(y)
+    (y * gy).sum().backward()
+    hf = h.detach().float().requires_grad_()
+    w = conv.weight.detach().clone().requires_grad_()
+    b = conv.bias.detach().clone().requires_grad_()
+    y_ref = (hf * w.reshape(-1)).sum(-1) + b
+    (y_ref * gy).sum().backward()
+    assert rel_err(y, y_ref) < 1e-5
+    assert rel_err(h.grad, hf.grad) < 1e-2            # bf16 output rounding
+    assert rel_err(conv.weight.grad.reshape(-1), w.grad.reshape(-1)) < 1e-4
+    assert rel_err(conv.bias.grad, b.grad) < 1e-4
