@@ -65,14 +65,15 @@ constexpr bool tma_store_epilogue() {
 #ifdef PLC_NO_TMA_STORE
   return false;
 #else
-  return EPI == 0 /*EPI_LSTM_FWD*/ && N_TILE == 256;
+  return (EPI == 0 /*EPI_LSTM_FWD*/ || EPI == 1 /*EPI_LSTM_BWD_GATES*/) && N_TILE == 256;
 #endif
 }
 
 template <int N_TILE, int kCta = 1, int EPI = 2>
 struct ConvTcCfg {
   static constexpr bool kTmaStore = tma_store_epilogue<N_TILE, EPI>();
-  // staging: c' fp32 as two [128 px][32 ch] boxes (2 x 16 KB) + h' bf16 as one [128 px][64 ch] box (16 KB)
+  // staging (forward): c' fp32 as two [128 px][32 ch] boxes (2 x 16 KB) + h' bf16 as one [128 px][64 ch] box (16 KB)
+  // staging (bwd gates, per 32-channel half): dZ bf16 as four [128 px][32 ch] boxes (4 x 8 KB) + dc_prev fp32 (16 KB)
   static constexpr int kStoreBytes = kTmaStore ? 3 * 16384 : 0;
   // cta_group::2: the CTA pair shares one 256 x N_TILE accumulator tile; each CTA stages its own 128 pixels of A
   // and HALF of the B tile (N_TILE/2 packed-weight rows), so the per-SM operand feed drops from 48 to 32 KB / K-block.
@@ -105,6 +106,9 @@ __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int
   y0 = ty * p.th;
   x0 = tx * p.tw;
 }
+
+// per-granule operands of the gate-gradient epilogue (8 channels of one pixel)
+struct GateIn { float4 c0, c1, d0, d1; uint4 dh, dh2; };
 
 // epilogue warps: the LSTM epilogues are MUFU/latency heavy (5 transcendentals per element) and must finish a tile
 // faster than the tensor core produces the next one -> two warps per TMEM lane quadrant, alternating 16-channel chunks.
@@ -312,6 +316,24 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           }
         }
       }
+      // bwd gates (TMA-store path): this warp's first granule operands, fetched before the accumulator wait
+      GateIn gfirst;
+      if constexpr (EPI == EPI_LSTM_BWD_GATES && Cfg::kTmaStore) {
+        if (valid) {
+          const int g0 = half * (4 / (kEpiWarps / 4));
+          const size_t off = pix * p.Ch + n_tile * CH_TILE + g0 * 8;
+          const float4* cs = reinterpret_cast<const float4*>(p.c_prev + off);
+          gfirst.c0 = __ldg(cs); gfirst.c1 = __ldg(cs + 1);
+          if (p.dc_next) {
+            const float4* ds = reinterpret_cast<const float4*>(p.dc_next + off);
+            gfirst.d0 = __ldg(ds); gfirst.d1 = __ldg(ds + 1);
+          } else {
+            gfirst.d0 = make_float4(0.f, 0.f, 0.f, 0.f); gfirst.d1 = gfirst.d0;
+          }
+          gfirst.dh = __ldg(reinterpret_cast<const uint4*>(p.dh + off));
+          gfirst.dh2 = p.dh2 ? __ldg(reinterpret_cast<const uint4*>(p.dh2 + off)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
       long long te = (p.prof && warp == 4) ? clock64() : 0;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
@@ -422,6 +444,135 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
             tma_store_4d(&tmap_o0, so, ch0, x0, y0, b);
             tma_store_4d(&tmap_o0, so + 16384, ch0 + 32, x0, y0, b);
             tma_store_4d(&tmap_o1, so + 2 * 16384, ch0, x0, y0, b);
+            tma_store_commit();
+          }
+        }
+      } else if constexpr (EPI == EPI_LSTM_BWD_GATES && Cfg::kTmaStore) {
+        // ---- gate recompute + dZ / dc_prev, 8-channel granules, outputs through smem + TMA stores.
+        // Two rounds per tile (channels 0-31, 32-63 of the slice); every warp does GPR granules per round and
+        // prefetches the next granule's c_prev / dh / dc_next while it works on the current one.
+        const int ch0 = n_tile * CH_TILE;
+        const bool issuer = (warp == 4) && (lane == 0);
+        constexpr int WQ = kEpiWarps / 4;          // warps per TMEM lane quadrant
+        constexpr int GPR = 4 / WQ;                // granules per round per warp
+        static_assert(CH_TILE == 64 && (4 % WQ) == 0, "TMA-store gate epilogue assumes a 64-channel slice");
+        using GIn = GateIn;
+        GIn gin[2];
+        auto issue_loads = [&](int g, GIn& in) {
+          if (valid) {
+            const size_t off = pix * p.Ch + ch0 + g * 8;
+            const float4* cs = reinterpret_cast<const float4*>(p.c_prev + off);
+            in.c0 = __ldg(cs); in.c1 = __ldg(cs + 1);
+            if (p.dc_next) {
+              const float4* ds = reinterpret_cast<const float4*>(p.dc_next + off);
+              in.d0 = __ldg(ds); in.d1 = __ldg(ds + 1);
+            } else {
+              in.d0 = make_float4(0.f, 0.f, 0.f, 0.f); in.d1 = in.d0;
+            }
+            in.dh = __ldg(reinterpret_cast<const uint4*>(p.dh + off));
+            in.dh2 = p.dh2 ? __ldg(reinterpret_cast<const uint4*>(p.dh2 + off)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        };
+        // (the first granule's loads were issued before the accumulator wait: see `gfirst` above)
+        gin[0] = gfirst;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          if (issuer) tma_store_wait_read();       // staging buffer free again?
+          named_bar_sync(1, 32 * kEpiWarps);
+#pragma unroll
+          for (int j = 0; j < GPR; ++j) {
+            constexpr int kLast = 2 * GPR - 1;
+            const int idx = r * GPR + j;
+            const int gl = half * GPR + j;          // granule within the round: 0..3
+            const int g = r * 4 + gl;               // granule within the 64-channel slice: 0..7
+            if (idx < kLast) {                      // prefetch the next granule's operands
+              const int nidx = idx + 1;
+              issue_loads((nidx / GPR) * 4 + half * GPR + (nidx % GPR), gin[nidx & 1]);
+            }
+            uint32_t vi[8], vf[8], vo[8], vg[8];
+            tmem_ld8(t_acc + 0 * CH_TILE + g * 8, vi);
+            tmem_ld8(t_acc + 1 * CH_TILE + g * 8, vf);
+            tmem_ld8(t_acc + 2 * CH_TILE + g * 8, vo);
+            tmem_ld8(t_acc + 3 * CH_TILE + g * 8, vg);
+            const int chb = ch0 + g * 8;
+            float bi[8], bf[8], bo[8], bg[8];
+            {
+              const float4* s0 = reinterpret_cast<const float4*>(bias_s + 0 * p.Ch + chb);
+              const float4* s1 = reinterpret_cast<const float4*>(bias_s + 1 * p.Ch + chb);
+              const float4* s2 = reinterpret_cast<const float4*>(bias_s + 2 * p.Ch + chb);
+              const float4* s3 = reinterpret_cast<const float4*>(bias_s + 3 * p.Ch + chb);
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                const float4 a = s0[v], b4 = s1[v], c4 = s2[v], d4 = s3[v];
+                bi[4 * v] = a.x; bi[4 * v + 1] = a.y; bi[4 * v + 2] = a.z; bi[4 * v + 3] = a.w;
+                bf[4 * v] = b4.x; bf[4 * v + 1] = b4.y; bf[4 * v + 2] = b4.z; bf[4 * v + 3] = b4.w;
+                bo[4 * v] = c4.x; bo[4 * v + 1] = c4.y; bo[4 * v + 2] = c4.z; bo[4 * v + 3] = c4.w;
+                bg[4 * v] = d4.x; bg[4 * v + 1] = d4.y; bg[4 * v + 2] = d4.z; bg[4 * v + 3] = d4.w;
+              }
+            }
+            tmem_ld_wait();
+            if (idx == kLast) release();
+            if (valid) {
+              const GIn& in = gin[idx & 1];
+              const float cp[8] = {in.c0.x, in.c0.y, in.c0.z, in.c0.w, in.c1.x, in.c1.y, in.c1.z, in.c1.w};
+              const float dcn[8] = {in.d0.x, in.d0.y, in.d0.z, in.d0.w, in.d1.x, in.d1.y, in.d1.z, in.d1.w};
+              const uint32_t w1[4] = {in.dh.x, in.dh.y, in.dh.z, in.dh.w};
+              const uint32_t w2[4] = {in.dh2.x, in.dh2.y, in.dh2.z, in.dh2.w};
+              float dcp[8];
+              uint32_t zi[4], zf[4], zo[4], zg[4];
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                const __nv_bfloat162 t1 = *reinterpret_cast<const __nv_bfloat162*>(&w1[e >> 1]);
+                const __nv_bfloat162 t2 = *reinterpret_cast<const __nv_bfloat162*>(&w2[e >> 1]);
+                const float dhp[2] = {__low2float(t1) + __low2float(t2), __high2float(t1) + __high2float(t2)};
+                float di_[2], df_[2], do_[2], dg_[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int jj = e + u;
+                  const float ig = sigmoid_fast(__uint_as_float(vi[jj]) + bi[jj]);
+                  const float fg = sigmoid_fast(__uint_as_float(vf[jj]) + bf[jj]);
+                  const float og = sigmoid_fast(__uint_as_float(vo[jj]) + bo[jj]);
+                  const float gt = tanh_fast(__uint_as_float(vg[jj]) + bg[jj]);
+                  const float c2 = fmaf(fg, cp[jj], ig * gt);
+                  const float tc = tanh_fast(c2);
+                  const float dh_ = dhp[u];
+                  const float dc = fmaf(dh_ * og, 1.f - tc * tc, dcn[jj]);
+                  dcp[jj] = dc * fg;
+                  di_[u] = dc * gt * ig * (1.f - ig);
+                  df_[u] = dc * cp[jj] * fg * (1.f - fg);
+                  do_[u] = dh_ * tc * og * (1.f - og);
+                  dg_[u] = dc * ig * (1.f - gt * gt);
+                }
+                zi[e >> 1] = pack_bf16x2(di_[0], di_[1]);
+                zf[e >> 1] = pack_bf16x2(df_[0], df_[1]);
+                zo[e >> 1] = pack_bf16x2(do_[0], do_[1]);
+                zg[e >> 1] = pack_bf16x2(dg_[0], dg_[1]);
+              }
+              // staging: dZ gate boxes are [128 px][32 ch] bf16 = 64-byte rows (SWIZZLE_64B: chunk ^= (row >> 1) & 3);
+              //          dc_prev box is [128 px][32 ch] fp32 = 128-byte rows (SWIZZLE_128B: chunk ^= row & 7)
+              const uint32_t so = smem_u32(stage_out);
+              const uint32_t zrow = so + row * 64 + ((static_cast<uint32_t>(gl) ^ ((row >> 1) & 3)) << 4);
+              st_shared_v4(zrow + 0 * 8192, zi[0], zi[1], zi[2], zi[3]);
+              st_shared_v4(zrow + 1 * 8192, zf[0], zf[1], zf[2], zf[3]);
+              st_shared_v4(zrow + 2 * 8192, zo[0], zo[1], zo[2], zo[3]);
+              st_shared_v4(zrow + 3 * 8192, zg[0], zg[1], zg[2], zg[3]);
+              const uint32_t crow = so + 32768 + row * 128;
+              const uint32_t sw = row & 7;
+              st_shared_v4(crow + (((gl * 2) ^ sw) << 4), __float_as_uint(dcp[0]), __float_as_uint(dcp[1]),
+                           __float_as_uint(dcp[2]), __float_as_uint(dcp[3]));
+              st_shared_v4(crow + (((gl * 2 + 1) ^ sw) << 4), __float_as_uint(dcp[4]), __float_as_uint(dcp[5]),
+                           __float_as_uint(dcp[6]), __float_as_uint(dcp[7]));
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 32 * kEpiWarps);
+          if (issuer) {
+            const uint32_t so = smem_u32(stage_out);
+            const int cbase = ch0 + r * 32;
+#pragma unroll
+            for (int gate = 0; gate < 4; ++gate)
+              tma_store_4d(&tmap_o0, so + gate * 8192, gate * p.Ch + cbase, x0, y0, b);   // dZ, reference gate order
+            tma_store_4d(&tmap_o1, so + 32768, cbase, x0, y0, b);                         // dc_prev
             tma_store_commit();
           }
         }

@@ -66,7 +66,7 @@ int sm_count() {
 
 // NHWC bf16 activation [B,H,W,C] as a 4-D tensor map; box = [64 ch, tw, th, 1], SWIZZLE_128B.
 int make_tmap_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int tw, int th, int esize = 2,
-                  int box_c = 64) {
+                  int box_c = 64, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t es = (cuuint64_t)esize;
@@ -76,7 +76,7 @@ int make_tmap_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, 
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                    const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled(act B=%d H=%d W=%d C=%d box=%dx%d) -> %d", B, H, W, C, tw, th,
@@ -595,7 +595,14 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   }
   const int cta = pick_cta_group(p.num_m_tiles);
   if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile / cta))) return rc;
-  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, ta1, ta1, st))) return rc;
+  CUtensorMap tzo = ta1, tdc = ta1;
+  if (plc::tma_store_epilogue<256, plc::EPI_LSTM_BWD_GATES>() && g.n_tile == 256) {
+    // dZ half-slices: [32 ch] bf16 = 64-byte rows -> SWIZZLE_64B; dc_prev [32 ch] fp32 = 128-byte rows
+    if ((rc = make_tmap_act(&tzo, workspace, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th, 2, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
+    if ((rc = make_tmap_act(&tdc, dc_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
+  }
+  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, tzo, tdc, st))) return rc;
 
   // 2) dgrad: conv of dZ (4Ch channels) with the flipped/transposed image -> dx, dh_prev
   if (dx || dh_prev) {
