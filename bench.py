@@ -336,19 +336,45 @@ def main():
     peak_sus, peak_burst, peak_src = measured_peaks()
     cell_ms_total = sum(a.elapsed_time(b) for a, b, _ in events)
 
-    # ---------------- end-to-end region: pinned host frames -> device -> rollout -> predicted frames -> host
-    def e2e_step():
-        frames_dev.copy_(frames_host, non_blocking=True)
-        out = runner.run(frames_dev)
-        out_host.copy_(out, non_blocking=True)
+    # ---------------- end-to-end region: pinned host frames -> device -> rollout -> predicted frames -> host.
+    # Every step copies ITS input from pinned host memory and ITS result back; the copies run on a side stream
+    # (double-buffered) so that step i's D2H and step i+1's H2D overlap the compute of the neighbouring steps.
+    copy_s = torch.cuda.Stream()
+    main_s = torch.cuda.current_stream()
+    in_buf = [torch.empty_like(frames_dev) for _ in range(2)]
+    out_buf = [torch.empty_like(runner.out) for _ in range(2)]
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    run_done = [torch.cuda.Event() for _ in range(2)]
+    d2h_done = [torch.cuda.Event() for _ in range(2)]
 
-    for _ in range(Wm):
-        e2e_step()
+    def stage_in(i):
+        s_ = i & 1
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(run_done[s_])            # the run that last read this input buffer has finished
+            in_buf[s_].copy_(frames_host, non_blocking=True)
+            h2d_done[s_].record(copy_s)
+
+    def e2e_loop(n):
+        stage_in(0)
+        for i in range(n):
+            s_ = i & 1
+            if i + 1 < n:
+                stage_in(i + 1)
+            main_s.wait_event(h2d_done[s_])
+            main_s.wait_event(d2h_done[s_])            # the D2H that last read this output buffer has finished
+            out = runner.run(in_buf[s_], out=out_buf[s_])
+            run_done[s_].record(main_s)
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(run_done[s_])
+                out_host.copy_(out, non_blocking=True)
+                d2h_done[s_].record(copy_s)
+        main_s.wait_stream(copy_s)
+
+    e2e_loop(Wm)
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
-    for _ in range(K):
-        e2e_step()
+    e2e_loop(K)
     s1.record()
     torch.cuda.synchronize()
     barrier()

@@ -13,11 +13,14 @@
 //   pixel has i,f,o,g for its channels and applies convlstm.py:21-27 without leaving the SM.
 // * K side: blocks of 64 bf16 (=128 B, one SWIZZLE_128B atom row) ordered (src, tap, chunk).
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0 lane 0 : TMA producer          (smem ring: kStages x {A 16 KB, B N_TILE*128 B})
-//   warp 1 lane 0 : tcgen05.mma issuer    (accumulators double-buffered in TMEM: 2 x N_TILE cols)
+// Warp roles (1 CTA/SM, persistent over tiles; with cta_group::2 two CTAs form a pair on one 256-pixel tile):
+//   warp 0        : TMA producer (warp-uniform loop, one elected lane issues; smem ring of {A 16 KB, B N_TILE/cta*128 B})
+//   warp 1        : tcgen05.mma issuer, leader CTA only (accumulators double-buffered in TMEM: 2 x N_TILE columns)
 //   warp 2        : TMEM alloc / dealloc
-//   warps 4..7    : epilogue (tcgen05.ld -> gate math -> global), overlapped with the next tile's MMAs
+//   warps 4..     : epilogue -- 16 warps (forward), 8 (gate recompute) or 4 (plain): tcgen05.ld -> gate math ->
+//                   smem staging -> TMA tensor stores (64-channel slices) or direct global stores (narrow slices),
+//                   overlapped with the next tile's MMAs; the accumulator stage is released right after the last
+//                   tcgen05.ld of the tile.
 #pragma once
 #include "plc_ptx.cuh"
 
@@ -577,6 +580,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           }
         }
       } else if constexpr (EPI == EPI_LSTM_BWD_GATES) {
+        // ---- direct-store variant (channel slices narrower than 64): 16-channel chunks
         const int ch0 = n_tile * CH_TILE;
 #pragma unroll
         for (int m = 0; m < kMaxMine; ++m) {
@@ -611,10 +615,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
               }
             }
             float cp[16];
-            if constexpr (EPI == EPI_LSTM_FWD) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) cp[e] = cpre[m][e];
-            } else {
+            {
               const float4* src = reinterpret_cast<const float4*>(p.c_prev + off);
 #pragma unroll
               for (int v = 0; v < 4; ++v) {
@@ -622,54 +623,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                 cp[4 * v + 0] = t.x; cp[4 * v + 1] = t.y; cp[4 * v + 2] = t.z; cp[4 * v + 3] = t.w;
               }
             }
-            if constexpr (EPI == EPI_LSTM_FWD) {
-              float cn[16];
-              uint32_t hp[8];
-              uint32_t gi[8], gf[8], go[8], gg[8];
-#pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                float hv[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                  const int jj = j + u;
-                  const float ig = sigmoid_fast(__uint_as_float(vi[jj]));
-                  const float fg = sigmoid_fast(__uint_as_float(vf[jj]));
-                  const float og = sigmoid_fast(__uint_as_float(vo[jj]));
-                  const float gt = tanh_fast(__uint_as_float(vg[jj]));
-                  const float c2 = fmaf(fg, cp[jj], ig * gt);          // convlstm.py:26
-                  cn[jj] = c2;
-                  hv[u] = og * tanh_fast(c2);                          // convlstm.py:27
-                  vi[jj] = __float_as_uint(ig); vf[jj] = __float_as_uint(fg);
-                  vo[jj] = __float_as_uint(og); vg[jj] = __float_as_uint(gt);
-                }
-                hp[j >> 1] = pack_bf16x2(hv[0], hv[1]);
-              }
-              float4* cdst = reinterpret_cast<float4*>(p.c_out + off);
-#pragma unroll
-              for (int v = 0; v < 4; ++v)
-                cdst[v] = make_float4(cn[4 * v], cn[4 * v + 1], cn[4 * v + 2], cn[4 * v + 3]);
-              uint4* hdst = reinterpret_cast<uint4*>(p.h_out + off);
-              hdst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-              hdst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
-              if (p.gates_out) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  gi[j] = pack_bf16x2(__uint_as_float(vi[2 * j]), __uint_as_float(vi[2 * j + 1]));
-                  gf[j] = pack_bf16x2(__uint_as_float(vf[2 * j]), __uint_as_float(vf[2 * j + 1]));
-                  go[j] = pack_bf16x2(__uint_as_float(vo[2 * j]), __uint_as_float(vo[2 * j + 1]));
-                  gg[j] = pack_bf16x2(__uint_as_float(vg[2 * j]), __uint_as_float(vg[2 * j + 1]));
-                }
-                __nv_bfloat16* gbase = p.gates_out + pix * (4 * p.Ch) + chb;
-                uint4* d0 = reinterpret_cast<uint4*>(gbase + 0 * p.Ch);
-                uint4* d1 = reinterpret_cast<uint4*>(gbase + 1 * p.Ch);
-                uint4* d2 = reinterpret_cast<uint4*>(gbase + 2 * p.Ch);
-                uint4* d3 = reinterpret_cast<uint4*>(gbase + 3 * p.Ch);
-                d0[0] = make_uint4(gi[0], gi[1], gi[2], gi[3]); d0[1] = make_uint4(gi[4], gi[5], gi[6], gi[7]);
-                d1[0] = make_uint4(gf[0], gf[1], gf[2], gf[3]); d1[1] = make_uint4(gf[4], gf[5], gf[6], gf[7]);
-                d2[0] = make_uint4(go[0], go[1], go[2], go[3]); d2[1] = make_uint4(go[4], go[5], go[6], go[7]);
-                d3[0] = make_uint4(gg[0], gg[1], gg[2], gg[3]); d3[1] = make_uint4(gg[4], gg[5], gg[6], gg[7]);
-              }
-            } else {  // EPI_LSTM_BWD_GATES : SURVEY.md section 3.3
+            {
               float dhv[16], dcn[16], dcp[16];
               {
                 const uint4* s = reinterpret_cast<const uint4*>(p.dh + off);

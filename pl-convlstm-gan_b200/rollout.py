@@ -75,9 +75,10 @@ class NowcastRunner:
             events.append((e0, e1, pw))
 
     @torch.no_grad()
-    def run(self, frames: Tensor, events: Optional[List] = None) -> Tensor:
-        """frames [B,T_in,Cf,H,W] fp32 on device.  Returns predicted frames [T_out,B,H,W] fp32 (device buffer).
-        ``events``: optional list collecting (start_event, end_event, packed_weights) per cell launch."""
+    def run(self, frames: Tensor, events: Optional[List] = None, out: Optional[Tensor] = None) -> Tensor:
+        """frames [B,T_in,Cf,H,W] fp32 on device.  Returns predicted frames [T_out,B,H,W] fp32 (``out`` or the
+        runner's own device buffer).  ``events``: optional list collecting (start_event, end_event, packed_weights)
+        per cell launch."""
         m, B, L = self.m, self.B, len(self.c)
         T_in, T_out = m.t_in, m.t_out
         # [B,T,Cf,H,W] -> [T*B,Cf,H,W]: front-end for all steps in one launch
@@ -107,5 +108,6 @@ class NowcastRunner:
                     self._cell(self.fc_pw[l], x, self.h[l][cur[l]], self.c[l], dst, events)
                     cur[l] ^= 1
                 x = dst
-        F.head_forward(self.h_top, m.head.weight, m.head.bias, self.mode, out=self.out)
-        return self.out
+        out = self.out if out is None else out
+        F.head_forward(self.h_top, m.head.weight, m.head.bias, self.mode, out=out)
+        return out
