@@ -112,6 +112,9 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
  * kernels record per-CTA cycle counters (MMA warp total / waiting for TMEM / waiting for TMA, epilogue busy / idle).
  * NULL (default) disables it.  Not part of the reference-facing surface.                                   */
 int plc_debug_set_prof(void* device_buf_u64);
+/* Force the tensor-core kernels onto cta_group 1 or 2 (0 = automatic choice by problem size); used by the parity
+ * tests to cover the CTA-pair path on small shapes.                                                          */
+int plc_debug_set_cta_group(int cta_group);
 
 /* ---- layout helpers (HBM-bound elementwise kernels) ---------------------------------------
  * The reference keeps NCHW fp32 tensors (generator.py:156-160).  These convert between that and

@@ -36,6 +36,7 @@ SIGNATURES = {
     "plc_bwd_workspace_bytes": (_sz, [_dp]),
     "plc_cell_bwd": (_int, [_dp] + [_vp] * 15 + [_sz, _vp]),
     "plc_debug_set_prof": (_int, [_vp]),
+    "plc_debug_set_cta_group": (_int, [_int]),
     "plc_nchw_f32_to_nhwc_bf16": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),
     "plc_nhwc_bf16_to_nchw_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
     "plc_frontend_fwd": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _int, _int, _int, _vp, _vp]),

@@ -253,12 +253,14 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ s
 // cta_group choice: a CTA pair (cta_group::2) halves the per-SM weight-tile traffic and wins once there are
 // enough 128-pixel tiles to keep all 74 pairs busy; tiny problems keep 148 independent CTAs.
 // PLC_CTA_GROUP=1|2 overrides (used by the benchmarks to A/B the two paths).
+int g_cta_override = 0;   // plc_debug_set_cta_group
 int pick_cta_group(int num_m_tiles) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("PLC_CTA_GROUP");
     forced = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
   }
+  if (g_cta_override) return g_cta_override;
   if (forced) return forced;
   return num_m_tiles >= 2 * sm_count() ? 2 : 1;
 }
@@ -628,6 +630,12 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   if (dW_acc) {
     if ((rc = launch_wgrad_tc(d, x, h_prev, workspace, dW_acc, d->has_bias ? db_acc : nullptr, st))) return rc;
   }
+  return PLC_OK;
+}
+
+int plc_debug_set_cta_group(int cta_group) {
+  if (cta_group < 0 || cta_group > 2) return fail(PLC_ERR_BAD_DESC, "cta_group must be 0 (auto), 1 or 2");
+  g_cta_override = cta_group;
   return PLC_OK;
 }
 

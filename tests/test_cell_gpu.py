@@ -213,3 +213,62 @@ def test_backward_vs_reference_autograd_golden(path, mode_name, cuda_device):
         if rel_err(got, ref) >= tol[name]:
             msgs.append(report(name, got, ref))
     assert not msgs, " | ".join(msgs)
+
+
+# ---------------------------------------------------------------------------------------- CTA-pair (cta_group::2) path
+# Small shapes default to cta_group::1; force the pair path so that parity covers it too: odd number of 128-pixel
+# tiles (tail tile of a pair decodes to image index B and must be zero-filled / clipped), ragged edges, several N
+# tiles, narrow slices (direct-store epilogue) and 64-channel slices (TMA-store epilogue), no-input layer.
+PAIR_SHAPES = [
+    (1, 64, 64, 8, 16, 3),       # ONE tile: the pair's second CTA works on a fully out-of-range tile
+    (3, 64, 64, 8, 16, 3),       # odd tile count
+    (2, 64, 64, 16, 32, 3),
+    (1, 16, 16, 12, 15, 3),      # ragged + narrow slice (direct stores)
+    (1, 128, 128, 16, 16, 3),    # 2 N tiles
+    (3, 0, 64, 8, 8, 3),         # no input tensor
+    (2, 8, 32, 9, 7, 5),         # k = 5
+    (1, 72, 80, 6, 130, 3),      # W > 128
+]
+
+
+@pytest.fixture
+def force_pair():
+    import plconv
+    lib = plconv._lib.load()
+    lib.plc_debug_set_cta_group(2)
+    yield
+    lib.plc_debug_set_cta_group(0)
+
+
+@pytest.mark.parametrize("shape", PAIR_SHAPES, ids=lambda s: "B%d_Cin%d_Ch%d_%dx%d_k%d" % s)
+def test_pair_path_forward_and_backward_vs_oracle(shape, force_pair, cuda_device):
+    plconv, _ = _plconv()
+    B, cin, ch, H, W, k = shape
+    gen = torch.Generator().manual_seed(7 + sum(shape))
+    fan_in = (cin + ch) * k * k
+    w = (torch.rand(4 * ch, cin + ch, k, k, generator=gen) * 2 - 1) * (3.0 / fan_in) ** 0.5 * 2
+    b = torch.randn(4 * ch, generator=gen) * 0.5
+    x = torch.randn(B, max(cin, 1), H, W, generator=gen)[:, :cin] if cin else None
+    h = torch.randn(B, ch, H, W, generator=gen) * 0.5
+    c = torch.randn(B, ch, H, W, generator=gen)
+    gh = torch.randn(B, ch, H, W, generator=gen)
+    gc = torch.randn(B, ch, H, W, generator=gen)
+    xr = None if x is None else bf16r(x).double()
+    h_ref, c_ref = O.cell_forward(xr, bf16r(h).double(), c.double(), bf16r(w).double(), b.double())
+    if cin:
+        h2, c2 = run_cell(plconv.PLC_MODE_BF16_TC, x, h, c, w, b, cuda_device)
+    else:
+        from plconv import functional as F
+        pw = F.pack_weights(w.to(cuda_device), b.to(cuda_device), 0, ch, k, plconv.PLC_MODE_BF16_TC)
+        o = F.cell_forward(None, nhwc(h, torch.bfloat16, cuda_device), nhwc(c, torch.float32, cuda_device), pw)
+        torch.cuda.synchronize()
+        h2, c2 = nchw(o[0]), nchw(o[1])
+    assert rel_err(h2, h_ref) < BF16_TOL and rel_err(c2, c_ref) < BF16_TOL, \
+        report("h", h2, h_ref) + " | " + report("c", c2, c_ref)
+    if cin:
+        ref = O.cell_backward(xr, bf16r(h).double(), c.double(), bf16r(w).double(), b.double(), bf16r(gh).double(),
+                              gc.double())
+        dx, dhp, dcp, dW, db = run_cell_bwd(plconv.PLC_MODE_BF16_TC, x, h, c, w, b, gh, gc, cuda_device)
+        bad = [report(n_, got, ref[n_]) for n_, got in (("dx", dx), ("dh_prev", dhp), ("dc_prev", dcp), ("dW", dW),
+                                                         ("db", db)) if rel_err(got, ref[n_]) >= 2e-2]
+        assert not bad, " | ".join(bad)
