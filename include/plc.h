@@ -107,6 +107,31 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
                  const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc, float* db_acc,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- generic "same" convolution on the same tensor-core core (bf16; SURVEY.md section 8f "next-1") ----------------
+ * Replaces the plain nn.Conv2d layers of the reference Generator body: UpsampleBlock conv + PixelShuffle(2) + ReLU
+ * (generator.py:10-28), post_process convs (generator.py:67-71), attention convs (attention.py:6-10).
+ *   x   [B,H,W,Cin] bf16 NHWC;  out [B,H,W,Cout] bf16, or with pixel_shuffle [B,2H,2W,Cout/4] (torch PixelShuffle(2)
+ *   semantics: natural output channel n = c*4 + i*2 + j -> out[b, 2y+i, 2x+j, c]);  relu applied last.
+ *   Cin % 8 == 0, Cout % 8 == 0 (pixel_shuffle: Cout % 32 == 0): callers zero-pad channels.
+ * plc_conv_pack_weight: w_oihw [Cout,Cin,k,k] fp32 -> packed image (PLC_PACK_FWD also writes bias_packed [Cout] in
+ *   packed column order; PLC_PACK_DGRAD the flipped/transposed image).
+ * Backward: plc_conv_grad_mask forms dZ [B,H,W,Cout] (natural channel order) = dY * (Y > 0) undoing the shuffle;
+ *   plc_conv_bwd: dx [B,H,W,Cin] (nullable), dW_acc [Cout,Cin,k,k] fp32 +=, db_acc [Cout] fp32 += (nullable).   */
+typedef struct PlcConvDesc {
+  int32_t B, H, W, Cin, Cout, k;
+  int32_t relu;           /* apply ReLU to the output                              */
+  int32_t pixel_shuffle;  /* fuse PixelShuffle(2) into the store                   */
+  int32_t has_bias;
+} PlcConvDesc;
+size_t plc_conv_packed_weight_bytes(const PlcConvDesc* d, int pack_kind);
+int plc_conv_pack_weight(const PlcConvDesc* d, int pack_kind, const float* w_oihw, const float* bias, void* w_packed,
+                         float* bias_packed, void* stream);
+int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, void* out,
+                 void* stream);
+int plc_conv_grad_mask(const PlcConvDesc* d, const void* y, const void* dy, void* dz, void* stream);
+int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void* w_packed_dgrad, void* dx,
+                 float* dW_acc, float* db_acc, void* stream);
+
 /* ---- debug ---------------------------------------------------------------------------------
  * Developer aid (tools/kprof.py): when set to a zeroed device buffer of at least 148*16 uint64, the tensor-core conv
  * kernels record per-CTA cycle counters (MMA warp total / waiting for TMEM / waiting for TMA, epilogue busy / idle).

@@ -22,8 +22,13 @@ class PlcCellDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("B", "H", "W", "Cin", "Ch", "k", "mode", "has_bias")]
 
 
+class PlcConvDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "H", "W", "Cin", "Cout", "k", "relu", "pixel_shuffle", "has_bias")]
+
+
 _vp, _sz, _int = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
 _dp = ctypes.POINTER(PlcCellDesc)
+_cp = ctypes.POINTER(PlcConvDesc)
 
 # name -> (restype, argtypes); must list every symbol include/plc.h declares (tests check this)
 SIGNATURES = {
@@ -35,6 +40,11 @@ SIGNATURES = {
     "plc_cell_fwd": (_int, [_dp] + [_vp] * 9),
     "plc_bwd_workspace_bytes": (_sz, [_dp]),
     "plc_cell_bwd": (_int, [_dp] + [_vp] * 15 + [_sz, _vp]),
+    "plc_conv_packed_weight_bytes": (_sz, [_cp, _int]),
+    "plc_conv_pack_weight": (_int, [_cp, _int, _vp, _vp, _vp, _vp, _vp]),
+    "plc_conv_fwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp]),
+    "plc_conv_grad_mask": (_int, [_cp, _vp, _vp, _vp, _vp]),
+    "plc_conv_bwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plc_debug_set_prof": (_int, [_vp]),
     "plc_debug_set_cta_group": (_int, [_int]),
     "plc_nchw_f32_to_nhwc_bf16": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),

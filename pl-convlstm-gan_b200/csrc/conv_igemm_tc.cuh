@@ -53,6 +53,9 @@ struct ConvTcParams {
   __nv_bfloat16* out0;       // [M, Cin] bf16 or nullptr           (PLAIN)
   __nv_bfloat16* out1;       // [M, Ntot-Cin] bf16 or nullptr      (PLAIN)
   int n_total;               // PLAIN: total valid output columns
+  const float* plain_bias;   // PLAIN: [n_total] fp32 in packed column order, or nullptr
+  int plain_relu;            // PLAIN: apply max(x, 0)
+  int plain_shuffle;         // PLAIN: PixelShuffle(2) store: column n' = sub*(n_total/4) + c -> out0[b, 2y+sub/2, 2x+sub%2, c]
   unsigned long long* prof;  // debug: per-CTA cycle counters [gridDim][16] or nullptr (plc_debug_set_prof)
 };
 
@@ -710,12 +713,33 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
             for (int hlf = 0; hlf < 2; ++hlf) {
               const int n0 = n_tile * N_TILE + cc * 16 + hlf * 8;
               if (n0 < p.n_total) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[hlf * 8 + e]);
+                if (p.plain_bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.plain_bias + n0));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.plain_bias + n0) + 1);
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                if (p.plain_relu) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                }
                 uint4 o;
-                o.x = pack_bf16x2(__uint_as_float(v[hlf * 8 + 0]), __uint_as_float(v[hlf * 8 + 1]));
-                o.y = pack_bf16x2(__uint_as_float(v[hlf * 8 + 2]), __uint_as_float(v[hlf * 8 + 3]));
-                o.z = pack_bf16x2(__uint_as_float(v[hlf * 8 + 4]), __uint_as_float(v[hlf * 8 + 5]));
-                o.w = pack_bf16x2(__uint_as_float(v[hlf * 8 + 6]), __uint_as_float(v[hlf * 8 + 7]));
-                if (n0 < p.Cin) {
+                o.x = pack_bf16x2(f[0], f[1]);
+                o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]);
+                o.w = pack_bf16x2(f[6], f[7]);
+                if (p.plain_shuffle) {
+                  // PixelShuffle(2) fused into the store (generator.py:24-26): 8 consecutive packed columns are 8
+                  // channels of ONE sub-pixel
+                  const int cps = p.n_total >> 2;
+                  const int sub = n0 / cps, c = n0 - sub * cps;
+                  const size_t opix = (static_cast<size_t>(b) * (2 * p.H) + (2 * y + (sub >> 1))) * (2 * p.W) +
+                                      (2 * x + (sub & 1));
+                  *reinterpret_cast<uint4*>(p.out0 + opix * cps + c) = o;
+                } else if (n0 < p.Cin) {
                   if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pix * p.Cin + n0) = o;
                 } else {
                   if (p.out1) *reinterpret_cast<uint4*>(p.out1 + pix * (p.n_total - p.Cin) + (n0 - p.Cin)) = o;

@@ -195,10 +195,29 @@ __global__ void pack_w_tc_fwd_kernel(const float* __restrict__ w, __nv_bfloat16*
     out[idx] = __float2bfloat16(v);
   }
 }
-// dgrad image Wd[c][k'] : rows c in [0, Cin+Ch) ; k' = (tap', chunk of dZ channel n)*64 + jj, flipped taps
-__global__ void pack_w_tc_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Ch,
-                                       int ksize, int chunksz) {
-  const int kk = ksize * ksize, ctot = Cin + Ch;
+// generic conv forward image Wp[n'][k'] : k' = (tap, 64-chunk)*64 + jj ; packed row n' = sub*(Cout/4) + c for the
+// PixelShuffle(2) store (natural channel n = c*4 + sub), else n' = n.  bias_p[n'] = bias[n].
+__global__ void pack_w_conv_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                       __nv_bfloat16* __restrict__ out, float* __restrict__ bias_p, int Cin, int Cout,
+                                       int ksize, int chunks, int shuffle) {
+  const int kk = ksize * ksize, ktot = kk * chunks * 64, cps = Cout >> 2;
+  const size_t total = static_cast<size_t>(Cout) * ktot;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int kp = idx % ktot, np = idx / ktot;
+    const int n = shuffle ? (np % cps) * 4 + np / cps : np;
+    const int kb = kp >> 6, jj = kp & 63;
+    const int tap = kb / chunks, c = (kb % chunks) * 64 + jj;
+    float v = 0.f;
+    if (c < Cin) v = w[(static_cast<size_t>(n) * Cin + c) * kk + tap];
+    out[idx] = __float2bfloat16(v);
+    if (kp == 0 && bias_p) bias_p[np] = bias ? bias[n] : 0.f;
+  }
+}
+// generic dgrad image Wd[c][k'] : rows c in [0, ctot) ; k' = (tap', chunk of dZ channel n)*64 + jj, flipped taps
+__global__ void pack_w_conv_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int ctot,
+                                         int nout, int ksize, int chunksz) {
+  const int kk = ksize * ksize;
   const int ktot = kk * chunksz * 64;
   const size_t total = static_cast<size_t>(ctot) * ktot;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -208,11 +227,35 @@ __global__ void pack_w_tc_dgrad_kernel(const float* __restrict__ w, __nv_bfloat1
     const int tap = kb / chunksz;
     const int n = (kb % chunksz) * 64 + jj;
     float v = 0.f;
-    if (n < 4 * Ch) {
+    if (n < nout) {
       const int fy = ksize - 1 - tap / ksize, fx = ksize - 1 - tap % ksize;
       v = w[(static_cast<size_t>(n) * ctot + c) * kk + fy * ksize + fx];
     }
     out[idx] = __float2bfloat16(v);
+  }
+}
+// dZ (natural conv-output channel order) = dY * (Y > 0), optionally undoing PixelShuffle(2):
+//   shuffle: y, dy are [B, 2H, 2W, Cout/4]; dz[b,y,x, c*4 + sub] = dy[b, 2y+sub/2, 2x+sub%2, c] * (y[...] > 0)
+__global__ void conv_grad_mask_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
+                                      __nv_bfloat16* __restrict__ dz, size_t npix_in, int H, int W, int Cout, int relu,
+                                      int shuffle) {
+  const size_t total = npix_in * Cout;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t src = idx;
+    if (shuffle) {
+      const int n = idx % Cout;
+      const size_t pix = idx / Cout;
+      const int x = pix % W;
+      const size_t t = pix / W;
+      const int yy = t % H;
+      const size_t b = t / H;
+      const int c = n >> 2, sub = n & 3;
+      src = ((b * (2 * H) + 2 * yy + (sub >> 1)) * (2 * W) + 2 * x + (sub & 1)) * (Cout >> 2) + c;
+    }
+    const float g = __bfloat162float(dy[src]);
+    const bool on = !relu || __bfloat162float(y[src]) > 0.f;
+    dz[idx] = __float2bfloat16(on ? g : 0.f);
   }
 }
 
@@ -339,8 +382,19 @@ int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p) {
 }
 
 // wgrad on the tensor cores + bias-gradient column sum (bf16 mode)
+struct WgradShape { int B, H, W, k, Cin, Ch, N; };   // sources x [.,Cin] and h [.,Ch]; N = dZ channels
+
+int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev, const void* dz, float* dW, float* db,
+                          cudaStream_t st);
+
 int launch_wgrad_tc(const PlcCellDesc* d, const void* x, const void* h_prev, const void* dz, float* dW, float* db,
                     cudaStream_t st) {
+  WgradShape w{d->B, d->H, d->W, d->k, d->Cin, d->Ch, 4 * d->Ch};
+  return launch_wgrad_tc_shape(&w, x, h_prev, dz, dW, db, st);
+}
+
+int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev, const void* dz, float* dW, float* db,
+                          cudaStream_t st) {
   int rc;
   TcGeom g;
   pick_spatial_tile(d->H, d->W, &g, 6);   // 64-pixel blocks
@@ -354,23 +408,26 @@ int launch_wgrad_tc(const PlcCellDesc* d, const void* x, const void* h_prev, con
   p.CB = d->k * d->k * (p.chunks0 + p.chunks1);
   p.num_groups = cdiv(p.CB, plc::kWgMaxGB);
   p.GB = cdiv(p.CB, p.num_groups);
-  p.n_tiles = cdiv(4 * d->Ch, 128);
+  p.n_tiles = cdiv(d->N, 128);
   const int tiles = p.n_tiles * p.num_groups;
   int S = sm_count() / tiles;
   if (S < 1) S = 1;
   if (S > p.PB) S = p.PB;
   p.S = S;
-  p.C0 = d->Cin; p.C1 = d->Ch; p.N4 = 4 * d->Ch; p.Ctot = d->Cin + d->Ch;
+  p.C0 = d->Cin; p.C1 = d->Ch; p.N4 = d->N; p.Ctot = d->Cin + d->Ch;
   p.dW = dW;
   p.db = db;
   CUtensorMap tz, t0, t1;
-  if ((rc = make_tmap_act(&tz, dz, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th))) return rc;
-  if ((rc = make_tmap_act(&t1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th))) return rc;
+  if ((rc = make_tmap_act(&tz, dz, d->B, d->H, d->W, d->N, g.tw, g.th))) return rc;
+  if (d->Ch > 0) {
+    if ((rc = make_tmap_act(&t1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th))) return rc;
+  }
   if (d->Cin > 0) {
     if ((rc = make_tmap_act(&t0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th))) return rc;
   } else {
     t0 = t1;
   }
+  if (d->Ch == 0) t1 = t0;
   PLC_CUDA(cudaFuncSetAttribute(plc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plc::kWgSmemBytes));
   plc::wgrad_tc_kernel<<<tiles * S, 256, plc::kWgSmemBytes, st>>>(p, tz, t0, t1);
   PLC_CUDA(cudaGetLastError());
@@ -430,8 +487,8 @@ int plc_pack_weight(const PlcCellDesc* d, int pack_kind, const float* w_oihw, vo
       pack_w_tc_fwd_kernel<<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), d->Cin, d->Ch,
                                                        d->k, pick_ch_tile(d->Ch), cdiv(d->Cin, 64), cdiv(d->Ch, 64));
     else
-      pack_w_tc_dgrad_kernel<<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), d->Cin, d->Ch,
-                                                         d->k, cdiv(4 * d->Ch, 64));
+      pack_w_conv_dgrad_kernel<<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed),
+                                                           d->Cin + d->Ch, 4 * d->Ch, d->k, cdiv(4 * d->Ch, 64));
   }
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;
@@ -629,6 +686,127 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   // 3) wgrad + bias grad
   if (dW_acc) {
     if ((rc = launch_wgrad_tc(d, x, h_prev, workspace, dW_acc, d->has_bias ? db_acc : nullptr, st))) return rc;
+  }
+  return PLC_OK;
+}
+
+// ---------------------------------------------------------------------------------- generic "same" conv (bf16)
+static int check_conv(const PlcConvDesc* d) {
+  if (!d) return fail(PLC_ERR_BAD_DESC, "null conv descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0)
+    return fail(PLC_ERR_BAD_DESC, "bad conv sizes B=%d H=%d W=%d Cin=%d Cout=%d", d->B, d->H, d->W, d->Cin, d->Cout);
+  if (d->k <= 0 || (d->k % 2) == 0 || d->k > 7) return fail(PLC_ERR_BAD_DESC, "conv kernel size %d must be odd, <= 7", d->k);
+  if (d->Cin % 8 || d->Cout % 8)
+    return fail(PLC_ERR_ALIGNMENT, "conv needs Cin %% 8 == 0 and Cout %% 8 == 0 (got %d, %d): pad channels", d->Cin, d->Cout);
+  if (d->pixel_shuffle && d->Cout % 32) return fail(PLC_ERR_ALIGNMENT, "PixelShuffle(2) store needs Cout %% 32 == 0");
+  if ((long long)d->B * d->H * d->W >= (1ll << 31)) return fail(PLC_ERR_UNSUPPORTED, "B*H*W must be < 2^31");
+  return PLC_OK;
+}
+
+size_t plc_conv_packed_weight_bytes(const PlcConvDesc* d, int pack_kind) {
+  if (check_conv(d) != PLC_OK) return 0;
+  const size_t kk = static_cast<size_t>(d->k) * d->k;
+  if (pack_kind == PLC_PACK_FWD) return static_cast<size_t>(d->Cout) * kk * cdiv(d->Cin, 64) * 64 * 2;
+  if (pack_kind == PLC_PACK_DGRAD) return static_cast<size_t>(d->Cin) * kk * cdiv(d->Cout, 64) * 64 * 2;
+  fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
+  return 0;
+}
+
+int plc_conv_pack_weight(const PlcConvDesc* d, int pack_kind, const float* w_oihw, const float* bias, void* w_packed,
+                         float* bias_packed, void* stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  if (!w_oihw || !w_packed) return fail(PLC_ERR_NULL_ARG, "plc_conv_pack_weight: null pointer");
+  if (!aligned16(w_packed) || !aligned16(bias_packed)) return fail(PLC_ERR_ALIGNMENT, "packed buffers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pack_kind == PLC_PACK_FWD)
+    pack_w_conv_fwd_kernel<<<148 * 4, 256, 0, st>>>(w_oihw, bias, static_cast<__nv_bfloat16*>(w_packed), bias_packed,
+                                                    d->Cin, d->Cout, d->k, cdiv(d->Cin, 64), d->pixel_shuffle);
+  else if (pack_kind == PLC_PACK_DGRAD)
+    pack_w_conv_dgrad_kernel<<<148 * 4, 256, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), d->Cin, d->Cout,
+                                                      d->k, cdiv(d->Cout, 64));
+  else
+    return fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, void* out,
+                 void* stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  if (!x || !w_packed_fwd || !out) return fail(PLC_ERR_NULL_ARG, "plc_conv_fwd: null pointer");
+  if (!aligned16(x) || !aligned16(w_packed_fwd) || !aligned16(out) || !aligned16(bias_packed))
+    return fail(PLC_ERR_ALIGNMENT, "plc_conv_fwd: all device pointers must be 16-byte aligned");
+  PlcCellDesc cd{d->B, d->H, d->W, d->Cin, d->Cout, d->k, PLC_MODE_BF16_TC, 0};
+  TcGeom g;
+  pick_spatial_tile(d->H, d->W, &g);
+  plc::ConvTcParams q;
+  fill_geom(&cd, g, &q);
+  const int nt = pick_plain_n_tile(d->Cout);
+  q.num_n_tiles = cdiv(d->Cout, nt);
+  q.num_tiles = q.num_m_tiles * q.num_n_tiles;
+  q.chunks0 = cdiv(d->Cin, 64);
+  q.chunks1 = 0;
+  q.num_kb = d->k * d->k * q.chunks0;
+  q.n_total = d->Cout;
+  q.Cin = d->Cout;                     // no column split: everything goes to out0
+  q.out0 = static_cast<__nv_bfloat16*>(out);
+  q.plain_bias = d->has_bias ? bias_packed : nullptr;
+  q.plain_relu = d->relu;
+  q.plain_shuffle = d->pixel_shuffle;
+  const int cta = pick_cta_group(q.num_m_tiles);
+  CUtensorMap ta, tb;
+  if ((rc = make_tmap_act(&ta, x, d->B, d->H, d->W, d->Cin, g.tw, g.th))) return rc;
+  if ((rc = make_tmap_mat(&tb, w_packed_fwd, d->Cout, (long)q.num_kb * 64, 64, nt / cta))) return rc;
+  return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, ta, ta, static_cast<cudaStream_t>(stream));
+}
+
+int plc_conv_grad_mask(const PlcConvDesc* d, const void* y, const void* dy, void* dz, void* stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  if (!y || !dy || !dz) return fail(PLC_ERR_NULL_ARG, "plc_conv_grad_mask: null pointer");
+  const size_t npix = static_cast<size_t>(d->B) * d->H * d->W;
+  conv_grad_mask_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dz), npix,
+      d->H, d->W, d->Cout, d->relu, d->pixel_shuffle);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void* w_packed_dgrad, void* dx,
+                 float* dW_acc, float* db_acc, void* stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  if (!x || !dz) return fail(PLC_ERR_NULL_ARG, "plc_conv_bwd: null pointer");
+  if (dx && !w_packed_dgrad) return fail(PLC_ERR_NULL_ARG, "plc_conv_bwd: dgrad image missing");
+  if (!aligned16(x) || !aligned16(dz) || !aligned16(dx) || !aligned16(w_packed_dgrad))
+    return fail(PLC_ERR_ALIGNMENT, "plc_conv_bwd: all device pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dx) {   // dgrad: conv of dZ with the flipped / transposed image
+    PlcCellDesc cd{d->B, d->H, d->W, d->Cout, d->Cin, d->k, PLC_MODE_BF16_TC, 0};
+    TcGeom g;
+    pick_spatial_tile(d->H, d->W, &g);
+    plc::ConvTcParams q;
+    fill_geom(&cd, g, &q);
+    const int nt = pick_plain_n_tile(d->Cin);
+    q.num_n_tiles = cdiv(d->Cin, nt);
+    q.num_tiles = q.num_m_tiles * q.num_n_tiles;
+    q.chunks0 = cdiv(d->Cout, 64);
+    q.chunks1 = 0;
+    q.num_kb = d->k * d->k * q.chunks0;
+    q.n_total = d->Cin;
+    q.Cin = d->Cin;
+    q.out0 = static_cast<__nv_bfloat16*>(dx);
+    const int cta = pick_cta_group(q.num_m_tiles);
+    CUtensorMap tz, tb;
+    if ((rc = make_tmap_act(&tz, dz, d->B, d->H, d->W, d->Cout, g.tw, g.th))) return rc;
+    if ((rc = make_tmap_mat(&tb, w_packed_dgrad, d->Cin, (long)q.num_kb * 64, 64, nt / cta))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tb, tz, tz, st))) return rc;
+  }
+  if (dW_acc) {
+    WgradShape w{d->B, d->H, d->W, d->k, d->Cin, 0, d->Cout};
+    if ((rc = launch_wgrad_tc_shape(&w, x, nullptr, dz, dW_acc, d->has_bias ? db_acc : nullptr, st))) return rc;
   }
   return PLC_OK;
 }

@@ -244,3 +244,109 @@ class _HeadFn(torch.autograd.Function):
 def head(h: Tensor, weight: Tensor, bias: Optional[Tensor], mode: int) -> Tensor:
     """Differentiable 1x1 head: h [..., C] (contiguous, working layout) -> fp32 [...]."""
     return _HeadFn.apply(h.contiguous(), weight, bias, mode)
+
+
+# ------------------------------------------------------------------------------------------------ generic conv (bf16)
+from ._lib import PlcConvDesc  # noqa: E402
+
+
+def _rup(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+class ConvParams:
+    """Kernel-ready images of one plain conv layer's parameters, cached per parameter version.
+
+    Wraps the reference's `nn.Conv2d` PARAMETER HOLDER (weight [Cout, Cin, k, k], bias [Cout]); channel counts are
+    zero-padded to the kernel's granularity (Cin -> multiple of 8, Cout -> multiple of 8, or 32 with PixelShuffle)."""
+
+    def __init__(self, conv: torch.nn.Conv2d, relu: bool = False, pixel_shuffle: bool = False):
+        self.conv, self.relu, self.shuffle = conv, relu, pixel_shuffle
+        self.Cout, self.Cin, self.k, _ = conv.weight.shape
+        self.cin_p = _rup(self.Cin, 8)
+        self.cout_p = _rup(self.Cout, 32 if pixel_shuffle else 8)
+        self._cache = None
+
+    def desc(self, B, H, W) -> PlcConvDesc:
+        return PlcConvDesc(B, H, W, self.cin_p, self.cout_p, self.k, int(self.relu), int(self.shuffle),
+                           int(self.conv.bias is not None))
+
+    def packed(self, need_dgrad: bool):
+        w, b = self.conv.weight, self.conv.bias
+        key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version), str(w.device))
+        pc = self._cache
+        if pc is not None and pc[0] == key and (pc[3] is not None or not need_dgrad):
+            return pc[1], pc[2], pc[3]
+        lib = _lib.load()
+        wp = torch.zeros(self.cout_p, self.cin_p, self.k, self.k, device=w.device, dtype=torch.float32)
+        wp[:self.Cout, :self.Cin] = w.detach().to(torch.float32)
+        bp = None
+        if b is not None:
+            bp = torch.zeros(self.cout_p, device=w.device, dtype=torch.float32)
+            bp[:self.Cout] = b.detach().to(torch.float32)
+        d = self.desc(1, 1, 1)
+        fwd = torch.empty(lib.plc_conv_packed_weight_bytes(ctypes.byref(d), PLC_PACK_FWD), dtype=torch.uint8,
+                          device=w.device)
+        bias_packed = torch.zeros(self.cout_p, device=w.device, dtype=torch.float32)
+        _lib.check(lib.plc_conv_pack_weight(ctypes.byref(d), PLC_PACK_FWD, _ptr(wp), _ptr(bp), _ptr(fwd),
+                                            _ptr(bias_packed), _stream()), "plc_conv_pack_weight")
+        dg = None
+        if need_dgrad:
+            dg = torch.empty(lib.plc_conv_packed_weight_bytes(ctypes.byref(d), PLC_PACK_DGRAD), dtype=torch.uint8,
+                             device=w.device)
+            _lib.check(lib.plc_conv_pack_weight(ctypes.byref(d), PLC_PACK_DGRAD, _ptr(wp), None, _ptr(dg), None,
+                                                _stream()), "plc_conv_pack_weight")
+        self._cache = (key, fwd, bias_packed, dg)
+        return fwd, bias_packed, dg
+
+
+class _ConvFn(torch.autograd.Function):
+    """conv 'same' (+bias, +PixelShuffle(2), +ReLU) on NHWC bf16 tensors through plc_conv_fwd / plc_conv_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cp: ConvParams):
+        lib = _lib.load()
+        B, H, W, C = x.shape
+        if C != cp.cin_p or x.dtype != torch.bfloat16 or not x.is_contiguous():
+            raise RuntimeError(f"conv input must be contiguous bf16 [B,H,W,{cp.cin_p}], got {x.dtype} {tuple(x.shape)}")
+        fwd, bias_packed, _ = cp.packed(need_dgrad=torch.is_grad_enabled())
+        if cp.shuffle:
+            out = torch.empty(B, 2 * H, 2 * W, cp.cout_p // 4, dtype=torch.bfloat16, device=x.device)
+        else:
+            out = torch.empty(B, H, W, cp.cout_p, dtype=torch.bfloat16, device=x.device)
+        d = cp.desc(B, H, W)
+        _lib.check(lib.plc_conv_fwd(ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out), _stream()),
+                   "plc_conv_fwd")
+        ctx.cp = cp
+        ctx.save_for_backward(x, out)
+        ctx.x_needs_grad = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, out = ctx.saved_tensors
+        cp = ctx.cp
+        B, H, W, _ = x.shape
+        _, _, dg = cp.packed(need_dgrad=True)
+        d = cp.desc(B, H, W)
+        dy = dy.contiguous()
+        if cp.relu or cp.shuffle:
+            dz = torch.empty(B, H, W, cp.cout_p, dtype=torch.bfloat16, device=x.device)
+            _lib.check(lib.plc_conv_grad_mask(ctypes.byref(d), _ptr(out), _ptr(dy), _ptr(dz), _stream()),
+                       "plc_conv_grad_mask")
+        else:
+            dz = dy
+        dx = torch.empty_like(x) if ctx.x_needs_grad else None
+        dW = torch.zeros(cp.cout_p, cp.cin_p, cp.k, cp.k, dtype=torch.float32, device=x.device)
+        db = torch.zeros(cp.cout_p, dtype=torch.float32, device=x.device) if cp.conv.bias is not None else None
+        _lib.check(lib.plc_conv_bwd(ctypes.byref(d), _ptr(x), _ptr(dz), _ptr(dg), _ptr(dx), _ptr(dW), _ptr(db),
+                                    _stream()), "plc_conv_bwd")
+        gw = dW[:cp.Cout, :cp.Cin].to(cp.conv.weight.dtype)
+        gb = None if db is None else db[:cp.Cout].to(cp.conv.bias.dtype)
+        return dx, gw, gb, None
+
+
+def conv2d_same(x: Tensor, cp: ConvParams) -> Tensor:
+    """x [B,H,W,cin_p] bf16 -> [B,H,W,cout_p] (or [B,2H,2W,cout_p/4] with PixelShuffle); padded channels are zero."""
+    return _ConvFn.apply(x, cp.conv.weight, cp.conv.bias, cp)

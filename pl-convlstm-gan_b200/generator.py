@@ -6,8 +6,10 @@ checkpoint (``best_model.pth['model_state_dict']``, trainer.py:410-417) loads un
     upsample_blocks.{i}.conv.*, post_process.{0,2}.*
 The recurrence (cell1/cell2 over T steps, generator.py:156-171) runs in libplc.so.  The NON-recurrent body
 (front-end conv, PixelShuffle upsampling, DEM/LU gating, output head) is SURVEY.md section 8f "next-1": here it is plain
-PyTorch, restructured but arithmetically identical -- batched over T (it has no recurrence) and with the
-time-invariant attention gates hoisted out of the T loop (attention.py:13,26 depend only on static inputs).
+PyTorch in fp32 mode and NATIVE in bf16 mode: init_conv(+ReLU), the UpsampleBlock convs with PixelShuffle(2)+ReLU
+fused into the store, and both post_process convs run on the same tcgen05 implicit-GEMM core (plc_conv_fwd/bwd,
+NHWC bf16), batched over T (no recurrence there) with the time-invariant attention gates hoisted out of the T loop
+(attention.py:13,26 depend only on static inputs; they are computed once per forward with torch ops).
 Like the reference, ``upsample_blocks`` are created on first forward (generator.py:129-130; SURVEY.md section 5 gotcha 1);
 call ``materialize(scale)`` before ``load_state_dict`` when loading a checkpoint into a fresh model.
 """
@@ -19,6 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import functional as PF
 from .nn import ConvLSTMCell, _StackRolloutFn
 
 
@@ -75,6 +78,15 @@ class Generator(nn.Module):
         self.upsample_blocks = None                                                    # generator.py:64 (lazy)
         self.post_process = nn.Sequential(nn.Conv2d(hd1, 32, 3, padding=1), nn.ReLU(inplace=True),
                                           nn.Conv2d(32, 1, 3, padding=1))              # generator.py:67-71
+        self.mode = mode
+        self._native = {}      # name -> functional.ConvParams (kernel-ready images of the plain convs, bf16 mode)
+
+    def _cp(self, name: str, conv: nn.Conv2d, relu: bool, shuffle: bool = False):
+        cp = self._native.get(name)
+        if cp is None or cp.conv is not conv:
+            cp = PF.ConvParams(conv, relu=relu, pixel_shuffle=shuffle)
+            self._native[name] = cp
+        return cp
 
     def materialize(self, scale_factor: int, device=None) -> float:
         """Create the x2 upsample blocks for an integer scale (generator.py:73-92); returns the residual factor."""
@@ -111,6 +123,9 @@ class Generator(nn.Module):
         lu_hr = F.interpolate(lu, size=final_hw, mode="nearest")
         gate = self.dem_attn.gate(dem_hr) * self.lu_attn.gate(lu_hr)                    # generator.py:198-199
 
+        if self.mode == "bf16":
+            return self._forward_native(rain_lr, gate, remaining)
+
         # ---- front-end for all T frames at once (generator.py:166-168)
         x = F.relu(self.init_conv(_coord_channels(rain_lr.reshape(B * T, C, H, W))))
         hd0, hd1 = self.hidden_dims
@@ -141,3 +156,47 @@ class Generator(nn.Module):
         feat = (feat.view(B, T, hd1, hh, ww) * gate.unsqueeze(1)).view(B * T, hd1, hh, ww)
         out = self.post_process(feat)
         return out.view(B, T, 1, hh, ww)                                                # generator.py:205
+
+    def _forward_native(self, rain_lr: torch.Tensor, gate: torch.Tensor, remaining: float) -> torch.Tensor:
+        """bf16 mode: the whole per-step body in libplc.so (NHWC bf16, T-major batch [T*B, ...])."""
+        B, T, C, H, W = rain_lr.shape
+        dev = rain_lr.device
+        hd0, hd1 = self.hidden_dims
+        c1, c2 = self.cell1, self.cell2
+        # coord channels (coordconv.py:3-10) appended in NHWC, channels zero-padded to the kernel granularity
+        cp0 = self._cp("init", self.init_conv, relu=True)
+        x = rain_lr.permute(1, 0, 3, 4, 2).reshape(T * B, H, W, C)
+        rows = torch.linspace(0, 1, H, device=dev, dtype=x.dtype).view(1, H, 1, 1).expand(T * B, H, W, 1)
+        cols = torch.linspace(0, 1, W, device=dev, dtype=x.dtype).view(1, 1, W, 1).expand(T * B, H, W, 1)
+        x = F.pad(torch.cat([x, rows, cols], dim=-1), (0, cp0.cin_p - (C + 2))).to(torch.bfloat16).contiguous()
+        feat0 = PF.conv2d_same(x, cp0)                                                  # generator.py:166-168
+        xw = feat0.view(T, B, H, W, cp0.cout_p)
+        if cp0.cout_p != c1.working_cin:
+            xw = xw[..., :hd0]
+            xw = F.pad(xw, (0, c1.working_cin - hd0)).contiguous()
+        zeros = [torch.zeros(B, H, W, hd0, device=dev, dtype=c1.act_dtype),
+                 torch.zeros(B, H, W, hd0, device=dev, dtype=torch.float32),
+                 torch.zeros(B, H, W, hd1, device=dev, dtype=c2.act_dtype),
+                 torch.zeros(B, H, W, hd1, device=dev, dtype=torch.float32)]
+        outs = _StackRolloutFn.apply([c1, c2], T, xw, *zeros, c1.conv.weight, c1.conv.bias, c2.conv.weight,
+                                     c2.conv.bias)                                      # generator.py:156-171
+        feat = outs[0].reshape(T * B, H, W, hd1)
+        for i, blk in enumerate(self.upsample_blocks):                                  # generator.py:174-176
+            feat = PF.conv2d_same(feat, self._cp(f"up{i}", blk.conv, relu=True, shuffle=True))
+        if remaining > 1 or self.target_size is not None:                               # generator.py:179-195
+            f32 = feat.permute(0, 3, 1, 2).float()
+            if remaining > 1:
+                f32 = F.interpolate(f32, scale_factor=remaining, mode="bilinear", align_corners=False)
+            if self.target_size is not None:
+                f32 = F.interpolate(f32, size=self.target_size, mode="bilinear", align_corners=False)
+            feat = f32.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+        hh, ww = feat.shape[1:3]
+        g = gate.permute(0, 2, 3, 1).to(torch.bfloat16)                                 # [B,hh,ww,hd1], time-invariant
+        feat = (feat.view(T, B, hh, ww, hd1) * g.unsqueeze(0)).reshape(T * B, hh, ww, hd1)   # generator.py:198-199
+        cpa = self._cp("post0", self.post_process[0], relu=True)
+        cpb = self._cp("post2", self.post_process[2], relu=False)
+        y = PF.conv2d_same(feat.contiguous(), cpa)                                      # generator.py:202
+        if cpa.cout_p != cpb.cin_p:
+            y = F.pad(y[..., :cpa.Cout], (0, cpb.cin_p - cpa.Cout)).contiguous()
+        y = PF.conv2d_same(y, cpb)[..., 0]                                              # [T*B,hh,ww]
+        return y.float().view(T, B, hh, ww).permute(1, 0, 2, 3).unsqueeze(2)            # generator.py:205

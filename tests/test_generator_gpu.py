@@ -72,3 +72,24 @@ def test_generator_gradients_vs_reference_autograd(path, cuda_device):
         if rel_err(p.grad, ref) >= 2e-3:
             bad.append(report(name, p.grad, ref))
     assert not bad, " | ".join(bad)
+
+
+@pytest.mark.parametrize("path", golden_files("generator_b2"), ids=os.path.basename)
+def test_native_generator_gradients_bf16_vs_reference_autograd(path, cuda_device):
+    """bf16 mode: the WHOLE generator (front-end, recurrence, PixelShuffle upsampling, post_process) runs in
+    libplc.so forward and backward; parameter gradients against the reference's fp32 autograd.  Tolerance 6e-2 of the
+    per-tensor max (bf16 activations and gradients through ~8 conv layers and T steps)."""
+    g = load_golden(path)
+    gen = _build(g, "bf16", cuda_device)
+    rain, dem, lu = (torch.from_numpy(g[k]).to(cuda_device) for k in ("rain", "dem", "lu"))
+    pred = gen(rain, dem, lu)
+    total, _ = L.combined_loss(pred, rain, torch.from_numpy(g["s_coords"]).to(cuda_device),
+                               torch.from_numpy(g["s_vals"]).to(cuda_device), scale_factor=int(g["scale"]))
+    total.backward()
+    bad = []
+    for name, p in gen.named_parameters():
+        ref = torch.from_numpy(g["grad." + name])
+        assert p.grad is not None, name
+        if rel_err(p.grad, ref) >= 6e-2:
+            bad.append(report(name, p.grad, ref))
+    assert not bad, " | ".join(bad)

@@ -124,3 +124,43 @@ def test_head_forward_backward_vs_torch(cuda_device):
     assert rel_err(h.grad, hf.grad) < 1e-2            # bf16 output rounding
     assert rel_err(conv.weight.grad.reshape(-1), w.grad.reshape(-1)) < 1e-4
     assert rel_err(conv.bias.grad, b.grad) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", [(2, 9, 13, 32, 128, 3, True, True), (1, 16, 16, 64, 32, 3, True, False),
+                                 (2, 7, 20, 32, 1, 3, False, False), (1, 12, 12, 3, 64, 3, True, False),
+                                 (1, 8, 8, 16, 32, 1, False, False)],
+                         ids=lambda c: "B%d_%dx%d_%d-%d_k%d_relu%d_ps%d" % tuple(int(v) for v in c))
+def test_generic_conv_forward_backward_vs_torch(cfg, cuda_device):
+    """plc_conv_fwd/bwd (plain convs of the Generator body: generator.py:10-28, 67-71) vs torch fp32 on the same
+    bf16-rounded operands: conv + bias (+PixelShuffle(2)) (+ReLU), dx / dW / db."""
+    from plconv import functional as PF
+    B, H, W, cin, cout, k, relu, ps = cfg
+    torch.manual_seed(11)
+    conv = torch.nn.Conv2d(cin, cout, k, padding=k // 2).to(cuda_device)
+    cp = PF.ConvParams(conv, relu=relu, pixel_shuffle=ps)
+    x = torch.randn(B, cin, H, W, device=cuda_device)
+    xw = torch.nn.functional.pad(x.permute(0, 2, 3, 1), (0, cp.cin_p - cin)).to(torch.bfloat16).contiguous()
+    xw.requires_grad_()
+    y = PF.conv2d_same(xw, cp)
+    # torch restatement on bf16-rounded operands
+    xr = xw.detach()[..., :cin].float().permute(0, 3, 1, 2).requires_grad_()
+    wr = conv.weight.detach().to(torch.bfloat16).float().requires_grad_()
+    br = conv.bias.detach().clone().requires_grad_()
+    yr = torch.nn.functional.conv2d(xr, wr, br, padding=k // 2)
+    if ps:
+        yr = torch.nn.functional.pixel_shuffle(yr, 2)
+    if relu:
+        yr = torch.relu(yr)
+    co = cout // 4 if ps else cout
+    got = y[..., :co].permute(0, 3, 1, 2)
+    assert rel_err(got, yr) < 1e-2, report("y", got, yr)
+    if y.shape[-1] > co:
+        assert float(y.detach()[..., co:].abs().max()) == 0.0           # padded output channels stay zero
+    gy = torch.randn_like(yr)
+    gyw = torch.zeros_like(y)
+    gyw[..., :co] = gy.permute(0, 2, 3, 1).to(torch.bfloat16)
+    y.backward(gyw)
+    (yr * gyw[..., :co].float().permute(0, 3, 1, 2)).sum().backward()
+    assert rel_err(xw.grad[..., :cin].permute(0, 3, 1, 2), xr.grad) < 2e-2
+    assert rel_err(conv.weight.grad, wr.grad) < 2e-2, report("dW", conv.weight.grad, wr.grad)
+    assert rel_err(conv.bias.grad, br.grad) < 2e-2
