@@ -65,6 +65,29 @@ class NowcastRunner:
         self.cell_launches_per_run = L * (model.t_in + model.t_out)
         self.launches_per_run = 1 + self.cell_launches_per_run + 1
 
+    # ------------------------------------------------------------------ CUDA graph (launch-bound shapes)
+    def capture(self, frames_like: Tensor):
+        """Capture one whole rollout (front-end, T x L cell steps, head: 2 + L*(T_in+T_out) launches + state
+        resets) into a CUDA graph.  Worth it when a cell step is shorter than its host-side launch cost (small
+        frames / narrow hidden sizes); the tensor maps are kernel parameters, so they are baked into the graph and
+        every buffer involved is one of the runner's preallocated tensors.  Returns self; use :meth:`replay`."""
+        self._g_in = torch.empty_like(frames_like)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                         # warm-up outside capture (lazy module loading etc.)
+            self.run(self._g_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_out = self.run(self._g_in)
+        return self
+
+    def replay(self, frames: Tensor) -> Tensor:
+        """Run the captured rollout on new frames (copied into the graph's static input buffer)."""
+        self._g_in.copy_(frames, non_blocking=True)
+        self._graph.replay()
+        return self._g_out
+
     def _cell(self, pw, x, h_prev, c, h_out, events):
         if events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
