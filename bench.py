@@ -181,8 +181,9 @@ def committed_traffic():
 
 
 TRAIN = dict(global_batch=64, H=128, W=128, C=64, hidden=[64, 64], k=3, T=20)
-TRAIN_WORKLOAD = ("cfg3-style: 2-layer ConvLSTM (hidden [64,64], k3) recurrence training step, fwd + BPTT + grad "
-                  "all-reduce + clip + Adam, 128x128, T=20, global batch 64 sharded by batch")
+TRAIN_WORKLOAD = ("cfg3-style: encoder-forecaster generator training step (front-end conv, 2-layer ConvLSTM hidden [64,64] "
+                  "k3 encoder T=10 + forecaster T=10, 1x1 head, L1 frame loss): fwd + BPTT + grad all-reduce + clip + "
+                  "Adam, 128x128, global batch 64 sharded by batch; no discriminator exists in the reference")
 
 
 def run_train(args):
@@ -201,18 +202,17 @@ def run_train(args):
     sl = shard_batch(cfg["global_batch"], rank, world)
     B = sl.stop - sl.start
     torch.manual_seed(1234)                       # identical weights on every rank
-    stack = plconv.ConvLSTMStack(cfg["C"], cfg["hidden"], cfg["k"], True, "bf16").to(dev)
+    gen = plconv.NowcastGenerator(1, cfg["hidden"], cfg["k"], cfg["T"] // 2, cfg["T"] // 2, "bf16").to(dev)
     torch.manual_seed(1234 + rank)
-    xs = torch.relu(torch.randn(cfg["T"], B, cfg["H"], cfg["W"], cfg["C"], device=dev)).to(torch.bfloat16)
-    tgt = torch.rand(cfg["T"], B, cfg["H"], cfg["W"], device=dev)      # target frames (1 channel, like the reference)
-    head = torch.nn.Conv2d(cfg["hidden"][-1], 1, 1).to(dev)             # 1x1 output head (parameter holder)
-    from plconv import functional as PF
-    step = TrainStep(stack, [c.parameters() for c in stack.cells] + [head.parameters()], lr=5e-4, grad_clip_norm=0.5)
+    frames = torch.relu(torch.randn(B, cfg["T"] // 2, 1, cfg["H"], cfg["W"], device=dev) + 0.3)
+    tgt = torch.relu(torch.randn(B, cfg["T"] // 2, 1, cfg["H"], cfg["W"], device=dev) + 0.3)
+    groups = [c.parameters() for c in gen.encoder.cells] + [c.parameters() for c in gen.forecaster.cells] + \
+             [list(gen.init_conv.parameters()) + list(gen.head.parameters())]
+    step = TrainStep(gen, groups, lr=5e-4, grad_clip_norm=0.5)
 
     def forward_loss():
-        out, _ = stack.run_seq(xs)                 # fused rollout: one autograd node, explicit BPTT
-        frames = PF.head(out, head.weight, head.bias, plconv.PLC_MODE_BF16_TC)   # [T,B,H,W] fp32 (plc_head_fwd/bwd)
-        return (frames - tgt).abs().mean()         # L1 on frames, as the reference's loss terms (combined_loss.py)
+        pred = gen(frames)                         # front-end conv -> encoder -> forecaster -> head, all in libplc.so
+        return (pred - tgt).abs().mean()           # L1 on frames, as the reference's loss terms (combined_loss.py)
 
     def barrier():
         if world > 1:
@@ -241,19 +241,18 @@ def run_train(args):
         ms = float(t.item())
     if rank == 0:
         L = len(cfg["hidden"])
-        flops_fwd = sum(2.0 * cfg["H"] * cfg["W"] * (ci + ch) * cfg["k"] ** 2 * 4 * ch
-                        for ci, ch in zip([cfg["C"]] + cfg["hidden"][:-1], cfg["hidden"])) * cfg["T"]
+        flops_fwd = gen.cell_flops_per_sequence(cfg["H"], cfg["W"])
         seqs = cfg["global_batch"] * K
         peak_sus, peak_burst, peak_src = measured_peaks()
         algo_tf = 3.0 * flops_fwd * seqs / (ms * 1e-3) / 1e12 / world
         print(json.dumps({
-            "metric": "recurrence_train_sequences_per_sec", "value": seqs / (ms * 1e-3), "unit": "sequences/s",
+            "metric": "generator_train_sequences_per_sec", "value": seqs / (ms * 1e-3), "unit": "sequences/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": TRAIN_WORKLOAD, "global_batch": cfg["global_batch"], "per_gpu_batch": B,
                        "parallelism": f"dp{world} (batch shards + NCCL grad all-reduce overlapped with BPTT)",
                        "l2": "inputs larger than L2"},
-            "gpu_launches": K * (cfg["T"] * L * (1 + 3) + 2),
+            "gpu_launches": K * (cfg["T"] * L * (1 + 3) + 8),
             "loss": None if loss is None else float(loss),
             "roofline": {"bound": "tensor", "achieved": algo_tf, "peak": peak_sus, "unit": "TFLOP/s",
                          "frac": algo_tf / peak_sus, "peak_source": peak_src,

@@ -160,6 +160,11 @@ int plc_frontend_fwd(const float* frames, int N, int Cf, int H, int W, const flo
 int plc_head_fwd(const void* h, long npix, int C, const float* w, const float* bias, int mode, float* out,
                  void* stream);
 
+/* frames [B,T,Cf,H,W] fp32 (layout of the reference's rain_lr, generator.py:96) -> [T*B,H,W,Cp] bf16, T-major, with
+ * the coordinate planes of add_coord_channels (coordconv.py:3-10) appended and zero padding to Cp (Cp % 8 == 0,
+ * Cp >= Cf+2): the NHWC input of init_conv when it runs on the tensor-core conv (plc_conv_fwd).                */
+int plc_frames_to_nhwc(const float* frames, int B, int T, int Cf, int H, int W, int Cp, void* out, void* stream);
+
 /* backward of plc_head_fwd (bf16 mode): dh [npix, C] bf16 = dy * w;  dw_acc [C] += sum dy * h;  db_acc [1] += sum dy
  * (db_acc may be NULL).  dy [npix] fp32.                                                                       */
 int plc_head_bwd(const void* h, long npix, int C, const float* w, const float* dy, void* dh, float* dw_acc,

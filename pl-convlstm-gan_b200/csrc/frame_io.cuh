@@ -153,6 +153,34 @@ __global__ void head_kernel(const TIn* __restrict__ h, const float* __restrict__
   out[p] = acc;
 }
 
+// frames [B, T, Cf, H, W] fp32 (reference layout of rain_lr) -> [T*B, H, W, Cp] bf16, T-major, with the two coordinate
+// planes of coordconv.py:3-10 appended (row = y/(H-1), col = x/(W-1)) and zero padding up to Cp channels (Cp % 8 == 0).
+__global__ void __launch_bounds__(256) frames_to_nhwc_kernel(const float* __restrict__ frames,
+                                                             __nv_bfloat16* __restrict__ out, int B, int T, int Cf,
+                                                             int H, int W, int Cp) {
+  const size_t npix = static_cast<size_t>(B) * T * H * W;
+  const float inv_h = H > 1 ? 1.f / (H - 1) : 0.f, inv_w = W > 1 ? 1.f / (W - 1) : 0.f;
+  for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < npix;
+       p += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(p % W);
+    size_t r = p / W;
+    const int y = static_cast<int>(r % H);
+    r /= H;
+    const int b = static_cast<int>(r % B);
+    const int t = static_cast<int>(r / B);
+    const float* src = frames + ((static_cast<size_t>(b) * T + t) * Cf) * H * W + static_cast<size_t>(y) * W + x;
+    for (int c0 = 0; c0 < Cp; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        v[j] = c < Cf ? __ldg(src + static_cast<size_t>(c) * H * W) : (c == Cf ? y * inv_h : (c == Cf + 1 ? x * inv_w : 0.f));
+      }
+      store8<__nv_bfloat16>(out + p * Cp + c0, v);
+    }
+  }
+}
+
 // Backward of the 1x1 head: y[p] = sum_c h[p][c] * w[c] + b
 //   dh[p][c] = dy[p] * w[c]  (bf16, coalesced: G = C/8 lanes per pixel)
 //   dw[c]   += sum_p dy[p] * h[p][c],   db += sum_p dy[p]       (block partial sums -> atomics)

@@ -899,6 +899,17 @@ int plc_head_fwd(const void* h, long npix, int C, const float* w, const float* b
   return PLC_OK;
 }
 
+int plc_frames_to_nhwc(const float* frames, int B, int T, int Cf, int H, int W, int Cp, void* out, void* stream) {
+  if (!frames || !out) return fail(PLC_ERR_NULL_ARG, "plc_frames_to_nhwc: null pointer");
+  if (B <= 0 || T <= 0 || Cf <= 0 || H <= 0 || W <= 0 || Cp < Cf + 2 || Cp % 8)
+    return fail(PLC_ERR_BAD_DESC, "plc_frames_to_nhwc: need Cp %% 8 == 0 and Cp >= Cf + 2 (got Cf=%d Cp=%d)", Cf, Cp);
+  if (!aligned16(out)) return fail(PLC_ERR_ALIGNMENT, "plc_frames_to_nhwc: out must be 16-byte aligned");
+  plc::frames_to_nhwc_kernel<<<sm_count() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, static_cast<__nv_bfloat16*>(out), B, T, Cf, H, W, Cp);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
 int plc_head_bwd(const void* h, long npix, int C, const float* w, const float* dy, void* dh, float* dw_acc,
                  float* db_acc, void* stream) {
   if (!h || !w || !dy || !dh || !dw_acc) return fail(PLC_ERR_NULL_ARG, "plc_head_bwd: null pointer");

@@ -350,3 +350,28 @@ class _ConvFn(torch.autograd.Function):
 def conv2d_same(x: Tensor, cp: ConvParams) -> Tensor:
     """x [B,H,W,cin_p] bf16 -> [B,H,W,cout_p] (or [B,2H,2W,cout_p/4] with PixelShuffle); padded channels are zero."""
     return _ConvFn.apply(x, cp.conv.weight, cp.conv.bias, cp)
+
+
+def frames_to_nhwc(frames: Tensor, c_pad: int, out: Optional[Tensor] = None) -> Tensor:
+    """frames [B,T,Cf,H,W] fp32 -> [T*B,H,W,c_pad] bf16 (T-major) with the coordconv planes appended
+    (coordconv.py:3-10); the input of init_conv on the tensor-core conv."""
+    lib = _lib.load()
+    B, T, Cf, H, W = frames.shape
+    _require_cuda(frames, "frames")
+    if frames.dtype != torch.float32:
+        raise RuntimeError("frames must be float32")
+    if out is None:
+        out = torch.empty(T * B, H, W, c_pad, dtype=torch.bfloat16, device=frames.device)
+    _lib.check(lib.plc_frames_to_nhwc(_ptr(frames), B, T, Cf, H, W, c_pad, _ptr(out), _stream()), "plc_frames_to_nhwc")
+    return out
+
+
+def conv2d_same_into(x: Tensor, cp: ConvParams, out: Tensor) -> Tensor:
+    """Inference-only conv into a preallocated buffer (no autograd node)."""
+    lib = _lib.load()
+    B, H, W, _ = x.shape
+    fwd, bias_packed, _ = cp.packed(need_dgrad=False)
+    d = cp.desc(B, H, W)
+    _lib.check(lib.plc_conv_fwd(ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out), _stream()),
+               "plc_conv_fwd")
+    return out

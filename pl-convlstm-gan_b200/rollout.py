@@ -35,6 +35,27 @@ class NowcastGenerator(nn.Module):
         self.forecaster = ConvLSTMStack(0, self.hidden_dims, kernel_size, True, mode)
         self.head = nn.Conv2d(self.hidden_dims[-1], 1, 1)                   # parameter holder
 
+    def forward(self, frames: Tensor) -> Tensor:
+        """Differentiable rollout (training): frames [B,T_in,Cf,H,W] fp32 -> predicted frames [B,T_out,1,H,W] fp32.
+        bf16 mode only (every layer runs in libplc.so: front-end on the tensor-core conv, fused BPTT, 1x1 head)."""
+        if self.mode != "bf16":
+            raise RuntimeError("NowcastGenerator.forward is implemented for mode='bf16'")
+        B, T, Cf, H, W = frames.shape
+        cp0 = self._init_cp()
+        x = F.frames_to_nhwc(frames.contiguous(), cp0.cin_p)                       # + coord planes (coordconv.py:3-10)
+        feat = F.conv2d_same(x, cp0).view(T, B, H, W, cp0.cout_p)                   # generator.py:166-168
+        _, state = self.encoder.run_seq(feat)
+        out, _ = self.forecaster.run_seq(None, state, steps=self.t_out)            # [T_out,B,H,W,Ch]
+        y = F.head(out, self.head.weight, self.head.bias, _MODES[self.mode])       # [T_out,B,H,W] fp32
+        return y.permute(1, 0, 2, 3).unsqueeze(2)
+
+    def _init_cp(self):
+        cp = getattr(self, "_cp_init", None)
+        if cp is None or cp.conv is not self.init_conv:
+            cp = F.ConvParams(self.init_conv, relu=True)
+            object.__setattr__(self, "_cp_init", cp)
+        return cp
+
     def cell_flops_per_sequence(self, H: int, W: int) -> float:
         """Algorithmic FLOPs (2*M*N*K of every gate conv) for ONE sequence through encoder + forecaster."""
         tot = 0.0
@@ -55,6 +76,11 @@ class NowcastRunner:
         hd = model.hidden_dims
         L = len(hd)
         self.feat = torch.zeros(model.t_in * B, H, W, model.encoder.cells[0].working_cin, dtype=adt, device=device)
+        # bf16 mode: the front-end conv runs on the tensor-core conv (init_conv + ReLU), fed by a coord-plane prep kernel
+        self.tc_frontend = model.mode == "bf16" and model.hidden_dims[0] % 8 == 0
+        if self.tc_frontend:
+            self.cp0 = model._init_cp()
+            self.x8 = torch.zeros(model.t_in * B, H, W, self.cp0.cin_p, dtype=torch.bfloat16, device=device)
         # per layer: two h buffers (ping-pong; halo reads forbid in-place) and one c buffer (in-place is safe)
         self.h = [[torch.zeros(B, H, W, hd[l], dtype=adt, device=device) for _ in range(2)] for l in range(L)]
         self.c = [torch.zeros(B, H, W, hd[l], dtype=torch.float32, device=device) for l in range(L)]
@@ -63,7 +89,7 @@ class NowcastRunner:
         self.enc_pw = [c._packed(False) for c in model.encoder.cells]
         self.fc_pw = [c._packed(False) for c in model.forecaster.cells]
         self.cell_launches_per_run = L * (model.t_in + model.t_out)
-        self.launches_per_run = 1 + self.cell_launches_per_run + 1
+        self.launches_per_run = (2 if self.tc_frontend else 1) + self.cell_launches_per_run + 1
 
     # ------------------------------------------------------------------ CUDA graph (launch-bound shapes)
     def capture(self, frames_like: Tensor):
@@ -104,10 +130,14 @@ class NowcastRunner:
         per cell launch."""
         m, B, L = self.m, self.B, len(self.c)
         T_in, T_out = m.t_in, m.t_out
-        # [B,T,Cf,H,W] -> [T*B,Cf,H,W]: front-end for all steps in one launch
-        fr = frames.transpose(0, 1).reshape(T_in * B, m.in_channels, self.H, self.W).contiguous()
-        F.frontend_forward(fr, m.init_conv.weight, m.init_conv.bias, self.mode, c_stride=self.feat.shape[-1],
-                           out=self.feat)
+        # front-end for all T_in steps at once (T-major batch [T*B, ...])
+        if self.tc_frontend:
+            F.frames_to_nhwc(frames, self.cp0.cin_p, out=self.x8)
+            F.conv2d_same_into(self.x8, self.cp0, self.feat)
+        else:
+            fr = frames.transpose(0, 1).reshape(T_in * B, m.in_channels, self.H, self.W).contiguous()
+            F.frontend_forward(fr, m.init_conv.weight, m.init_conv.bias, self.mode, c_stride=self.feat.shape[-1],
+                               out=self.feat)
         for l in range(L):                                   # generator.py:156-160: zero initial state
             self.h[l][0].zero_()
             self.c[l].zero_()
