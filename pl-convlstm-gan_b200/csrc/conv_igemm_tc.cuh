@@ -35,8 +35,11 @@ struct ConvTcParams {
   int tw, th, tw_log2;       // tile = th x tw pixels, tw*th == 128, tw power of two
   int tiles_x, tiles_y;      // per image
   int num_m_tiles, num_n_tiles, num_tiles;
-  int chunks0, chunks1;      // 64-channel K chunks of source 0 / source 1
-  int num_kb;                // ksize^2 * (chunks0 + chunks1)
+  int kc;                    // channels per TMA box: 64, 32 or 16 (narrow sources pack G = 64/kc taps into one K stage)
+  int chunks0, chunks1;      // kc-channel chunks of source 0 / source 1
+  int num_boxes;             // ksize^2 * (chunks0 + chunks1) boxes of [kc ch x 128 px]
+  int num_kb;                // K stages of 64 elements = ceil(num_boxes / (64/kc)); tail boxes repeat the last one
+                             // against zero weights
   // LSTM epilogues
   int Ch;                    // hidden channels
   int Cin;                   // EPI_PLAIN: first Cin output columns go to out0, the rest to out1
@@ -191,46 +194,62 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     // ===================================================================== TMA producer
     uint32_t stage = 0, phase = 0;
     const int kk = p.ksize * p.ksize;
+    const int G = kBlockK / p.kc;
+    const uint32_t sub_bytes = kTileM * p.kc * 2;         // one [128 px][kc ch] box
     const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b), full_base = smem_u32(full_bar);
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       int n_tile, b, y0, x0;
       decode_tile<kCta>(p, tile, rank, n_tile, b, y0, x0);
       const int n_row = n_tile * N_TILE + rank * (N_TILE / kCta);
-      int kb = 0;
-      for (int src = 0; src < 2; ++src) {
-        const int chunks = src ? p.chunks1 : p.chunks0;
-        const CUtensorMap* tm = src ? &tmap_a1 : &tmap_a0;
-        if (chunks == 0) continue;
-        for (int tap = 0; tap < kk; ++tap) {
+      // box iterator over (source, tap, kc-chunk); G boxes fill one 64-element K stage
+      int src = p.chunks0 > 0 ? 0 : 1, tap = 0, ck = 0, bx = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t a_dst = a_base + stage * kABytes, b_dst = b_base + stage * Cfg::kBBytes;
+        uint32_t bar;
+        if constexpr (kCta == 1) {
+          bar = full_base + stage * 8;
+          if (elect_one()) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        } else {
+          // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there)
+          bar = mapa_u32(full_base + stage * 8, 0);
+          if (rank == 0 && elect_one()) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+        }
+        __syncwarp();
+        for (int g = 0; g < G; ++g) {
           const int dy = tap / p.ksize - p.pad;
-          const int dx = tap % p.ksize - p.pad;
-          for (int ck = 0; ck < chunks; ++ck, ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (elect_one()) {
-              const uint32_t a_dst = a_base + stage * kABytes, b_dst = b_base + stage * Cfg::kBBytes;
-              if constexpr (kCta == 1) {
-                mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                tma_load_4d_s(a_dst, tm, full_base + stage * 8, ck * kBlockK, x0 + dx, y0 + dy, b);
-                tma_load_2d_s(b_dst, &tmap_b, full_base + stage * 8, kb * kBlockK, n_row);
-              } else {
-                // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there)
-                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-                const uint32_t lead_bar = mapa_u32(full_base + stage * 8, 0);
-                tma_load_4d_cg2(a_dst, tm, lead_bar, ck * kBlockK, x0 + dx, y0 + dy, b);
-                tma_load_2d_cg2(b_dst, &tmap_b, lead_bar, kb * kBlockK, n_row);
-              }
+          const int dx = tap - (tap / p.ksize) * p.ksize - p.pad;
+          if (elect_one()) {
+            const CUtensorMap* tm = src ? &tmap_a1 : &tmap_a0;
+            if constexpr (kCta == 1) tma_load_4d_s(a_dst + g * sub_bytes, tm, bar, ck * p.kc, x0 + dx, y0 + dy, b);
+            else tma_load_4d_cg2(a_dst + g * sub_bytes, tm, bar, ck * p.kc, x0 + dx, y0 + dy, b);
+          }
+          if (bx + 1 < p.num_boxes) {       // advance; the K tail re-loads the last box (its weights are zero)
+            ++bx;
+            if (++ck == (src ? p.chunks1 : p.chunks0)) {
+              ck = 0;
+              if (++tap == kk) { tap = 0; src = 1; }
             }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
+        if (elect_one()) {
+          if constexpr (kCta == 1) tma_load_2d_s(b_dst, &tmap_b, bar, kb * kBlockK, n_row);
+          else tma_load_2d_cg2(b_dst, &tmap_b, bar, kb * kBlockK, n_row);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && rank == 0) {
     // ===================================================================== MMA issuer (leader CTA only)
     constexpr uint32_t idesc = make_idesc_bf16(kTileM * kCta, N_TILE, 0, 0);
-    const uint64_t adesc0 = make_smem_desc(smem_u32(smem_a), 0, 1024);
+    const uint64_t adesc0 = make_smem_desc_kmajor(smem_u32(smem_a), p.kc * 2);   // rows of kc bf16, matching swizzle
     const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), 0, 1024);
+    // A offset (16-byte units) of the k-th UMMA_K=16 slice of a stage: box (16k / kc), then 32 bytes per slice inside it
+    uint32_t aoff[kBlockK / 16];
+#pragma unroll
+    for (int k = 0; k < kBlockK / 16; ++k)
+      aoff[k] = (((16 * k) / p.kc) * (kTileM * p.kc * 2) + ((16 * k) % p.kc) * 2) >> 4;
     uint32_t stage = 0, phase = 0;
     int it = 0;
     long long t_empty = 0, t_full = 0, t0 = clock64();
@@ -254,7 +273,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 bytes per UMMA_K=16 inside the 128-byte swizzle atom
-            umma_bf16<kCta>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16<kCta>(d_tmem, adesc + aoff[k], bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if constexpr (kCta == 1) {

@@ -165,31 +165,58 @@ int pick_plain_n_tile(int n_total) {
   return best;
 }
 
+// K-side geometry: sources with C0 and C1 channels are read as TMA boxes of kc channels (64, 32 or 16); G = 64/kc
+// boxes (consecutive (source, tap, chunk) triples) fill one 64-element K stage.  Pick the kc with the fewest stages.
+struct KGeom { int kc, chunks0, chunks1, num_boxes, num_kb; };
+KGeom kgeom(int C0, int C1, int k) {
+  KGeom best{};
+  const int cands[3] = {64, 32, 16};
+  for (int kc : cands) {
+    KGeom g;
+    g.kc = kc;
+    g.chunks0 = cdiv(C0, kc);
+    g.chunks1 = cdiv(C1, kc);
+    g.num_boxes = k * k * (g.chunks0 + g.chunks1);
+    g.num_kb = cdiv(g.num_boxes, 64 / kc);
+    if (best.kc == 0 || g.num_kb < best.num_kb) best = g;
+  }
+  return best;
+}
+CUtensorMapSwizzle swizzle_for_kc(int kc) {
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+// packed K index kp -> input channel of cat(src0, src1) and tap; returns -1 for padding
+__device__ __forceinline__ int decode_packed_k(int kp, int kc, int kk, int chunks0, int chunks1, int C0, int C1,
+                                               int& tap) {
+  const int G = 64 / kc;
+  const int box = (kp >> 6) * G + (kp & 63) / kc, jj = (kp & 63) % kc;
+  tap = 0;
+  if (box >= kk * (chunks0 + chunks1)) return -1;
+  if (box < kk * chunks0) {
+    tap = box / chunks0;
+    const int c = (box % chunks0) * kc + jj;
+    return c < C0 ? c : -1;
+  }
+  const int b1 = box - kk * chunks0;
+  tap = b1 / chunks1;
+  const int c = (b1 % chunks1) * kc + jj;
+  return c < C1 ? C0 + c : -1;
+}
+
 // ------------------------------------------------------------------ bf16 packing kernels
 // forward image Wp[n'][k'] : n' = slice*N_TILE + gate*CH_TILE + j ; k' = kb*64 + jj, kb = (src, tap, chunk)
 __global__ void pack_w_tc_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Ch,
-                                     int ksize, int ch_tile, int chunks0, int chunks1) {
+                                     int ksize, int ch_tile, KGeom kg) {
   const int kk = ksize * ksize, ctot = Cin + Ch;
-  const int ktot = kk * (chunks0 + chunks1) * 64, ntot = 4 * Ch, n_tile = 4 * ch_tile;
+  const int ktot = kg.num_kb * 64, ntot = 4 * Ch, n_tile = 4 * ch_tile;
   const size_t total = static_cast<size_t>(ntot) * ktot;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int kp = idx % ktot, np = idx / ktot;
     const int slice = np / n_tile, r = np % n_tile, gate = r / ch_tile, j = r % ch_tile;
     const int o = gate * Ch + slice * ch_tile + j;
-    int kb = kp >> 6;
-    const int jj = kp & 63;
-    int ic = -1, tap = 0;
-    if (kb < kk * chunks0) {
-      tap = kb / chunks0;
-      const int c = (kb % chunks0) * 64 + jj;
-      if (c < Cin) ic = c;
-    } else {
-      kb -= kk * chunks0;
-      tap = kb / chunks1;
-      const int c = (kb % chunks1) * 64 + jj;
-      if (c < Ch) ic = Cin + c;
-    }
+    int tap;
+    const int ic = decode_packed_k(kp, kg.kc, kk, kg.chunks0, kg.chunks1, Cin, Ch, tap);
     float v = 0.f;
     if (ic >= 0) v = w[(static_cast<size_t>(o) * ctot + ic) * kk + tap];
     out[idx] = __float2bfloat16(v);
@@ -199,35 +226,34 @@ __global__ void pack_w_tc_fwd_kernel(const float* __restrict__ w, __nv_bfloat16*
 // PixelShuffle(2) store (natural channel n = c*4 + sub), else n' = n.  bias_p[n'] = bias[n].
 __global__ void pack_w_conv_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                        __nv_bfloat16* __restrict__ out, float* __restrict__ bias_p, int Cin, int Cout,
-                                       int ksize, int chunks, int shuffle) {
-  const int kk = ksize * ksize, ktot = kk * chunks * 64, cps = Cout >> 2;
+                                       int ksize, KGeom kg, int shuffle) {
+  const int kk = ksize * ksize, ktot = kg.num_kb * 64, cps = Cout >> 2;
   const size_t total = static_cast<size_t>(Cout) * ktot;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int kp = idx % ktot, np = idx / ktot;
     const int n = shuffle ? (np % cps) * 4 + np / cps : np;
-    const int kb = kp >> 6, jj = kp & 63;
-    const int tap = kb / chunks, c = (kb % chunks) * 64 + jj;
+    int tap;
+    const int c = decode_packed_k(kp, kg.kc, kk, kg.chunks0, 0, Cin, 0, tap);
     float v = 0.f;
-    if (c < Cin) v = w[(static_cast<size_t>(n) * Cin + c) * kk + tap];
+    if (c >= 0) v = w[(static_cast<size_t>(n) * Cin + c) * kk + tap];
     out[idx] = __float2bfloat16(v);
     if (kp == 0 && bias_p) bias_p[np] = bias ? bias[n] : 0.f;
   }
 }
 // generic dgrad image Wd[c][k'] : rows c in [0, ctot) ; k' = (tap', chunk of dZ channel n)*64 + jj, flipped taps
 __global__ void pack_w_conv_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int ctot,
-                                         int nout, int ksize, int chunksz) {
+                                         int nout, int ksize, KGeom kg) {
   const int kk = ksize * ksize;
-  const int ktot = kk * chunksz * 64;
+  const int ktot = kg.num_kb * 64;
   const size_t total = static_cast<size_t>(ctot) * ktot;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int kp = idx % ktot, c = idx / ktot;
-    const int kb = kp >> 6, jj = kp & 63;
-    const int tap = kb / chunksz;
-    const int n = (kb % chunksz) * 64 + jj;
+    int tap;
+    const int n = decode_packed_k(kp, kg.kc, kk, kg.chunks0, 0, nout, 0, tap);
     float v = 0.f;
-    if (n < nout) {
+    if (n >= 0) {
       const int fy = ksize - 1 - tap / ksize, fx = ksize - 1 - tap % ksize;
       v = w[(static_cast<size_t>(n) * ctot + c) * kk + fy * ksize + fx];
     }
@@ -368,6 +394,10 @@ void fill_geom(const PlcCellDesc* d, const TcGeom& g, plc::ConvTcParams* p) {
   p->Ch = d->Ch; p->Cin = d->Cin;
 }
 
+void set_kgeom(plc::ConvTcParams* p, const KGeom& kg) {
+  p->kc = kg.kc; p->chunks0 = kg.chunks0; p->chunks1 = kg.chunks1; p->num_boxes = kg.num_boxes; p->num_kb = kg.num_kb;
+}
+
 int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p) {
   g->ch_tile = pick_ch_tile(d->Ch);
   g->n_tile = 4 * g->ch_tile;
@@ -375,9 +405,7 @@ int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p) {
   fill_geom(d, *g, p);
   p->num_n_tiles = d->Ch / g->ch_tile;
   p->num_tiles = p->num_m_tiles * p->num_n_tiles;
-  p->chunks0 = cdiv(d->Cin, 64);
-  p->chunks1 = cdiv(d->Ch, 64);
-  p->num_kb = d->k * d->k * (p->chunks0 + p->chunks1);
+  set_kgeom(p, kgeom(d->Cin, d->Ch, d->k));
   return PLC_OK;
 }
 
@@ -457,11 +485,11 @@ size_t plc_packed_weight_bytes(const PlcCellDesc* d, int pack_kind) {
   const size_t kk = static_cast<size_t>(d->k) * d->k;
   if (d->mode == PLC_MODE_FP32) return kk * (d->Cin + d->Ch) * 4 * d->Ch * sizeof(float);
   if (pack_kind == PLC_PACK_FWD) {
-    const size_t ktot = kk * (cdiv(d->Cin, 64) + cdiv(d->Ch, 64)) * 64;
+    const size_t ktot = static_cast<size_t>(kgeom(d->Cin, d->Ch, d->k).num_kb) * 64;
     return static_cast<size_t>(4) * d->Ch * ktot * 2;
   }
   if (pack_kind == PLC_PACK_DGRAD) {
-    const size_t ktot = kk * cdiv(4 * d->Ch, 64) * 64;
+    const size_t ktot = static_cast<size_t>(kgeom(4 * d->Ch, 0, d->k).num_kb) * 64;
     return static_cast<size_t>(d->Cin + d->Ch) * ktot * 2;
   }
   fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
@@ -485,10 +513,10 @@ int plc_pack_weight(const PlcCellDesc* d, int pack_kind, const float* w_oihw, vo
     if (!aligned16(w_packed)) return fail(PLC_ERR_ALIGNMENT, "w_packed must be 16-byte aligned");
     if (pack_kind == PLC_PACK_FWD)
       pack_w_tc_fwd_kernel<<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), d->Cin, d->Ch,
-                                                       d->k, pick_ch_tile(d->Ch), cdiv(d->Cin, 64), cdiv(d->Ch, 64));
+                                                       d->k, pick_ch_tile(d->Ch), kgeom(d->Cin, d->Ch, d->k));
     else
       pack_w_conv_dgrad_kernel<<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed),
-                                                           d->Cin + d->Ch, 4 * d->Ch, d->k, cdiv(4 * d->Ch, 64));
+                                                           d->Cin + d->Ch, 4 * d->Ch, d->k, kgeom(4 * d->Ch, 0, d->k));
   }
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;
@@ -537,9 +565,9 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   p.h_out = static_cast<__nv_bfloat16*>(h_out);
   p.gates_out = static_cast<__nv_bfloat16*>(gates_out);
   CUtensorMap ta0, ta1, tb;
-  if ((rc = make_tmap_act(&ta1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th))) return rc;
+  if ((rc = make_tmap_act(&ta1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, p.kc, swizzle_for_kc(p.kc)))) return rc;
   if (d->Cin > 0) {
-    if ((rc = make_tmap_act(&ta0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th))) return rc;
+    if ((rc = make_tmap_act(&ta0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th, 2, p.kc, swizzle_for_kc(p.kc)))) return rc;
   } else {
     ta0 = ta1;
   }
@@ -646,9 +674,9 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   p.dc_prev = dc_prev;
   p.dz = static_cast<__nv_bfloat16*>(workspace);
   CUtensorMap ta0, ta1, tb;
-  if ((rc = make_tmap_act(&ta1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th))) return rc;
+  if ((rc = make_tmap_act(&ta1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, p.kc, swizzle_for_kc(p.kc)))) return rc;
   if (d->Cin > 0) {
-    if ((rc = make_tmap_act(&ta0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th))) return rc;
+    if ((rc = make_tmap_act(&ta0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th, 2, p.kc, swizzle_for_kc(p.kc)))) return rc;
   } else {
     ta0 = ta1;
   }
@@ -671,14 +699,13 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     const int nt = pick_plain_n_tile(n_total);
     q.num_n_tiles = cdiv(n_total, nt);
     q.num_tiles = q.num_m_tiles * q.num_n_tiles;
-    q.chunks0 = cdiv(4 * d->Ch, 64);
-    q.chunks1 = 0;
-    q.num_kb = kk * q.chunks0;
+    set_kgeom(&q, kgeom(4 * d->Ch, 0, d->k));
     q.n_total = n_total;
     q.out0 = static_cast<__nv_bfloat16*>(dx);
     q.out1 = static_cast<__nv_bfloat16*>(dh_prev);
     CUtensorMap tz, tbd;
-    if ((rc = make_tmap_act(&tz, workspace, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th))) return rc;
+    if ((rc = make_tmap_act(&tz, workspace, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th, 2, q.kc, swizzle_for_kc(q.kc))))
+      return rc;
     if ((rc = make_tmap_mat(&tbd, w_packed_dgrad, n_total, (long)q.num_kb * 64, 64, nt / cta))) return rc;
     if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tbd, tz, tz, st))) return rc;
   }
@@ -706,8 +733,9 @@ static int check_conv(const PlcConvDesc* d) {
 size_t plc_conv_packed_weight_bytes(const PlcConvDesc* d, int pack_kind) {
   if (check_conv(d) != PLC_OK) return 0;
   const size_t kk = static_cast<size_t>(d->k) * d->k;
-  if (pack_kind == PLC_PACK_FWD) return static_cast<size_t>(d->Cout) * kk * cdiv(d->Cin, 64) * 64 * 2;
-  if (pack_kind == PLC_PACK_DGRAD) return static_cast<size_t>(d->Cin) * kk * cdiv(d->Cout, 64) * 64 * 2;
+  (void)kk;
+  if (pack_kind == PLC_PACK_FWD) return static_cast<size_t>(d->Cout) * kgeom(d->Cin, 0, d->k).num_kb * 64 * 2;
+  if (pack_kind == PLC_PACK_DGRAD) return static_cast<size_t>(d->Cin) * kgeom(d->Cout, 0, d->k).num_kb * 64 * 2;
   fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
   return 0;
 }
@@ -721,10 +749,10 @@ int plc_conv_pack_weight(const PlcConvDesc* d, int pack_kind, const float* w_oih
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pack_kind == PLC_PACK_FWD)
     pack_w_conv_fwd_kernel<<<148 * 4, 256, 0, st>>>(w_oihw, bias, static_cast<__nv_bfloat16*>(w_packed), bias_packed,
-                                                    d->Cin, d->Cout, d->k, cdiv(d->Cin, 64), d->pixel_shuffle);
+                                                    d->Cin, d->Cout, d->k, kgeom(d->Cin, 0, d->k), d->pixel_shuffle);
   else if (pack_kind == PLC_PACK_DGRAD)
     pack_w_conv_dgrad_kernel<<<148 * 4, 256, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), d->Cin, d->Cout,
-                                                      d->k, cdiv(d->Cout, 64));
+                                                      d->k, kgeom(d->Cout, 0, d->k));
   else
     return fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
   PLC_CUDA(cudaGetLastError());
@@ -746,9 +774,7 @@ int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, 
   const int nt = pick_plain_n_tile(d->Cout);
   q.num_n_tiles = cdiv(d->Cout, nt);
   q.num_tiles = q.num_m_tiles * q.num_n_tiles;
-  q.chunks0 = cdiv(d->Cin, 64);
-  q.chunks1 = 0;
-  q.num_kb = d->k * d->k * q.chunks0;
+  set_kgeom(&q, kgeom(d->Cin, 0, d->k));
   q.n_total = d->Cout;
   q.Cin = d->Cout;                     // no column split: everything goes to out0
   q.out0 = static_cast<__nv_bfloat16*>(out);
@@ -757,7 +783,7 @@ int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, 
   q.plain_shuffle = d->pixel_shuffle;
   const int cta = pick_cta_group(q.num_m_tiles);
   CUtensorMap ta, tb;
-  if ((rc = make_tmap_act(&ta, x, d->B, d->H, d->W, d->Cin, g.tw, g.th))) return rc;
+  if ((rc = make_tmap_act(&ta, x, d->B, d->H, d->W, d->Cin, g.tw, g.th, 2, q.kc, swizzle_for_kc(q.kc)))) return rc;
   if ((rc = make_tmap_mat(&tb, w_packed_fwd, d->Cout, (long)q.num_kb * 64, 64, nt / cta))) return rc;
   return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, ta, ta, static_cast<cudaStream_t>(stream));
 }
@@ -792,15 +818,13 @@ int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void
     const int nt = pick_plain_n_tile(d->Cin);
     q.num_n_tiles = cdiv(d->Cin, nt);
     q.num_tiles = q.num_m_tiles * q.num_n_tiles;
-    q.chunks0 = cdiv(d->Cout, 64);
-    q.chunks1 = 0;
-    q.num_kb = d->k * d->k * q.chunks0;
+    set_kgeom(&q, kgeom(d->Cout, 0, d->k));
     q.n_total = d->Cin;
     q.Cin = d->Cin;
     q.out0 = static_cast<__nv_bfloat16*>(dx);
     const int cta = pick_cta_group(q.num_m_tiles);
     CUtensorMap tz, tb;
-    if ((rc = make_tmap_act(&tz, dz, d->B, d->H, d->W, d->Cout, g.tw, g.th))) return rc;
+    if ((rc = make_tmap_act(&tz, dz, d->B, d->H, d->W, d->Cout, g.tw, g.th, 2, q.kc, swizzle_for_kc(q.kc)))) return rc;
     if ((rc = make_tmap_mat(&tb, w_packed_dgrad, d->Cin, (long)q.num_kb * 64, 64, nt / cta))) return rc;
     if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tb, tz, tz, st))) return rc;
   }

@@ -234,6 +234,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= kLayoutSw128 << 61;
   return d;
 }
+// K-major operand whose rows are `row_bytes` (32 / 64 / 128) wide with the matching TMA swizzle mode:
+// layout code 6 = SWIZZLE_32B, 4 = SWIZZLE_64B, 2 = SWIZZLE_128B; SBO = 8 rows.
+__device__ __forceinline__ uint64_t make_smem_desc_kmajor(uint32_t smem_addr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(((8 * row_bytes) >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= layout << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 // a_major/b_major: 0 = K-major, 1 = MN-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_major, int b_major) {
