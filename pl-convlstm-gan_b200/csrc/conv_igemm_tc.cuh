@@ -116,6 +116,9 @@ __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int
   x0 = tx * p.tw;
 }
 
+template <int V>
+struct IntC { static constexpr int value = V; };
+
 // per-granule operands of the gate-gradient epilogue (8 channels of one pixel)
 struct GateIn { float4 c0, c1, d0, d1; uint4 dh, dh2; };
 
@@ -192,60 +195,72 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   // stays far below the 512 cycles the tensor core needs for it (a lane-0-only loop cost ~750 cycles/K-block).
   if (warp == 0) {
     // ===================================================================== TMA producer
-    uint32_t stage = 0, phase = 0;
-    const int kk = p.ksize * p.ksize;
-    const int G = kBlockK / p.kc;
-    const uint32_t sub_bytes = kTileM * p.kc * 2;         // one [128 px][kc ch] box
     const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b), full_base = smem_u32(full_bar);
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      int n_tile, b, y0, x0;
-      decode_tile<kCta>(p, tile, rank, n_tile, b, y0, x0);
-      const int n_row = n_tile * N_TILE + rank * (N_TILE / kCta);
-      // box iterator over (source, tap, kc-chunk); G boxes fill one 64-element K stage
-      int src = p.chunks0 > 0 ? 0 : 1, tap = 0, ck = 0, bx = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        const uint32_t a_dst = a_base + stage * kABytes, b_dst = b_base + stage * Cfg::kBBytes;
-        uint32_t bar;
-        if constexpr (kCta == 1) {
-          bar = full_base + stage * 8;
-          if (elect_one()) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-        } else {
-          // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there)
-          bar = mapa_u32(full_base + stage * 8, 0);
-          if (rank == 0 && elect_one()) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-        }
-        __syncwarp();
-        for (int g = 0; g < G; ++g) {
-          const int dy = tap / p.ksize - p.pad;
-          const int dx = tap - (tap / p.ksize) * p.ksize - p.pad;
-          if (elect_one()) {
-            const CUtensorMap* tm = src ? &tmap_a1 : &tmap_a0;
-            if constexpr (kCta == 1) tma_load_4d_s(a_dst + g * sub_bytes, tm, bar, ck * p.kc, x0 + dx, y0 + dy, b);
-            else tma_load_4d_cg2(a_dst + g * sub_bytes, tm, bar, ck * p.kc, x0 + dx, y0 + dy, b);
-          }
-          if (bx + 1 < p.num_boxes) {       // advance; the K tail re-loads the last box (its weights are zero)
-            ++bx;
-            if (++ck == (src ? p.chunks1 : p.chunks0)) {
-              ck = 0;
-              if (++tap == kk) { tap = 0; src = 1; }
+    // One specialised copy of the loop per G = 64/kc (boxes per 64-element K stage): the producer sits on the critical
+    // path once the kernel is feed-bound, so its per-stage instruction count must stay small (G = 1 is the plain
+    // "one box + one weight tile per stage" loop).
+    auto produce = [&](auto g_const) {
+      constexpr int G = decltype(g_const)::value;
+      constexpr int KC = kBlockK / G;
+      constexpr uint32_t sub_bytes = kTileM * KC * 2;     // one [128 px][kc ch] box
+      uint32_t stage = 0, phase = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        int n_tile, b, y0, x0;
+        decode_tile<kCta>(p, tile, rank, n_tile, b, y0, x0);
+        const int n_row = n_tile * N_TILE + rank * (N_TILE / kCta);
+        // box iterator over (source, tap = (ky, kx), kc-chunk); the K tail re-loads the last box (zero weights)
+        int src = p.chunks0 > 0 ? 0 : 1, ky = 0, kx = 0, ck = 0, bx = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          int cch[G], cdx[G], cdy[G], csrc[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            cch[g] = ck * KC; cdx[g] = x0 + kx - p.pad; cdy[g] = y0 + ky - p.pad; csrc[g] = src;
+            if (bx + 1 < p.num_boxes) {
+              ++bx;
+              if (++ck == (src ? p.chunks1 : p.chunks0)) {
+                ck = 0;
+                if (++kx == p.ksize) {
+                  kx = 0;
+                  if (++ky == p.ksize) { ky = 0; src = 1; }
+                }
+              }
             }
           }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            const uint32_t a_dst = a_base + stage * kABytes, b_dst = b_base + stage * Cfg::kBBytes;
+            if constexpr (kCta == 1) {
+              const uint32_t bar = full_base + stage * 8;
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+                tma_load_4d_s(a_dst + g * sub_bytes, csrc[g] ? &tmap_a1 : &tmap_a0, bar, cch[g], cdx[g], cdy[g], b);
+              tma_load_2d_s(b_dst, &tmap_b, bar, kb * kBlockK, n_row);
+            } else {
+              // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there)
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              const uint32_t bar = mapa_u32(full_base + stage * 8, 0);
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+                tma_load_4d_cg2(a_dst + g * sub_bytes, csrc[g] ? &tmap_a1 : &tmap_a0, bar, cch[g], cdx[g], cdy[g], b);
+              tma_load_2d_cg2(b_dst, &tmap_b, bar, kb * kBlockK, n_row);
+            }
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) {
-          if constexpr (kCta == 1) tma_load_2d_s(b_dst, &tmap_b, bar, kb * kBlockK, n_row);
-          else tma_load_2d_cg2(b_dst, &tmap_b, bar, kb * kBlockK, n_row);
-        }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-    }
+    };
+    if (p.kc == 64) produce(IntC<1>{});
+    else if (p.kc == 32) produce(IntC<2>{});
+    else produce(IntC<4>{});
   } else if (warp == 1 && rank == 0) {
     // ===================================================================== MMA issuer (leader CTA only)
     constexpr uint32_t idesc = make_idesc_bf16(kTileM * kCta, N_TILE, 0, 0);
     const uint64_t adesc0 = make_smem_desc_kmajor(smem_u32(smem_a), p.kc * 2);   // rows of kc bf16, matching swizzle
     const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b), 0, 1024);
     // A offset (16-byte units) of the k-th UMMA_K=16 slice of a stage: box (16k / kc), then 32 bytes per slice inside it
+    const bool wide = p.kc == 64;
     uint32_t aoff[kBlockK / 16];
 #pragma unroll
     for (int k = 0; k < kBlockK / 16; ++k)
@@ -273,7 +288,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 bytes per UMMA_K=16 inside the 128-byte swizzle atom
-            umma_bf16<kCta>(d_tmem, adesc + aoff[k], bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16<kCta>(d_tmem, adesc + (wide ? 2u * k : aoff[k]), bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if constexpr (kCta == 1) {
