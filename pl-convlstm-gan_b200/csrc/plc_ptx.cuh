@@ -81,6 +81,11 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
       "r"(c2), "r"(c3)
       : "memory");
 }
+// warm L2 with a box that a later TMA load will fetch (no smem, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // same, with shared-space u32 addresses already computed
 __device__ __forceinline__ void tma_load_2d_s(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
