@@ -434,11 +434,15 @@ int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev
   p.PB = d->B * g.tiles_x * g.tiles_y;
   p.chunks0 = cdiv(d->Cin, 64); p.chunks1 = cdiv(d->Ch, 64);
   p.CB = d->k * d->k * (p.chunks0 + p.chunks1);
+  // CTA pairs (cta_group::2, 256-row output tiles) once dZ has >= 256 channels and there is enough work
+  const bool pair = d->N >= 256 && pick_cta_group(p.PB / 2) == 2;
   p.num_groups = cdiv(p.CB, plc::kWgMaxGB);
   p.GB = cdiv(p.CB, p.num_groups);
-  p.n_tiles = cdiv(d->N, 128);
+  if (pair) p.GB = 2 * cdiv(p.GB, 2);                      // even: the pair splits the columns in halves
+  p.num_groups = cdiv(p.CB, p.GB);
+  p.n_tiles = cdiv(d->N, pair ? 256 : 128);
   const int tiles = p.n_tiles * p.num_groups;
-  int S = sm_count() / tiles;
+  int S = (sm_count() / (pair ? 2 : 1)) / tiles;
   if (S < 1) S = 1;
   if (S > p.PB) S = p.PB;
   p.S = S;
@@ -456,9 +460,25 @@ int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev
     t0 = t1;
   }
   if (d->Ch == 0) t1 = t0;
-  PLC_CUDA(cudaFuncSetAttribute(plc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plc::kWgSmemBytes));
-  plc::wgrad_tc_kernel<<<tiles * S, 256, plc::kWgSmemBytes, st>>>(p, tz, t0, t1);
-  PLC_CUDA(cudaGetLastError());
+  if (pair) {
+    PLC_CUDA(cudaFuncSetAttribute(plc::wgrad_tc_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, plc::kW2SmemBytes));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * tiles * S);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = plc::kW2SmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PLC_CUDA(cudaLaunchKernelEx(&cfg, plc::wgrad_tc_kernel2, p, tz, t0, t1));
+  } else {
+    PLC_CUDA(cudaFuncSetAttribute(plc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plc::kWgSmemBytes));
+    plc::wgrad_tc_kernel<<<tiles * S, 256, plc::kWgSmemBytes, st>>>(p, tz, t0, t1);
+    PLC_CUDA(cudaGetLastError());
+  }
   return PLC_OK;
 }
 

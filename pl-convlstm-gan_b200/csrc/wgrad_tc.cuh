@@ -216,4 +216,185 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
   }
 }
 
+// --------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for N4 >= 256: one pair owns a [256 gate-channels x 64*GB columns] output tile.
+// Each CTA stages its own 128 rows of dZ^T (2 boxes) and HALF of the source columns (GB/2 boxes) per 64-pixel stage:
+// 40 KB per 768 MMA cycles (53 B/clk/SM) instead of 64 KB (85 B/clk) -> the reduction is tensor-bound, not feed-bound,
+// and 5 stages fit instead of 3.
+constexpr int kW2Half = 3;                                      // source boxes per CTA per stage (GB = 2, 4 or 6)
+constexpr int kW2StageBytes = (2 + kW2Half) * kWgBoxBytes;      // 40 KB
+constexpr int kW2Stages = 5;
+constexpr int kW2SmemBytes = kW2Stages * kW2StageBytes + kWgOnesBytes + 256 + 1024;
+
+__global__ void __launch_bounds__(256, 1)
+wgrad_tc_kernel2(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_dz,
+                 const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ones_s = smem + kW2Stages * kW2StageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones_s + kWgOnesBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kW2Stages;
+  uint64_t* acc_bar = bars + 2 * kW2Stages;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kW2Stages + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  int job = blockIdx.x >> 1;                    // pair index
+  const int s = job % p.S; job /= p.S;
+  const int group = job % p.num_groups;
+  const int n_tile = job / p.num_groups;        // 256-row tile of n
+  const int cb0 = group * p.GB;
+  const int nblk = min(p.GB, p.CB - cb0);       // valid column blocks of this pair (the rest are dummies)
+  const int kk = p.ksize * p.ksize;
+  const int na_half = (p.GB < 4 ? p.GB : 4) >> 1;   // blocks per CTA in MMA a (N_a = 128 * na_half)
+  const bool has_b = p.GB > 4;                      // MMA b: N = 128, one block per CTA
+  const int nslots = na_half + (has_b ? 1 : 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_dz);
+    tma_prefetch_desc(&tmap_a0);
+    tma_prefetch_desc(&tmap_a1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kW2Stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<2>(tmem_ptr_s, kWgTmemCols);
+  const bool do_db = (p.db != nullptr) && (group == 0);
+  if (do_db) {
+    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_s)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const int my_blocks = (p.PB - s + p.S - 1) / p.S;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    int dxs[kW2Half], dys[kW2Half], cks[kW2Half];
+    bool s1[kW2Half];
+#pragma unroll
+    for (int t = 0; t < kW2Half; ++t) {
+      // slot t of this CTA -> column block j of the group
+      int j = t < na_half ? rank * na_half + t : 4 + rank;
+      if (j >= nblk) j = 0;                     // dummy column block: load something valid, the epilogue skips it
+      int cb = cb0 + j, tap, ck;
+      bool is1 = false;
+      if (cb < kk * p.chunks0) { tap = cb / p.chunks0; ck = cb % p.chunks0; }
+      else { cb -= kk * p.chunks0; is1 = true; tap = cb / p.chunks1; ck = cb % p.chunks1; }
+      dys[t] = tap / p.ksize - p.pad; dxs[t] = tap % p.ksize - p.pad; cks[t] = ck * 64; s1[t] = is1;
+    }
+    uint32_t stage = 0, phase = 0;
+    const uint32_t bytes = 2u * (2 + nslots) * kWgBoxBytes;   // both CTAs' bytes land on the leader's barrier
+    int tx = s % p.tiles_x, r0 = s / p.tiles_x;
+    int ty = r0 % p.tiles_y, b = r0 / p.tiles_y;
+    const int step_x = p.S % p.tiles_x, step_r = p.S / p.tiles_x;
+    const int step_y = step_r % p.tiles_y, step_b = step_r / p.tiles_y;
+    const int n0 = n_tile * 256 + rank * 128;
+    for (int i = 0; i < my_blocks; ++i) {
+      const int x0 = tx * p.tw, y0 = ty * p.th;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], bytes);
+        const uint32_t st = smem_u32(smem) + stage * kW2StageBytes;
+        const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+        tma_load_4d_cg2(st, &tmap_dz, bar, n0, x0, y0, b);
+        tma_load_4d_cg2(st + kWgBoxBytes, &tmap_dz, bar, n0 + 64, x0, y0, b);
+#pragma unroll
+        for (int t = 0; t < kW2Half; ++t) {
+          if (t < nslots)
+            tma_load_4d_cg2(st + (2 + t) * kWgBoxBytes, s1[t] ? &tmap_a1 : &tmap_a0, bar, cks[t], x0 + dxs[t],
+                            y0 + dys[t], b);
+        }
+      }
+      __syncwarp();
+      if (++stage == kW2Stages) { stage = 0; phase ^= 1; }
+      tx += step_x; ty += step_y; b += step_b;
+      if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+      if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===================================================================== MMA issuer (leader CTA)
+    const uint32_t idesc_a = make_idesc_bf16(256, 128 * na_half, 1, 1);
+    const uint32_t idesc_b = make_idesc_bf16(256, 128, 1, 1);
+    const uint32_t idesc_o = make_idesc_bf16(256, 16, 1, 1);
+    uint32_t stage = 0, phase = 0;
+    for (int i = 0; i < my_blocks; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem) + stage * kW2StageBytes;
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < kWgPix / 16; ++ks) {
+          const uint64_t adesc = make_smem_desc_mn(st + ks * 2048, kWgBoxBytes);
+          const uint64_t bdesc0 = make_smem_desc_mn(st + 2 * kWgBoxBytes + ks * 2048, kWgBoxBytes);
+          umma_bf16<2>(tmem_base, adesc, bdesc0, idesc_a, (i | ks) != 0);
+          if (has_b) {
+            const uint64_t bdesc1 = make_smem_desc_mn(st + (2 + na_half) * kWgBoxBytes + ks * 2048, kWgBoxBytes);
+            umma_bf16<2>(tmem_base + 256, adesc, bdesc1, idesc_b, (i | ks) != 0);
+          }
+          if (do_db) {
+            const uint64_t odesc = make_smem_desc_mn(smem_u32(ones_s) + ks * 2048, kWgBoxBytes);
+            umma_bf16<2>(tmem_base + kWgDbCol, adesc, odesc, idesc_o, (i | ks) != 0);
+          }
+        }
+        umma_commit_mc2(&empty_bar[stage], 0b11);
+        if (i == my_blocks - 1) umma_commit_mc2(acc_bar, 0b11);
+      }
+      __syncwarp();
+      if (++stage == kW2Stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp >= 4 && my_blocks > 0) {
+    // ===================================================================== epilogue (both CTAs, own 128 rows)
+    const int q = warp - 4;
+    const int n = n_tile * 256 + rank * 128 + q * 32 + lane;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if (do_db) {
+      uint32_t v[16];
+      tmem_ld16(t_row + kWgDbCol, v);
+      tmem_ld_wait();
+      if (n < p.N4) atomicAdd(p.db + n, __uint_as_float(v[0]));
+    }
+    for (int j = 0; j < nblk; ++j) {
+      int cb = cb0 + j;
+      int src, tap, ck;
+      if (cb < kk * p.chunks0) { src = 0; tap = cb / p.chunks0; ck = cb % p.chunks0; }
+      else { cb -= kk * p.chunks0; src = 1; tap = cb / p.chunks1; ck = cb % p.chunks1; }
+      const int csrc = src ? p.C1 : p.C0;
+      const int col = (j < 4) ? j * 64 : 256 + (j - 4) * 64;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[16];
+        tmem_ld16(t_row + col + cc * 16, v);
+        tmem_ld_wait();
+        if (n < p.N4) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int c = ck * 64 + cc * 16 + e;
+            if (c < csrc) {
+              const int ic = src ? p.C0 + c : c;
+              atomicAdd(p.dW + (static_cast<size_t>(n) * p.Ctot + ic) * kk + tap, __uint_as_float(v[e]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, kWgTmemCols);
+  }
+}
+
 }  // namespace plc
