@@ -98,10 +98,15 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
  *   dc_next [B,H,W,Ch]  gradient w.r.t. c_out, fp32 (NULL = zeros)
  *   dx      [B,H,W,Cin] out (NULL = not needed), dtype of x
  *   dh_prev [B,H,W,Ch]  out, dtype of h;   dc_prev [B,H,W,Ch] out fp32 (may alias dc_next)
- *   dW_acc  [4Ch, Cin+Ch, k, k] fp32, reference layout, ACCUMULATED into (+=) across steps
+ *   dW_acc  the library's fp32 weight-gradient ACCUMULATOR IMAGE (plc_wgrad_acc_bytes(d) bytes, zeroed by the caller
+ *           before the first step, accumulated into across all T steps).  bf16 mode: packed [4Ch][column blocks*64]
+ *           so the kernel can use 16-byte vector reductions; fp32 mode: the OIHW layout itself.  Convert once per
+ *           backward pass with plc_wgrad_unpack, which ADDS it into `conv.weight.grad` [4Ch, Cin+Ch, k, k].
  *   db_acc  [4Ch] fp32, accumulated (NULL iff !has_bias)
  *   workspace: plc_bwd_workspace_bytes(d) bytes of scratch (holds dZ).                          */
 size_t plc_bwd_workspace_bytes(const PlcCellDesc* d);
+size_t plc_wgrad_acc_bytes(const PlcCellDesc* d);
+int plc_wgrad_unpack(const PlcCellDesc* d, const float* dW_acc, float* dW_oihw, void* stream);
 int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
                  const void* w_packed_fwd, const void* w_packed_dgrad, const float* bias, const void* dh,
                  const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc, float* db_acc,
@@ -116,7 +121,8 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
  * plc_conv_pack_weight: w_oihw [Cout,Cin,k,k] fp32 -> packed image (PLC_PACK_FWD also writes bias_packed [Cout] in
  *   packed column order; PLC_PACK_DGRAD the flipped/transposed image).
  * Backward: plc_conv_grad_mask forms dZ [B,H,W,Cout] (natural channel order) = dY * (Y > 0) undoing the shuffle;
- *   plc_conv_bwd: dx [B,H,W,Cin] (nullable), dW_acc [Cout,Cin,k,k] fp32 +=, db_acc [Cout] fp32 += (nullable).   */
+ *   plc_conv_bwd: dx [B,H,W,Cin] (nullable), dW_acc = accumulator image (plc_conv_wgrad_acc_bytes; convert with
+ *   plc_conv_wgrad_unpack, which adds into [Cout,Cin,k,k]), db_acc [Cout] fp32 += (nullable).                   */
 typedef struct PlcConvDesc {
   int32_t B, H, W, Cin, Cout, k;
   int32_t relu;           /* apply ReLU to the output                              */
@@ -129,6 +135,8 @@ int plc_conv_pack_weight(const PlcConvDesc* d, int pack_kind, const float* w_oih
 int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, void* out,
                  void* stream);
 int plc_conv_grad_mask(const PlcConvDesc* d, const void* y, const void* dy, void* dz, void* stream);
+size_t plc_conv_wgrad_acc_bytes(const PlcConvDesc* d);
+int plc_conv_wgrad_unpack(const PlcConvDesc* d, const float* dW_acc, float* dW_oihw, void* stream);
 int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void* w_packed_dgrad, void* dx,
                  float* dW_acc, float* db_acc, void* stream);
 

@@ -39,6 +39,10 @@ SIGNATURES = {
     "plc_pack_weight": (_int, [_dp, _int, _vp, _vp, _vp]),
     "plc_cell_fwd": (_int, [_dp] + [_vp] * 9),
     "plc_bwd_workspace_bytes": (_sz, [_dp]),
+    "plc_wgrad_acc_bytes": (_sz, [_dp]),
+    "plc_wgrad_unpack": (_int, [_dp, _vp, _vp, _vp]),
+    "plc_conv_wgrad_acc_bytes": (_sz, [_cp]),
+    "plc_conv_wgrad_unpack": (_int, [_cp, _vp, _vp, _vp]),
     "plc_cell_bwd": (_int, [_dp] + [_vp] * 15 + [_sz, _vp]),
     "plc_conv_packed_weight_bytes": (_sz, [_cp, _int]),
     "plc_conv_pack_weight": (_int, [_cp, _int, _vp, _vp, _vp, _vp, _vp]),

@@ -737,6 +737,32 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   return PLC_OK;
 }
 
+// ---------------------------------------------------------------------------------- weight-gradient accumulator
+static size_t wgrad_acc_elems(int mode, int Cin, int Ch, int N, int k) {
+  const size_t kk = static_cast<size_t>(k) * k;
+  if (mode == PLC_MODE_FP32) return static_cast<size_t>(N) * (Cin + Ch) * kk;              // OIHW itself
+  return static_cast<size_t>(N) * kk * (cdiv(Cin, 64) + cdiv(Ch, 64)) * 64;                 // packed [N][CB*64]
+}
+static int wgrad_unpack(int mode, int Cin, int Ch, int N, int k, const float* acc, float* dW, cudaStream_t st) {
+  if (!acc || !dW) return fail(PLC_ERR_NULL_ARG, "wgrad unpack: null pointer");
+  if (mode == PLC_MODE_FP32)
+    plc::add_inplace_kernel<<<148 * 4, 256, 0, st>>>(acc, dW, wgrad_acc_elems(mode, Cin, Ch, N, k));
+  else
+    plc::wgrad_unpack_kernel<<<148 * 4, 256, 0, st>>>(acc, dW, N, Cin, Ch, k);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+size_t plc_wgrad_acc_bytes(const PlcCellDesc* d) {
+  if (check_desc(d) != PLC_OK) return 0;
+  return wgrad_acc_elems(d->mode, d->Cin, d->Ch, 4 * d->Ch, d->k) * sizeof(float);
+}
+int plc_wgrad_unpack(const PlcCellDesc* d, const float* acc, float* dW_oihw, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  return wgrad_unpack(d->mode, d->Cin, d->Ch, 4 * d->Ch, d->k, acc, dW_oihw, static_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------------------------- generic "same" conv (bf16)
 static int check_conv(const PlcConvDesc* d) {
   if (!d) return fail(PLC_ERR_BAD_DESC, "null conv descriptor");
@@ -806,6 +832,16 @@ int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, 
   if ((rc = make_tmap_act(&ta, x, d->B, d->H, d->W, d->Cin, g.tw, g.th, 2, q.kc, swizzle_for_kc(q.kc)))) return rc;
   if ((rc = make_tmap_mat(&tb, w_packed_fwd, d->Cout, (long)q.num_kb * 64, 64, nt / cta))) return rc;
   return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, ta, ta, static_cast<cudaStream_t>(stream));
+}
+
+size_t plc_conv_wgrad_acc_bytes(const PlcConvDesc* d) {
+  if (check_conv(d) != PLC_OK) return 0;
+  return wgrad_acc_elems(PLC_MODE_BF16_TC, d->Cin, 0, d->Cout, d->k) * sizeof(float);
+}
+int plc_conv_wgrad_unpack(const PlcConvDesc* d, const float* acc, float* dW_oihw, void* stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  return wgrad_unpack(PLC_MODE_BF16_TC, d->Cin, 0, d->Cout, d->k, acc, dW_oihw, static_cast<cudaStream_t>(stream));
 }
 
 int plc_conv_grad_mask(const PlcConvDesc* d, const void* y, const void* dy, void* dz, void* stream) {

@@ -24,7 +24,7 @@ struct WgradTcParams {
   int CB, GB, num_groups;     // column blocks (src,tap,chunk); blocks per CTA; groups
   int n_tiles, S;             // 128-row tiles of n = 4Ch; pixel splits
   int C0, C1, N4, Ctot;       // true channel counts
-  float* dW;                  // [N4][Ctot][k][k]
+  float* dW;                  // packed fp32 accumulator [N4][CB*64]: column = column-block*64 + channel-in-chunk
   float* db;                  // [N4] or nullptr: bias gradient = dZ^T x ones, one extra N=16 MMA per K-step
 };
 
@@ -37,6 +37,34 @@ constexpr int kWgOnesBytes = kWgBoxBytes;            // [64 px][64 ch] of bf16 1
 constexpr int kWgDbCol = 384;                        // TMEM column of the db accumulator (16 columns)
 constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + kWgOnesBytes + 256 + 1024;
 constexpr int kWgTmemCols = 512;
+
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// packed accumulator -> reference OIHW gradient:  dW[n][ic][tap] += acc[n][(column block of (src, tap, ic/64))*64 + ic%64]
+__global__ void wgrad_unpack_kernel(const float* __restrict__ acc, float* __restrict__ dW, int N4, int C0, int C1,
+                                    int ksize) {
+  const int kk = ksize * ksize, ctot = C0 + C1;
+  const int chunks0 = (C0 + 63) / 64, chunks1 = (C1 + 63) / 64;
+  const int Kp = kk * (chunks0 + chunks1) * 64;
+  const size_t total = static_cast<size_t>(N4) * ctot * kk;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int tap = idx % kk;
+    const int ic = (idx / kk) % ctot;
+    const int n = idx / (static_cast<size_t>(kk) * ctot);
+    int cb, c;
+    if (ic < C0) { c = ic; cb = tap * chunks0 + c / 64; }
+    else { c = ic - C0; cb = kk * chunks0 + tap * chunks1 + c / 64; }
+    dW[idx] += acc[static_cast<size_t>(n) * Kp + cb * 64 + (c & 63)];
+  }
+}
+__global__ void add_inplace_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] += src[i];
+}
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
   // MN-major SWIZZLE_128B canonical layout ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units:
@@ -184,26 +212,18 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
       if (n < p.N4) atomicAdd(p.db + n, __uint_as_float(v[0]));
     }
     for (int j = 0; j < nblk; ++j) {
-      int cb = cb0 + j;
-      int src, tap, ck;
-      if (cb < kk * p.chunks0) { src = 0; tap = cb / p.chunks0; ck = cb % p.chunks0; }
-      else { cb -= kk * p.chunks0; src = 1; tap = cb / p.chunks1; ck = cb % p.chunks1; }
-      const int csrc = src ? p.C1 : p.C0;
       const int col = (j < 4) ? j * 64 : 256 + (j - 4) * 64;
+      float* dst = p.dW + static_cast<size_t>(n) * (p.CB * 64) + static_cast<size_t>(cb0 + j) * 64;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t v[16];
         tmem_ld16(t_row + col + cc * 16, v);
         tmem_ld_wait();
-        if (n < p.N4) {
+        if (n < p.N4) {   // 16 consecutive fp32 of the packed accumulator: four 16-byte vector reductions
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int c = ck * 64 + cc * 16 + e;
-            if (c < csrc) {
-              const int ic = src ? p.C0 + c : c;
-              atomicAdd(p.dW + (static_cast<size_t>(n) * p.Ctot + ic) * kk + tap, __uint_as_float(v[e]));
-            }
-          }
+          for (int e = 0; e < 16; e += 4)
+            red_add_v4(dst + cc * 16 + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                       __uint_as_float(v[e + 3]));
         }
       }
     }
@@ -365,26 +385,18 @@ wgrad_tc_kernel2(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap
       if (n < p.N4) atomicAdd(p.db + n, __uint_as_float(v[0]));
     }
     for (int j = 0; j < nblk; ++j) {
-      int cb = cb0 + j;
-      int src, tap, ck;
-      if (cb < kk * p.chunks0) { src = 0; tap = cb / p.chunks0; ck = cb % p.chunks0; }
-      else { cb -= kk * p.chunks0; src = 1; tap = cb / p.chunks1; ck = cb % p.chunks1; }
-      const int csrc = src ? p.C1 : p.C0;
       const int col = (j < 4) ? j * 64 : 256 + (j - 4) * 64;
+      float* dst = p.dW + static_cast<size_t>(n) * (p.CB * 64) + static_cast<size_t>(cb0 + j) * 64;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t v[16];
         tmem_ld16(t_row + col + cc * 16, v);
         tmem_ld_wait();
-        if (n < p.N4) {
+        if (n < p.N4) {   // 16 consecutive fp32 of the packed accumulator: four 16-byte vector reductions
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int c = ck * 64 + cc * 16 + e;
-            if (c < csrc) {
-              const int ic = src ? p.C0 + c : c;
-              atomicAdd(p.dW + (static_cast<size_t>(n) * p.Ctot + ic) * kk + tap, __uint_as_float(v[e]));
-            }
-          }
+          for (int e = 0; e < 16; e += 4)
+            red_add_v4(dst + cc * 16 + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                       __uint_as_float(v[e + 3]));
         }
       }
     }

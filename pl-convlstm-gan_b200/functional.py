@@ -116,14 +116,29 @@ def bwd_workspace(B: int, H: int, W: int, pw: PackedWeights, device) -> Tensor:
     return torch.empty(lib.plc_bwd_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8, device=device)
 
 
-def cell_backward(x: Optional[Tensor], h_prev: Tensor, c_prev: Tensor, pw: PackedWeights, dh: Tensor,
-                  dh2: Optional[Tensor], dc_next: Optional[Tensor], dW_acc: Optional[Tensor],
-                  db_acc: Optional[Tensor], need_dx: bool = True, workspace: Optional[Tensor] = None,
-                  dx: Optional[Tensor] = None, dh_prev: Optional[Tensor] = None,
-                  dc_prev: Optional[Tensor] = None):
-    """BPTT of one cell step: returns (dx, dh_prev, dc_prev); dW_acc/db_acc are += in place.
+def wgrad_accumulator(B: int, H: int, W: int, pw: PackedWeights, device) -> Tensor:
+    """Zeroed fp32 accumulator image for dW (layout private to the library; see plc_wgrad_acc_bytes)."""
+    lib = _lib.load()
+    d = make_desc(B, H, W, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)
+    return torch.zeros(lib.plc_wgrad_acc_bytes(ctypes.byref(d)) // 4, dtype=torch.float32, device=device)
 
-    dW_acc is fp32 in the reference layout [4Ch, Cin+Ch, k, k] (Cin = pw.Cin, i.e. the padded count)."""
+
+def wgrad_unpack(acc: Tensor, pw: PackedWeights, dW: Tensor) -> Tensor:
+    """dW [4Ch, Cin+Ch, k, k] fp32 (reference layout, Cin = pw.Cin) += unpack(acc)."""
+    lib = _lib.load()
+    d = make_desc(1, 1, 1, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)
+    _lib.check(lib.plc_wgrad_unpack(ctypes.byref(d), _ptr(acc), _ptr(dW), _stream()), "plc_wgrad_unpack")
+    return dW
+
+
+def cell_backward_acc(x: Optional[Tensor], h_prev: Tensor, c_prev: Tensor, pw: PackedWeights, dh: Tensor,
+                      dh2: Optional[Tensor], dc_next: Optional[Tensor], dW_img: Optional[Tensor],
+                      db_acc: Optional[Tensor], need_dx: bool = True, workspace: Optional[Tensor] = None,
+                      dx: Optional[Tensor] = None, dh_prev: Optional[Tensor] = None,
+                      dc_prev: Optional[Tensor] = None):
+    """BPTT of one cell step: returns (dx, dh_prev, dc_prev).  `dW_img` is the accumulator image from
+    :func:`wgrad_accumulator` (accumulated in place across steps; convert once with :func:`wgrad_unpack`);
+    `db_acc` [4Ch] fp32 is accumulated in place."""
     lib = _lib.load()
     B, H, W, Ch = h_prev.shape
     if pw.dgrad is None:
@@ -139,10 +154,23 @@ def cell_backward(x: Optional[Tensor], h_prev: Tensor, c_prev: Tensor, pw: Packe
     d = make_desc(B, H, W, pw.Cin, Ch, pw.k, pw.mode, pw.bias is not None)
     _lib.check(lib.plc_cell_bwd(ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h_prev), _ptr(c_prev),
                                 _ptr(pw.fwd), _ptr(pw.dgrad), _ptr(pw.bias), _ptr(dh), _ptr(dh2), _ptr(dc_next),
-                                _ptr(dx), _ptr(dh_prev), _ptr(dc_prev), _ptr(dW_acc), _ptr(db_acc),
+                                _ptr(dx), _ptr(dh_prev), _ptr(dc_prev), _ptr(dW_img), _ptr(db_acc),
                                 _ptr(workspace), workspace.numel(), _stream()),
                "plc_cell_bwd")
     return dx, dh_prev, dc_prev
+
+
+def cell_backward(x: Optional[Tensor], h_prev: Tensor, c_prev: Tensor, pw: PackedWeights, dh: Tensor,
+                  dh2: Optional[Tensor], dc_next: Optional[Tensor], dW_acc: Optional[Tensor],
+                  db_acc: Optional[Tensor], **kw):
+    """Single-step convenience form: `dW_acc` is fp32 in the REFERENCE layout [4Ch, Cin+Ch, k, k] (Cin = pw.Cin, i.e.
+    the padded count) and is += in place (accumulator image + unpack handled here)."""
+    B, H, W, _ = h_prev.shape
+    img = wgrad_accumulator(B, H, W, pw, h_prev.device) if dW_acc is not None else None
+    out = cell_backward_acc(x, h_prev, c_prev, pw, dh, dh2, dc_next, img, db_acc, **kw)
+    if dW_acc is not None:
+        wgrad_unpack(img, pw, dW_acc)
+    return out
 
 
 def nchw_to_nhwc(src: Tensor, mode: int, c_pad: Optional[int] = None) -> Tensor:
@@ -339,9 +367,11 @@ class _ConvFn(torch.autograd.Function):
             dz = dy
         dx = torch.empty_like(x) if ctx.x_needs_grad else None
         dW = torch.zeros(cp.cout_p, cp.cin_p, cp.k, cp.k, dtype=torch.float32, device=x.device)
+        img = torch.zeros(lib.plc_conv_wgrad_acc_bytes(ctypes.byref(d)) // 4, dtype=torch.float32, device=x.device)
         db = torch.zeros(cp.cout_p, dtype=torch.float32, device=x.device) if cp.conv.bias is not None else None
-        _lib.check(lib.plc_conv_bwd(ctypes.byref(d), _ptr(x), _ptr(dz), _ptr(dg), _ptr(dx), _ptr(dW), _ptr(db),
+        _lib.check(lib.plc_conv_bwd(ctypes.byref(d), _ptr(x), _ptr(dz), _ptr(dg), _ptr(dx), _ptr(img), _ptr(db),
                                     _stream()), "plc_conv_bwd")
+        _lib.check(lib.plc_conv_wgrad_unpack(ctypes.byref(d), _ptr(img), _ptr(dW), _stream()), "plc_conv_wgrad_unpack")
         gw = dW[:cp.Cout, :cp.Cin].to(cp.conv.weight.dtype)
         gb = None if db is None else db[:cp.Cout].to(cp.conv.bias.dtype)
         return dx, gw, gb, None

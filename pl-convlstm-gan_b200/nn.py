@@ -195,7 +195,7 @@ class _StackRolloutFn(torch.autograd.Function):
         pws = [pw if pw.dgrad is not None else c._packed(need_dgrad=True) for pw, c in zip(ctx.pws, cells)]
         B, H, W, _ = hs[0][0].shape
         dev = hs[0].device
-        dW = [torch.zeros(4 * c.hidden_dim, pw.Cin + c.hidden_dim, pw.k, pw.k, device=dev) for c, pw in zip(cells, pws)]
+        dW_img = [F.wgrad_accumulator(B, H, W, pw, dev) for pw in pws]     # accumulated over all T steps
         db = [torch.zeros(4 * c.hidden_dim, device=dev) if pw.bias is not None else None for c, pw in zip(cells, pws)]
         ws = [F.bwd_workspace(B, H, W, pw, dev) for pw in pws]
         # recurrent carries: dh ping-pong (read as dh2 while the next dh_prev is written), dc in place
@@ -233,8 +233,8 @@ class _StackRolloutFn(torch.autograd.Function):
                 if need_dx:
                     out_dx = dxs[t] if (l == 0) else dx_buf[l]
                 dst = dh_buf[l][flip[l]]
-                F.cell_backward(x_in, hs[l][t], cs[l][t], pws[l], dh, dh2, dc_carry[l], dW[l], db[l], need_dx=need_dx,
-                                workspace=ws[l], dx=out_dx, dh_prev=dst, dc_prev=dc_buf[l])
+                F.cell_backward_acc(x_in, hs[l][t], cs[l][t], pws[l], dh, dh2, dc_carry[l], dW_img[l], db[l],
+                                    need_dx=need_dx, workspace=ws[l], dx=out_dx, dh_prev=dst, dc_prev=dc_buf[l])
                 dh_carry[l], dc_carry[l] = dst, dc_buf[l]
                 flip[l] ^= 1
                 d_above = out_dx if l > 0 else None
@@ -243,7 +243,8 @@ class _StackRolloutFn(torch.autograd.Function):
             grads.append(dh_carry[l] if ctx.state_needs_grad[2 * l] else None)
             grads.append(dc_carry[l] if ctx.state_needs_grad[2 * l + 1] else None)
         for l, cell in enumerate(cells):
-            g = dW[l]
+            g = torch.zeros(4 * cell.hidden_dim, pws[l].Cin + cell.hidden_dim, pws[l].k, pws[l].k, device=dev)
+            F.wgrad_unpack(dW_img[l], pws[l], g)             # one layout conversion per backward pass
             if pws[l].Cin != cell.input_dim:                 # drop zero-padded x channels
                 g = torch.cat([g[:, :cell.input_dim], g[:, pws[l].Cin:]], dim=1)
             grads.append(g.to(cell.conv.weight.dtype))

@@ -50,8 +50,9 @@ def main():  # noqa: C901
         dW = torch.zeros(4 * ch, cin + ch, k, k, device=dev)
         db = torch.zeros(4 * ch, device=dev)
         ws = F.bwd_workspace(B, H, W, pw, dev)
+        img = F.wgrad_accumulator(B, H, W, pw, dev)
         dx, dhp, dcp = (torch.empty_like(x) if cin else None), torch.empty_like(h), torch.empty_like(c)
-        med, mn = time_fn(lambda: F.cell_backward(x, h, c, pw, dh, None, dc, dW, db, workspace=ws, dx=dx,
+        med, mn = time_fn(lambda: F.cell_backward_acc(x, h, c, pw, dh, None, dc, img, db, workspace=ws, dx=dx,
                                                   dh_prev=dhp, dc_prev=dcp), iters=10, warm=2)
         print(f"bwd  median {med:.1f} us  min {mn:.1f} us  {2 * flops / med / 1e6:.1f} TFLOP/s (2F algorithmic)")
 

@@ -45,8 +45,9 @@ def main():
                 dW = torch.zeros(4 * ch, 2 * ch, k, k, device=dev)
                 db = torch.zeros(4 * ch, device=dev)
                 ws = F.bwd_workspace(B, hw, hw, pw, dev)
+                img = F.wgrad_accumulator(B, hw, hw, pw, dev)
                 dx, dhp, dcp = torch.empty_like(x), torch.empty_like(h), torch.empty_like(c)
-                bwd, _ = time_fn(lambda: F.cell_backward(x, h, c, pw, dh, None, dc, dW, db, workspace=ws, dx=dx,
+                bwd, _ = time_fn(lambda: F.cell_backward_acc(x, h, c, pw, dh, None, dc, img, db, workspace=ws, dx=dx,
                                                          dh_prev=dhp, dc_prev=dcp), iters=10, warm=3)
                 tf_f = flops / fwd / 1e6
                 tf_t = 3 * flops / (fwd + bwd) / 1e6
