@@ -20,6 +20,7 @@
 namespace {
 
 thread_local std::string g_err;
+unsigned long long* g_prof_buf = nullptr;   // debug cycle counters (plc_debug_set_prof)
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -334,8 +335,6 @@ int pick_cta_group(int num_m_tiles) {
   return num_m_tiles >= 2 * sm_count() ? 2 : 1;
 }
 
-// debug cycle counters (tools/kprof.py): a caller-provided device buffer of 148*16 u64, zeroed by the caller
-unsigned long long* g_prof_buf = nullptr;
 
 template <int NT, int EPI, int CTA>
 int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
@@ -449,6 +448,7 @@ int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev
   p.C0 = d->Cin; p.C1 = d->Ch; p.N4 = d->N; p.Ctot = d->Cin + d->Ch;
   p.dW = dW;
   p.db = db;
+  p.prof = g_prof_buf;
   CUtensorMap tz, t0, t1;
   if ((rc = make_tmap_act(&tz, dz, d->B, d->H, d->W, d->N, g.tw, g.th))) return rc;
   if (d->Ch > 0) {

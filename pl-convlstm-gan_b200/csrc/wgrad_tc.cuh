@@ -26,6 +26,7 @@ struct WgradTcParams {
   int C0, C1, N4, Ctot;       // true channel counts
   float* dW;                  // packed fp32 accumulator [N4][CB*64]: column = column-block*64 + channel-in-chunk
   float* db;                  // [N4] or nullptr: bias gradient = dZ^T x ones, one extra N=16 MMA per K-step
+  unsigned long long* prof;   // debug cycle counters (plc_debug_set_prof) or nullptr
 };
 
 constexpr int kWgPix = 64;                         // pixels per stage (UMMA K' = 4 x 16)
@@ -345,25 +346,25 @@ wgrad_tc_kernel2(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap
     const uint32_t idesc_a = make_idesc_bf16(256, 128 * na_half, 1, 1);
     const uint32_t idesc_b = make_idesc_bf16(256, 128, 1, 1);
     const uint32_t idesc_o = make_idesc_bf16(256, 16, 1, 1);
+    const uint64_t desc0 = make_smem_desc_mn(smem_u32(smem), kWgBoxBytes);
+    const uint64_t odesc0 = make_smem_desc_mn(smem_u32(ones_s), kWgBoxBytes);
     uint32_t stage = 0, phase = 0;
+    long long t_full = 0, t0 = clock64();
     for (int i = 0; i < my_blocks; ++i) {
+      const long long tb = p.prof ? clock64() : 0;
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      const uint32_t st = smem_u32(smem) + stage * kW2StageBytes;
+      if (p.prof) t_full += clock64() - tb;
       if (elect_one()) {
+        // descriptors: one base built before the loop, then plain adds in 16-byte units (stage, box, 16-pixel K slice)
+        const uint64_t sdesc = desc0 + stage * (kW2StageBytes >> 4);
 #pragma unroll
         for (int ks = 0; ks < kWgPix / 16; ++ks) {
-          const uint64_t adesc = make_smem_desc_mn(st + ks * 2048, kWgBoxBytes);
-          const uint64_t bdesc0 = make_smem_desc_mn(st + 2 * kWgBoxBytes + ks * 2048, kWgBoxBytes);
-          umma_bf16<2>(tmem_base, adesc, bdesc0, idesc_a, (i | ks) != 0);
-          if (has_b) {
-            const uint64_t bdesc1 = make_smem_desc_mn(st + (2 + na_half) * kWgBoxBytes + ks * 2048, kWgBoxBytes);
-            umma_bf16<2>(tmem_base + 256, adesc, bdesc1, idesc_b, (i | ks) != 0);
-          }
-          if (do_db) {
-            const uint64_t odesc = make_smem_desc_mn(smem_u32(ones_s) + ks * 2048, kWgBoxBytes);
-            umma_bf16<2>(tmem_base + kWgDbCol, adesc, odesc, idesc_o, (i | ks) != 0);
-          }
+          const uint64_t adesc = sdesc + ks * (2048 >> 4);
+          umma_bf16<2>(tmem_base, adesc, adesc + 2 * (kWgBoxBytes >> 4), idesc_a, (i | ks) != 0);
+          if (has_b)
+            umma_bf16<2>(tmem_base + 256, adesc, adesc + (2 + na_half) * (kWgBoxBytes >> 4), idesc_b, (i | ks) != 0);
+          if (do_db) umma_bf16<2>(tmem_base + kWgDbCol, adesc, odesc0 + ks * (2048 >> 4), idesc_o, (i | ks) != 0);
         }
         umma_commit_mc2(&empty_bar[stage], 0b11);
         if (i == my_blocks - 1) umma_commit_mc2(acc_bar, 0b11);
@@ -371,12 +372,19 @@ wgrad_tc_kernel2(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap
       __syncwarp();
       if (++stage == kW2Stages) { stage = 0; phase ^= 1; }
     }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 16 + 0] = clock64() - t0;
+      p.prof[blockIdx.x * 16 + 2] = t_full;
+      p.prof[blockIdx.x * 16 + 3] = my_blocks;
+    }
   } else if (warp >= 4 && my_blocks > 0) {
     // ===================================================================== epilogue (both CTAs, own 128 rows)
     const int q = warp - 4;
     const int n = n_tile * 256 + rank * 128 + q * 32 + lane;
+    const long long te = (p.prof && warp == 4) ? clock64() : 0;
     mbar_wait(acc_bar, 0);
     tc_fence_after();
+    const long long te1 = (p.prof && warp == 4) ? clock64() : 0;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     if (do_db) {
       uint32_t v[16];
@@ -399,6 +407,10 @@ wgrad_tc_kernel2(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap
                        __uint_as_float(v[e + 3]));
         }
       }
+    }
+    if (p.prof && warp == 4 && lane == 0) {
+      p.prof[blockIdx.x * 16 + 4] = te1 - te;          // epilogue warp: waiting for the accumulator
+      p.prof[blockIdx.x * 16 + 5] = clock64() - te1;   //                flushing it (vector reductions)
     }
   }
   tc_fence_before();
