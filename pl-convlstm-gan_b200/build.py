@@ -51,5 +51,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_kprof() -> str:
+    """Developer build with in-kernel cycle counters compiled in (-DPLC_KPROF) -> tools/ubench/libplc_kprof.so;
+    load it with PLC_LIB=tools/ubench/libplc_kprof.so (tools/kprof*.py)."""
+    out = os.path.join(os.path.dirname(HERE), "tools", "ubench", "libplc_kprof.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-DPLC_KPROF"] + _sources() + ["-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--kprof" in sys.argv:
+        print(build_kprof())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

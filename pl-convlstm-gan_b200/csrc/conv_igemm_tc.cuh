@@ -271,16 +271,16 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      long long ta = p.prof ? clock64() : 0;
+      long long ta = (kProfEnabled && p.prof) ? clock64() : 0;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tc_fence_after();
-      if (p.prof) t_empty += clock64() - ta;
+      if ((kProfEnabled && p.prof)) t_empty += clock64() - ta;
       const uint32_t d_tmem = tmem_base + as * N_TILE;
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        long long tb = p.prof ? clock64() : 0;
+        long long tb = (kProfEnabled && p.prof) ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (p.prof) t_full += clock64() - tb;
+        if ((kProfEnabled && p.prof)) t_full += clock64() - tb;
         if (elect_one()) {
           // descriptor start-address field is in 16-byte units
           const uint64_t adesc = adesc0 + stage * (kABytes >> 4);
@@ -303,7 +303,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-    if (p.prof && lane == 0) {
+    if ((kProfEnabled && p.prof) && lane == 0) {
       p.prof[blockIdx.x * 16 + 0] = clock64() - t0;   // MMA warp: total
       p.prof[blockIdx.x * 16 + 1] = t_empty;          //           waiting for the epilogue to free TMEM
       p.prof[blockIdx.x * 16 + 2] = t_full;           //           waiting for TMA data
@@ -318,8 +318,9 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     const int ty = row >> p.tw_log2;
     const int tx = row & (p.tw - 1);
     int it = 0;
-    long long epi_t0 = 0;
+    long long epi_t0 = 0, pa_wait = 0, pa_busy = 0, pa_barA = 0, pa_ld = 0, pa_math = 0, pa_barB = 0, pa_pre = 0, pa_iss = 0, pa_top = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+      const long long tTop = ((kProfEnabled && p.prof) && warp == 4 && lane == 0) ? clock64() : 0;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       int n_tile, b, y0, x0;
@@ -374,13 +375,14 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           gfirst.dh2 = p.dh2 ? __ldg(reinterpret_cast<const uint4*>(p.dh2 + off)) : make_uint4(0u, 0u, 0u, 0u);
         }
       }
-      long long te = (p.prof && warp == 4) ? clock64() : 0;
+      long long te = ((kProfEnabled && p.prof) && warp == 4) ? clock64() : 0;
+      if ((kProfEnabled && p.prof) && warp == 4 && lane == 0) pa_pre += te - tTop;     // decode + operand prefetch issue
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      if (p.prof && warp == 4 && lane == 0) {
+      if ((kProfEnabled && p.prof) && warp == 4 && lane == 0) {
         const long long now = clock64();
-        p.prof[blockIdx.x * 16 + 4] += now - te;                    // epilogue warp 4: waiting for an accumulator
-        if (it > 0) p.prof[blockIdx.x * 16 + 5] += te - epi_t0;     //                  busy (previous tile's work)
+        pa_wait += now - te;                    // epilogue warp 4: waiting for an accumulator
+        if (it > 0) pa_busy += te - epi_t0;     //                  busy (previous tile's work)
         epi_t0 = now;
       }
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * N_TILE;
@@ -388,11 +390,14 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       if constexpr (EPI == EPI_LSTM_FWD) {
         const int ch0 = n_tile * CH_TILE;
         const bool issuer = (warp == 4) && (lane == 0);
+        const bool pw4 = (kProfEnabled && p.prof) && warp == 4 && lane == 0;
+        long long tA = pw4 ? clock64() : 0;
         if constexpr (Cfg::kTmaStore) {
           // staging buffer free again?  (the issuer's previous bulk stores have finished reading it)
           if (issuer) tma_store_wait_read();
           named_bar_sync(1, 32 * kEpiWarps);
         }
+        if (pw4) pa_barA += clock64() - tA;   // barrier A (staging free)
 #pragma unroll
         for (int m = 0; m < kMaxGran; ++m) {
           const int g = half + m * kChunkStep;
@@ -419,8 +424,11 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
               bg[4 * v] = d4.x; bg[4 * v + 1] = d4.y; bg[4 * v + 2] = d4.z; bg[4 * v + 3] = d4.w;
             }
           }
+          long long tL = pw4 ? clock64() : 0;
           tmem_ld_wait();
+          if (pw4) pa_ld += clock64() - tL;   // tcgen05.wait::ld
           if (g + kChunkStep >= kGran) release();
+          tL = pw4 ? clock64() : 0;
           if (valid) {
             const size_t off = pix * p.Ch + chb;
             float cn[8];
@@ -475,16 +483,21 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
               }
             }
           }
+          if (pw4) pa_math += clock64() - tL;   // gate math + st.shared
         }
+        long long tB = pw4 ? clock64() : 0;
         if constexpr (Cfg::kTmaStore) {
           fence_proxy_async_smem();               // my st.shared -> visible to the TMA (async proxy)
           named_bar_sync(1, 32 * kEpiWarps);
+          if (pw4) pa_barB += clock64() - tB;   // fence + barrier B
           if (issuer) {                           // OOB rows / images (ragged tiles, odd tail pair) are clipped by TMA
+            const long long tS = (kProfEnabled && p.prof) ? clock64() : 0;
             const uint32_t so = smem_u32(stage_out);
             tma_store_4d(&tmap_o0, so, ch0, x0, y0, b);
             tma_store_4d(&tmap_o0, so + 16384, ch0 + 32, x0, y0, b);
             tma_store_4d(&tmap_o1, so + 2 * 16384, ch0, x0, y0, b);
             tma_store_commit();
+            if ((kProfEnabled && p.prof)) pa_iss += clock64() - tS;
           }
         }
       } else if constexpr (EPI == EPI_LSTM_BWD_GATES && Cfg::kTmaStore) {
@@ -517,8 +530,11 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         gin[0] = gfirst;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
+          const bool pw4 = (kProfEnabled && p.prof) && warp == 4 && lane == 0;
+          long long tA = pw4 ? clock64() : 0;
           if (issuer) tma_store_wait_read();       // staging buffer free again?
           named_bar_sync(1, 32 * kEpiWarps);
+          if (pw4) pa_barA += clock64() - tA;
 #pragma unroll
           for (int j = 0; j < GPR; ++j) {
             constexpr int kLast = 2 * GPR - 1;
@@ -550,8 +566,11 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                 bg[4 * v] = d4.x; bg[4 * v + 1] = d4.y; bg[4 * v + 2] = d4.z; bg[4 * v + 3] = d4.w;
               }
             }
+            long long tL = pw4 ? clock64() : 0;
             tmem_ld_wait();
+            if (pw4) pa_ld += clock64() - tL;
             if (idx == kLast) release();
+            tL = pw4 ? clock64() : 0;
             if (valid) {
               const GIn& in = gin[idx & 1];
               const float cp[8] = {in.c0.x, in.c0.y, in.c0.z, in.c0.w, in.c1.x, in.c1.y, in.c1.z, in.c1.w};
@@ -603,9 +622,12 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
               st_shared_v4(crow + (((gl * 2 + 1) ^ sw) << 4), __float_as_uint(dcp[4]), __float_as_uint(dcp[5]),
                            __float_as_uint(dcp[6]), __float_as_uint(dcp[7]));
             }
+            if (pw4) pa_math += clock64() - tL;
           }
+          long long tB = pw4 ? clock64() : 0;
           fence_proxy_async_smem();
           named_bar_sync(1, 32 * kEpiWarps);
+          if (pw4) pa_barB += clock64() - tB;
           if (issuer) {
             const uint32_t so = smem_u32(stage_out);
             const int cbase = ch0 + r * 32;
@@ -787,6 +809,11 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     }
     if constexpr (Cfg::kTmaStore) {
       if (warp == 4 && lane == 0) tma_store_wait_all();   // bulk stores complete before the CTA retires
+    }
+    if ((kProfEnabled && p.prof) && warp == 4 && lane == 0) {
+      unsigned long long* q = p.prof + blockIdx.x * 16;
+      q[4] = pa_wait; q[5] = pa_busy; q[6] = pa_barA; q[7] = pa_ld; q[8] = pa_math; q[9] = pa_barB;
+      q[10] = pa_pre; q[11] = pa_iss; q[12] = pa_top;
     }
   }
 

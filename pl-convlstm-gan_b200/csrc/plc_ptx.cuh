@@ -8,6 +8,14 @@
 
 namespace plc {
 
+// In-kernel cycle counters (tools/kprof*.py) exist only in builds made with -DPLC_KPROF (build.py --kprof):
+// in the product build every `(kProfEnabled && p.prof)` test is a compile-time false and the code vanishes.
+#ifdef PLC_KPROF
+constexpr bool kProfEnabled = true;
+#else
+constexpr bool kProfEnabled = false;
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

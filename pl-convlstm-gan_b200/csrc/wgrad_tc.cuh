@@ -351,10 +351,10 @@ wgrad_tc_kernel2(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap
     uint32_t stage = 0, phase = 0;
     long long t_full = 0, t0 = clock64();
     for (int i = 0; i < my_blocks; ++i) {
-      const long long tb = p.prof ? clock64() : 0;
+      const long long tb = (kProfEnabled && p.prof) ? clock64() : 0;
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (p.prof) t_full += clock64() - tb;
+      if ((kProfEnabled && p.prof)) t_full += clock64() - tb;
       if (elect_one()) {
         // descriptors: one base built before the loop, then plain adds in 16-byte units (stage, box, 16-pixel K slice)
         const uint64_t sdesc = desc0 + stage * (kW2StageBytes >> 4);
@@ -372,7 +372,7 @@ wgrad_tc_kernel2(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap
       __syncwarp();
       if (++stage == kW2Stages) { stage = 0; phase ^= 1; }
     }
-    if (p.prof && lane == 0) {
+    if ((kProfEnabled && p.prof) && lane == 0) {
       p.prof[blockIdx.x * 16 + 0] = clock64() - t0;
       p.prof[blockIdx.x * 16 + 2] = t_full;
       p.prof[blockIdx.x * 16 + 3] = my_blocks;
@@ -381,10 +381,10 @@ wgrad_tc_kernel2(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap
     // ===================================================================== epilogue (both CTAs, own 128 rows)
     const int q = warp - 4;
     const int n = n_tile * 256 + rank * 128 + q * 32 + lane;
-    const long long te = (p.prof && warp == 4) ? clock64() : 0;
+    const long long te = ((kProfEnabled && p.prof) && warp == 4) ? clock64() : 0;
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    const long long te1 = (p.prof && warp == 4) ? clock64() : 0;
+    const long long te1 = ((kProfEnabled && p.prof) && warp == 4) ? clock64() : 0;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     if (do_db) {
       uint32_t v[16];
@@ -408,7 +408,7 @@ wgrad_tc_kernel2(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap
         }
       }
     }
-    if (p.prof && warp == 4 && lane == 0) {
+    if ((kProfEnabled && p.prof) && warp == 4 && lane == 0) {
       p.prof[blockIdx.x * 16 + 4] = te1 - te;          // epilogue warp: waiting for the accumulator
       p.prof[blockIdx.x * 16 + 5] = clock64() - te1;   //                flushing it (vector reductions)
     }

@@ -6,6 +6,10 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_KLIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "ubench", "libplc_kprof.so")
+if not os.path.exists(_KLIB):
+    raise SystemExit("build the instrumented library first:  python pl-convlstm-gan_b200/build.py --kprof")
+os.environ.setdefault("PLC_LIB", _KLIB)   # cycle counters only exist in the -DPLC_KPROF build
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
@@ -39,6 +43,10 @@ def main():
     print(f"  wait TMEM-empty (epilogue) {te:.0f} ({100 * te / tot:.1f}%)   wait TMA-full {tf:.0f} ({100 * tf / tot:.1f}%)"
           f"   issuing {tot - te - tf:.0f} ({100 * (tot - te - tf) / tot:.1f}%)")
     ep = p[p[:, 5] > 0]
+    t = max(tiles, 1)
+    print(f"  per tile: barrier-A {ep[:, 6].mean() / t:.0f}  tmem-ld-wait {ep[:, 7].mean() / t:.0f}  math+st.shared "
+          f"{ep[:, 8].mean() / t:.0f}  fence+barrier-B {ep[:, 9].mean() / t:.0f}  decode+prefetch {ep[:, 10].mean() / t:.0f}  "
+          f"store-issue {ep[:, 11].mean() / t:.0f}")
     print(f"epilogue warp 4 (all CTAs {len(ep)}): idle-wait {ep[:, 4].mean():.0f} cyc, busy {ep[:, 5].mean():.0f} cyc, "
           f"busy per tile {ep[:, 5].mean() / max(tiles - 1, 1):.0f}")
 

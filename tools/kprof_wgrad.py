@@ -2,6 +2,10 @@
 """In-kernel cycle accounting of the pair wgrad kernel.  python tools/kprof_wgrad.py B C Ch H W k"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_KLIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "ubench", "libplc_kprof.so")
+if not os.path.exists(_KLIB):
+    raise SystemExit("build the instrumented library first:  python pl-convlstm-gan_b200/build.py --kprof")
+os.environ.setdefault("PLC_LIB", _KLIB)   # cycle counters only exist in the -DPLC_KPROF build
 sys.path.insert(0, ROOT)
 import torch
 import plconv
