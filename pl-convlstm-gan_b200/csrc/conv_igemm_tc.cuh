@@ -35,6 +35,8 @@ struct ConvTcParams {
   int tw, th, tw_log2;       // tile = th x tw pixels, tw*th == 128, tw power of two
   int tiles_x, tiles_y;      // per image
   int num_m_tiles, num_n_tiles, num_tiles;
+  // exact n / d for n < 2^20 via one 64-bit multiply: q = (n * mul) >> 40, mul = ceil(2^40 / d)  (0 = use '/')
+  unsigned long long div_n_tiles, div_tiles_x, div_tiles_y;
   int kc;                    // channels per TMA box: 64, 32 or 16 (narrow sources pack G = 64/kc taps into one K stage)
   int chunks0, chunks1;      // kc-channel chunks of source 0 / source 1
   int num_boxes;             // ksize^2 * (chunks0 + chunks1) boxes of [kc ch x 128 px]
@@ -103,15 +105,19 @@ struct ConvTcCfg {
 // tile -> (n_tile, image b, patch origin).  With kCta == 2 a "tile" is a PAIR tile: two adjacent 128-pixel m-tiles
 // (CTA rank r takes m_tile = 2*mpair + r; an odd tail m-tile decodes to b == B, which TMA zero-fills and the
 // epilogue masks).
+__device__ __forceinline__ int fast_div(int n, int d, unsigned long long mul) {
+  return mul ? static_cast<int>((static_cast<unsigned long long>(n) * mul) >> 40) : n / d;
+}
 template <int kCta>
 __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int rank, int& n_tile, int& b, int& y0,
                                             int& x0) {
-  n_tile = tile % p.num_n_tiles;
-  int m_tile = (tile / p.num_n_tiles) * kCta + rank;
-  int tx = m_tile % p.tiles_x;
-  int r = m_tile / p.tiles_x;
-  int ty = r % p.tiles_y;
-  b = r / p.tiles_y;
+  const int mq = fast_div(tile, p.num_n_tiles, p.div_n_tiles);
+  n_tile = tile - mq * p.num_n_tiles;
+  const int m_tile = mq * kCta + rank;
+  const int r = fast_div(m_tile, p.tiles_x, p.div_tiles_x);
+  const int tx = m_tile - r * p.tiles_x;
+  b = fast_div(r, p.tiles_y, p.div_tiles_y);
+  const int ty = r - b * p.tiles_y;
   y0 = ty * p.th;
   x0 = tx * p.tw;
 }

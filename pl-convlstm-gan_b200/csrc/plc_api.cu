@@ -343,6 +343,13 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
   plc::ConvTcParams p = p_in;
   p.prof = g_prof_buf;
   auto kfn = plc::conv_igemm_tc_kernel<NT, EPI, CTA>;
+  {  // fast exact division constants for the tile decode (valid while every dividend stays below 2^20)
+    auto magic = [](int d) -> unsigned long long { return ((1ull << 40) + d - 1) / static_cast<unsigned long long>(d); };
+    const bool small = static_cast<long long>(p.num_m_tiles + 1) * p.num_n_tiles < (1 << 20);
+    p.div_n_tiles = small ? magic(p.num_n_tiles) : 0;
+    p.div_tiles_x = small ? magic(p.tiles_x) : 0;
+    p.div_tiles_y = small ? magic(p.tiles_y) : 0;
+  }
   PLC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int tiles = CTA == 2 ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_tiles;
   const int slots = sm_count() / CTA;
