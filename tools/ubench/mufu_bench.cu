@@ -16,6 +16,9 @@ __device__ __forceinline__ float op(float x) {
     y = __uint_as_float(v);
   }
   if (OP == 4) y = fmaf(x, 1.0001f, 0.5f);
+  if (OP == 6) {  // register-register FFMA (no immediates)
+    asm volatile("fma.rn.f32 %0, %1, %1, %1;" : "=f"(y) : "f"(x));
+  }
   return y;
 }
 
@@ -32,6 +35,41 @@ __global__ void k(float* out, int iters) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += a[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// packed fp32: fma.rn.f32x2 does two FMAs per instruction (Blackwell FFMA2)
+__global__ void k_f32x2(float* out, int iters) {
+  unsigned long long a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (unsigned long long)__float_as_uint(threadIdx.x * 1e-3f + i * 0.1f) * 0x100000001ull;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(a[i]));
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s ^= a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float((unsigned)s);
+}
+void run_x2(int warps_per_sm) {
+  int sms = 148, iters = 4096;
+  float* out;
+  cudaMalloc(&out, sms * warps_per_sm * 32 * sizeof(float));
+  k_f32x2<<<sms, warps_per_sm * 32>>>(out, 16);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  k_f32x2<<<sms, warps_per_sm * 32>>>(out, iters);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  int clk_khz;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  double ops = double(sms) * warps_per_sm * 32 * iters * 8;
+  printf("%-18s warps/SM %2d : %.2f thread-INSTR/clk/SM (x2 results each) at %d MHz nominal\n", "fma.rn.f32x2", warps_per_sm,
+         ops / (ms * 1e-3) / sms / (clk_khz * 1e3), clk_khz / 1000);
+  cudaFree(out);
 }
 
 template <int OP>
@@ -62,7 +100,9 @@ int main() {
     run<3>("tanh.approx.f16x2", w);
     run<1>("ex2.approx.f32", w);
     run<2>("rcp.approx.f32", w);
-    run<4>("ffma", w);
+    run<4>("ffma (imm)", w);
+    run<6>("ffma (reg)", w);
+    run_x2(w);
   }
   return 0;
 }
