@@ -178,6 +178,32 @@ int plc_frames_to_nhwc(const float* frames, int B, int T, int Cf, int H, int W, 
 int plc_head_bwd(const void* h, long npix, int C, const float* w, const float* dy, void* dh, float* dw_acc,
                  float* db_acc, void* stream);
 
+/* ---- CombinedLoss (SURVEY.md section 8f "next-2") ---------------------------------------------
+ * plc_combined_loss replaces CombinedLoss.forward (src/losses/combined_loss.py:173-191) and its autograd:
+ * station point supervision (:79-141), conservation by area pooling (:64-74), spatial gradient (:146-155), temporal
+ * consistency (:160-168), in fp32.
+ *   pred      [B,T,1,H*scale,W*scale] fp32      lr_input [B,T,1,H,W] fp32
+ *   s_coords  [N,2] int64 (row, col) on the LR grid; mapped to HR pixels with ((c + 0.5) * coord_scale - 0.5) truncated
+ *   s_values  [T,N] (svals_has_batch = 0) or [B,T,N] fp32, NaN = no observation
+ *   terms_out [5] fp32 DEVICE: total, point, conserve, smooth, temporal          (no host synchronisation)
+ *   dpred     [B,T,1,H*scale,W*scale] fp32 = grad_scale * d total / d pred, or NULL for loss values only
+ *   grad_scale DEVICE scalar (the upstream gradient of `total`), or NULL for 1
+ *   workspace plc_loss_workspace_bytes(d) bytes, 16-byte aligned
+ * Only integer upsampling ratios are supported (the Generator only produces those).                          */
+typedef struct PlcLossDesc {
+  int32_t B, T, H, W;       /* LR grid                                                   */
+  int32_t scale;            /* HR = LR * scale                                           */
+  int32_t n_stations;
+  int32_t svals_has_batch;
+  int32_t weight_mode;      /* 0 off, 1 log, 2 sqrt, 3 stratified (combined_loss.py:22-59) */
+  float coord_scale;        /* scale_factor argument of CombinedLoss.forward             */
+  float lambda_point, lambda_conserve, lambda_smooth, lambda_temporal;
+} PlcLossDesc;
+size_t plc_loss_workspace_bytes(const PlcLossDesc* d);
+int plc_combined_loss(const PlcLossDesc* d, const float* pred, const float* lr_input, const long long* s_coords,
+                      const float* s_values, void* workspace, float* terms_out, float* dpred, const float* grad_scale,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,9 +26,17 @@ class PlcConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("B", "H", "W", "Cin", "Cout", "k", "relu", "pixel_shuffle", "has_bias")]
 
 
+class PlcLossDesc(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "scale", "n_stations", "svals_has_batch",
+                                               "weight_mode")] +
+                [(n, ctypes.c_float) for n in ("coord_scale", "lambda_point", "lambda_conserve", "lambda_smooth",
+                                               "lambda_temporal")])
+
+
 _vp, _sz, _int = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
 _dp = ctypes.POINTER(PlcCellDesc)
 _cp = ctypes.POINTER(PlcConvDesc)
+_lp = ctypes.POINTER(PlcLossDesc)
 
 # name -> (restype, argtypes); must list every symbol include/plc.h declares (tests check this)
 SIGNATURES = {
@@ -57,6 +65,8 @@ SIGNATURES = {
     "plc_head_fwd": (_int, [_vp, ctypes.c_long, _int, _vp, _vp, _int, _vp, _vp]),
     "plc_frames_to_nhwc": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp]),
     "plc_head_bwd": (_int, [_vp, ctypes.c_long, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "plc_loss_workspace_bytes": (_sz, [_lp]),
+    "plc_combined_loss": (_int, [_lp] + [_vp] * 9),
 }
 
 _lock = threading.Lock()

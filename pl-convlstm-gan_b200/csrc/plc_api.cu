@@ -15,6 +15,7 @@
 #include "conv_igemm_tc.cuh"
 #include "conv_simt.cuh"
 #include "frame_io.cuh"
+#include "loss.cuh"
 #include "wgrad_tc.cuh"
 
 namespace {
@@ -1011,6 +1012,72 @@ int plc_head_bwd(const void* h, long npix, int C, const float* w, const float* d
 #define PLC_HB(GG) case GG: plc::head_bwd_kernel_bf16<GG><<<blocks, 256, 0, st>>>(hb, w, dy, dhb, dw_acc, db_acc, (size_t)npix); break;
   switch (G) { PLC_HB(1) PLC_HB(2) PLC_HB(4) PLC_HB(8) PLC_HB(16) PLC_HB(32) }
 #undef PLC_HB
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+static int loss_check(const PlcLossDesc* d, const char* fn) {
+  if (!d) return fail(PLC_ERR_NULL_ARG, "%s: null descriptor", fn);
+  if (d->B <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->scale <= 0 || d->n_stations < 0)
+    return fail(PLC_ERR_BAD_DESC, "%s: B,T,H,W,scale must be positive (got B=%d T=%d H=%d W=%d scale=%d N=%d)", fn, d->B,
+                d->T, d->H, d->W, d->scale, d->n_stations);
+  if (d->weight_mode < 0 || d->weight_mode > 3)
+    return fail(PLC_ERR_BAD_DESC, "%s: weight_mode must be 0 (off), 1 (log), 2 (sqrt) or 3 (stratified)", fn);
+  if (static_cast<long long>(d->H) * d->scale > 0x7fffffffLL || static_cast<long long>(d->W) * d->scale > 0x7fffffffLL)
+    return fail(PLC_ERR_BAD_DESC, "%s: high-resolution grid too large", fn);
+  return PLC_OK;
+}
+
+size_t plc_loss_workspace_bytes(const PlcLossDesc* d) {
+  if (loss_check(d, "plc_loss_workspace_bytes") != PLC_OK) return 0;
+  return 64;   /* the reduction cells; the conservation residual signs stay in shared memory */
+}
+
+int plc_combined_loss(const PlcLossDesc* d, const float* pred, const float* lr_input, const long long* s_coords,
+                      const float* s_values, void* workspace, float* terms_out, float* dpred, const float* grad_scale,
+                      void* stream) {
+  if (int rc = loss_check(d, "plc_combined_loss")) return rc;
+  if (!pred || !lr_input || !workspace || !terms_out) return fail(PLC_ERR_NULL_ARG, "plc_combined_loss: null pointer");
+  if (d->n_stations > 0 && (!s_coords || !s_values))
+    return fail(PLC_ERR_NULL_ARG, "plc_combined_loss: n_stations > 0 needs s_coords and s_values");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  plc::LossParams p{};
+  p.B = d->B; p.T = d->T; p.H = d->H; p.W = d->W; p.s = d->scale;
+  p.Hs = d->H * d->scale; p.Ws = d->W * d->scale;
+  p.n_st = d->n_stations; p.svals_has_batch = d->svals_has_batch; p.coord_scale = d->coord_scale;
+  p.weight_mode = d->weight_mode;
+  p.l_point = d->lambda_point; p.l_cons = d->lambda_conserve; p.l_smooth = d->lambda_smooth; p.l_temp = d->lambda_temporal;
+  p.pred = pred; p.lr = lr_input; p.coords = s_coords; p.svals = s_values;
+  p.sums = static_cast<float*>(workspace);
+  p.dpred = dpred;
+  p.grad_scale = grad_scale;
+  PLC_CUDA(cudaMemsetAsync(workspace, 0, 64, st));
+  const size_t cap = static_cast<size_t>(sm_count()) * 8;
+  auto blocks = [&](size_t n) { return static_cast<unsigned>(std::min(cap, (n + 255) / 256)); };
+  // block = 256 threads as (bx along x) x (by strips of ~8 rows); band = m LR rows ~ 8 * by HR rows; the sign table
+  // (m * W floats) lives in shared memory
+  const bool vec4 = p.Ws % 4 == 0 && aligned16(pred) && (!dpred || aligned16(dpred));
+  int bx = 4;
+  while (bx < 256 && bx * (vec4 ? 4 : 1) < p.Ws) bx *= 2;
+  const int by = 256 / bx;
+  const int m = std::min(p.H, std::max(1, (8 * by + p.s / 2) / p.s));
+  const int rpt = (m * p.s + by - 1) / by;
+  const int bands = (p.H + m - 1) / m;
+  const size_t smem = sizeof(float) * m * p.W;
+  const long long nblk = static_cast<long long>(p.B) * p.T * bands;
+  if (smem > 160 * 1024 || nblk > 0x7fffffffLL)
+    return fail(PLC_ERR_UNSUPPORTED, "plc_combined_loss: grid too large (W=%d, %lld blocks)", p.W, nblk);
+  auto kern = vec4 ? plc::loss_grid_kernel<4> : plc::loss_grid_kernel<1>;
+  if (smem > 48 * 1024)
+    PLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<static_cast<unsigned>(std::min<long long>(nblk, cap)), dim3(bx, by), smem, st>>>(p, m, bands,
+                                                                                         static_cast<int>(nblk), rpt);
+  const size_t n_obs = static_cast<size_t>(p.B) * p.T * p.n_st;
+  if (n_obs) {
+    plc::loss_point_kernel<<<blocks(n_obs), 256, 0, st>>>(p);
+    if (dpred) plc::loss_point_grad_kernel<<<blocks(n_obs), 256, 0, st>>>(p);
+  }
+  plc::loss_finalize_kernel<<<1, 1, 0, st>>>(p, terms_out);
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;
 }

@@ -149,3 +149,48 @@ if __name__ == "__main__":
     for case in GENERATOR_CASES:
         gen_generator(*case)
     print("wrote", len(GENERATOR_CASES), "generator fixtures")
+
+
+# ------------------------------------------------------------------------------------------------
+# CombinedLoss alone (SURVEY.md section 8f "next-2"): loss terms and d total / d pred from the unmodified reference
+# (combined_loss.py:173-191) for every weight strategy, [T,N] and [B,T,N] observations, NaN gaps, stations that
+# fall outside the grid, exact ties (sign(0) = 0) and non-default lambdas.
+def gen_loss(name, seed, B, T, H, W, scale, n_st, batch_obs, strategy, weighted, lambdas):
+    from src.losses.combined_loss import CombinedLoss
+    torch.manual_seed(seed)
+    pred = (torch.rand(B, T, 1, H * scale, W * scale) * 8.0).requires_grad_(True)
+    with torch.no_grad():
+        pred[0, 0, 0, 0, :4] = 1.5                           # ties: zero spatial differences
+        if T > 1:
+            pred[0, 1, 0, 1, :] = pred[0, 0, 0, 1, :]        # ties in time
+    lr = torch.rand(B, T, 1, H, W) * 8.0
+    coords = torch.stack([torch.randint(0, H, (n_st,)), torch.randint(0, W, (n_st,))], dim=1)
+    if n_st > 2:
+        coords[1] = torch.tensor([H + 3, 0])                 # outside the grid -> dropped (combined_loss.py:101-107)
+        coords[2] = coords[0]                                # two gauges in one pixel
+    obs = torch.rand((B, T, n_st) if batch_obs else (T, n_st)) * 60.0
+    obs[..., 0, 0] = float("nan")
+    if n_st > 3:
+        obs[..., -1, 3] = float("nan")
+    mod = CombinedLoss(*lambdas, use_weighted_loss=weighted, weight_strategy=strategy)
+    total, parts = mod(pred, lr, coords, obs, scale_factor=scale)
+    total.backward()
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), pred=np32(pred), lr=np32(lr), coords=coords.numpy().astype(np.int64),
+        obs=np32(obs), scale=np.int32(scale), lambdas=np.array(lambdas, dtype=np.float32),
+        strategy=np.array(strategy), weighted=np.int32(weighted), dpred=np32(pred.grad), total=np32(total),
+        point=np32(parts["point"]), conserve=np32(parts["conserve"]), smooth=np32(parts["smooth"]),
+        temporal=np32(parts["temporal"]))
+
+
+LOSS_CASES = [
+    ("loss_log_b2_t3_6x7_x2", 401, 2, 3, 6, 7, 2, 6, False, "log", True, (1.0, 1.0, 0.1, 0.05)),
+    ("loss_sqrt_b1_t4_5x5_x4_batchobs", 402, 1, 4, 5, 5, 4, 5, True, "sqrt", True, (0.7, 1.3, 0.2, 0.1)),
+    ("loss_strat_b3_t2_4x9_x1", 403, 3, 2, 4, 9, 1, 8, True, "stratified", True, (1.0, 1.0, 0.1, 0.05)),
+    ("loss_unweighted_b2_t2_8x8_x8", 404, 2, 2, 8, 8, 8, 4, False, "log", False, (2.0, 0.5, 0.3, 0.0)),
+]
+
+if __name__ == "__main__":
+    for case in LOSS_CASES:
+        gen_loss(*case)
+    print("wrote", len(LOSS_CASES), "loss fixtures")

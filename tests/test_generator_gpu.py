@@ -93,3 +93,25 @@ def test_native_generator_gradients_bf16_vs_reference_autograd(path, cuda_device
         if rel_err(p.grad, ref) >= 6e-2:
             bad.append(report(name, p.grad, ref))
     assert not bad, " | ".join(bad)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-3), ("bf16", 6e-2)])
+@pytest.mark.parametrize("path", golden_files("generator_b2"), ids=os.path.basename)
+def test_product_generator_plus_product_loss_vs_reference(path, mode, tol, cuda_device):
+    """The whole trainer.py:297-310 path on product code only: plconv.Generator -> plconv.CombinedLoss
+    (plc_combined_loss) -> backward; loss value and every parameter gradient against the unmodified reference."""
+    import plconv
+    g = load_golden(path)
+    gen = _build(g, mode, cuda_device)
+    rain, dem, lu = (torch.from_numpy(g[k]).to(cuda_device) for k in ("rain", "dem", "lu"))
+    total, parts = plconv.CombinedLoss()(gen(rain, dem, lu), rain, torch.from_numpy(g["s_coords"]),
+                                         torch.from_numpy(g["s_vals"]), scale_factor=int(g["scale"]))
+    total.backward()
+    assert abs(float(total) - float(g["loss_total"])) <= tol * abs(float(g["loss_total"])) + 1e-6
+    bad = []
+    for name, p in gen.named_parameters():
+        ref = torch.from_numpy(g["grad." + name])
+        assert p.grad is not None, name
+        if rel_err(p.grad, ref) >= tol:
+            bad.append(report(name, p.grad, ref))
+    assert not bad, " | ".join(bad)

@@ -169,3 +169,19 @@ def test_loss_oracle_matches_reference_golden(path):
     for k in ("point", "conserve", "smooth", "temporal"):
         assert abs(float(parts[k]) - float(g["loss_" + k])) <= 1e-5 * max(1.0, abs(float(g["loss_" + k]))), k
     assert abs(float(total) - float(g["loss_total"])) <= 1e-5 * abs(float(g["loss_total"]))
+
+
+@pytest.mark.parametrize("path", golden_files("loss_"), ids=os.path.basename)
+def test_loss_oracle_terms_and_gradient_match_reference_golden(path):
+    """All weight strategies, [T,N] / [B,T,N] observations, NaN gaps, off-grid gauges, ties: values AND d total/d pred."""
+    from oracle import loss_oracle as L
+    g = load_golden(path)
+    pred = T(g["pred"]).requires_grad_(True)
+    total, parts = L.combined_loss(pred, T(g["lr"]), T(g["coords"]), T(g["obs"]), scale_factor=int(g["scale"]),
+                                   lambdas=tuple(float(v) for v in g["lambdas"]), strategy=str(g["strategy"]),
+                                   use_weighted=bool(g["weighted"]))
+    total.backward()
+    for k in ("point", "conserve", "smooth", "temporal"):
+        assert abs(float(parts[k]) - float(g[k])) <= 1e-6 * max(1.0, abs(float(g[k]))), k
+    assert abs(float(total) - float(g["total"])) <= 1e-6 * abs(float(g["total"]))
+    assert torch.allclose(pred.grad, T(g["dpred"]), rtol=1e-6, atol=1e-9)

@@ -12,7 +12,6 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 import plconv  # noqa: E402
-from oracle import loss_oracle as L  # noqa: E402  (benchmark harness only: the loss is not part of the product)
 
 
 def run(B, T, H, W, hd, scale, lu_ch, mode, iters=10):
@@ -27,11 +26,12 @@ def run(B, T, H, W, hd, scale, lu_ch, mode, iters=10):
     s_coords = torch.stack([torch.randint(0, H, (n_st,)), torch.randint(0, W, (n_st,))], 1).to(dev)
     s_vals = (torch.rand(T, n_st) * 20).to(dev)
     opt = torch.optim.Adam(gen.parameters(), lr=5e-4)
+    loss_mod = plconv.CombinedLoss()                       # fused loss + gradient (plc_combined_loss)
 
     def step():
         opt.zero_grad()
         pred = gen(rain, dem, lu)
-        loss, _ = L.combined_loss(pred, rain, s_coords, s_vals, scale_factor=scale)
+        loss, _ = loss_mod(pred, rain, s_coords, s_vals, scale_factor=scale)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(gen.parameters(), 0.5)
         opt.step()
