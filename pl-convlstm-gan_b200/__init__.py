@@ -2,8 +2,9 @@
 
 Import name: ``plconv`` (this directory's name has hyphens; ``plconv/__init__.py`` aliases it).
 """
-from . import _lib, build, functional, generator, losses, nn, parallel, rollout, training  # noqa: F401
+from . import _lib, build, functional, generator, losses, nn, parallel, rollout, trainer, training  # noqa: F401
 from .losses import CombinedLoss  # noqa: F401
+from .trainer import Trainer, TrainerConfig  # noqa: F401
 from .generator import Generator  # noqa: F401
 from .nn import ConvLSTMCell, ConvLSTMStack, EncoderForecaster  # noqa: F401
 from .rollout import NowcastGenerator, NowcastRunner  # noqa: F401

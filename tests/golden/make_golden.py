@@ -194,3 +194,57 @@ if __name__ == "__main__":
     for case in LOSS_CASES:
         gen_loss(*case)
     print("wrote", len(LOSS_CASES), "loss fixtures")
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's optimisation loop (trainer.py:153-158 Adam, :286-315 train_epoch body) on the unmodified Generator
+# and CombinedLoss, CPU fp32: per-step loss terms + station RMSE (trainer.py:225-268) and the parameters after N
+# steps.  The Trainer class itself cannot be imported here (geopandas / matplotlib), so the loop body is replayed
+# statement by statement -- including its quirk: the optimizer is built BEFORE the first forward creates
+# upsample_blocks (generator.py:129-130), so those parameters are never updated nor zeroed, yet they are clipped.
+def gen_train(name, seed, steps, B, T, H, W, hd, scale, lu_ch, n_st):
+    import torch.nn.functional as F
+    from src.models.generator import Generator
+    from src.losses.combined_loss import CombinedLoss
+    torch.manual_seed(seed)
+    gen = Generator(in_channels=1, dem_channels=1, lu_channels=lu_ch, hidden_dims=list(hd), scale_factor=scale)
+    sd0 = {k: np32(v) for k, v in gen.state_dict().items()}
+    opt = torch.optim.Adam(gen.parameters(), lr=5e-4)                         # trainer.py:155-158
+    crit = CombinedLoss()
+    coords = torch.stack([torch.randint(0, H, (n_st,)), torch.randint(0, W, (n_st,))], dim=1)
+    out = {}
+    for i in range(steps):
+        rain = torch.rand(B, T, 1, H, W) * 5.0
+        dem = torch.rand(B, 1, H * scale, W * scale)
+        lu = torch.rand(B, lu_ch, H * scale, W * scale)
+        obs = torch.rand(B, T, n_st) * 20.0
+        obs[0, 0, i % n_st] = float("nan")
+        opt.zero_grad()
+        fake = gen(rain, dem, lu)
+        sf = fake.shape[-2] / rain.shape[-2]
+        loss, parts = crit(fake, rain, coords, obs, sf)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(gen.parameters(), max_norm=0.5)       # trainer.py:311-314
+        opt.step()
+        with torch.no_grad():                                                # trainer.py:225-268
+            sc = ((coords.float() + 0.5) * sf - 0.5).long()
+            at = fake[:, :, 0][:, :, sc[:, 0], sc[:, 1]]
+            m = ~torch.isnan(obs)
+            rmse = torch.sqrt(F.mse_loss(at[m], obs[m]))
+        out.update({f"rain{i}": np32(rain), f"dem{i}": np32(dem), f"lu{i}": np32(lu), f"obs{i}": np32(obs),
+                    f"loss{i}": np.array([float(loss)] + [float(parts[k]) for k in
+                                                          ("point", "conserve", "smooth", "temporal")], np.float32),
+                    f"rmse{i}": np32(rmse)})
+    sd1 = {k: np32(v) for k, v in gen.state_dict().items()}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), coords=coords.numpy().astype(np.int64),
+                        steps=np.int32(steps), scale=np.int32(scale), hidden_dims=np.array(hd, dtype=np.int32),
+                        lu_ch=np.int32(lu_ch), **out, **{"sd0." + k: v for k, v in sd0.items()},
+                        **{"sd1." + k: v for k, v in sd1.items()})
+
+
+TRAIN_CASES = [("train_b2_t3_8x10_h16_16_x2_4steps", 501, 4, 2, 3, 8, 10, (16, 16), 2, 3, 6)]
+
+if __name__ == "__main__":
+    for case in TRAIN_CASES:
+        gen_train(*case)
+    print("wrote", len(TRAIN_CASES), "training fixtures")

@@ -1,0 +1,182 @@
+"""Host logic of plconv.trainer on CPU (stub model: the CUDA kernels are not involved): early stopping against the
+live reference class, epoch loop / scheduler / best-model checkpoint format (trainer.py:402-418) / resume, the
+sync-free station RMSE against the reference formula, and the world-size-2 gloo path (collective-safe NaN-skip)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import plconv
+from plconv.trainer import EarlyStopping, Trainer, TrainerConfig, station_rmse
+
+REF = os.environ.get("PLC_REFERENCE", "/root/reference")
+
+
+class _StubGen(torch.nn.Module):
+    """rain [B,T,1,H,W] -> [B,T,1,2H,2W]; two top-level children so there are two gradient buckets."""
+
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Conv2d(1, 4, 3, padding=1)
+        self.b = torch.nn.Conv2d(4, 1, 3, padding=1)
+
+    def forward(self, rain, dem, lu):
+        B, T = rain.shape[:2]
+        x = torch.nn.functional.interpolate(rain.flatten(0, 1), scale_factor=2.0, mode="nearest")
+        return self.b(torch.relu(self.a(x))).view(B, T, 1, *x.shape[-2:])
+
+
+class _StubLoss(torch.nn.Module):
+    def forward(self, pred, lr, s_coords, s_values, scale_factor=1.0):
+        pooled = torch.nn.functional.avg_pool2d(pred.flatten(0, 1), 2).view_as(lr)
+        cons = (pooled - lr).abs().mean()
+        z = cons.detach() * 0
+        return cons, {"point": z, "conserve": cons.detach(), "smooth": z, "temporal": z}
+
+
+def _batches(n, seed=0, B=2, nan_at=None):
+    g = torch.Generator().manual_seed(seed)
+    coords = torch.tensor([[0, 0], [3, 4], [9, 9]])
+    out = []
+    for i in range(n):
+        rain = torch.rand(B, 2, 1, 6, 8, generator=g)
+        if nan_at == i:
+            rain[0, 0, 0, 0, 0] = float("nan")
+        out.append((rain, torch.zeros(B, 1, 12, 16), torch.zeros(B, 0, 12, 16), coords,
+                    torch.rand(B, 2, 3, generator=g)))
+    return out
+
+
+def _trainer(tmp=None, **kw):
+    torch.manual_seed(1)
+    cfg = TrainerConfig(scale_factor=2, output_dir=tmp, **kw)
+    return Trainer(cfg, device="cpu", model=_StubGen(), loss_module=_StubLoss())
+
+
+def test_early_stopping_matches_reference_class():
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, REF)
+    sys.dont_write_bytecode = True
+    from src.utils.early_stopping import EarlyStopping as RefES
+    scores = [5.0, 4.0, 4.0, 3.99, 4.5, 3.0, 3.2, 3.1, 3.05, 2.0]
+    for patience, delta in ((2, 0.0), (3, 0.05), (1, 0.0)):
+        a, b = EarlyStopping(patience, delta), RefES(patience=patience, min_delta=delta, verbose=False)
+        for e, s in enumerate(scores):
+            assert a(s, e) == b(s, e)
+            assert (a.counter, a.best_score, a.best_epoch, a.early_stop) == (b.counter, b.best_score, b.best_epoch,
+                                                                             b.early_stop)
+
+
+def test_station_rmse_matches_reference_formula():
+    torch.manual_seed(0)
+    fake = torch.rand(2, 3, 1, 12, 16)
+    coords = torch.tensor([[0, 0], [5, 7], [6, 2], [2, 7]])          # [6,2]*2 -> row 12: off the 12-row grid
+    obs = torch.rand(2, 3, 4)
+    obs[0, 1, 1] = float("nan")
+    got = station_rmse(fake, coords, obs, 2.0)
+    sc = ((coords.float() + 0.5) * 2.0 - 0.5).long()                 # trainer.py:236-262
+    ok = (sc[:, 0] < 12) & (sc[:, 1] < 16)
+    at = fake[:, :, 0][:, :, sc[ok, 0], sc[ok, 1]]
+    tv = obs[:, :, ok]
+    m = ~torch.isnan(tv)
+    want = torch.sqrt(torch.nn.functional.mse_loss(at[m], tv[m]))
+    assert torch.allclose(got, want, atol=1e-7)
+    assert float(station_rmse(fake, coords, torch.full((2, 3, 4), float("nan")), 2.0)) == 0.0
+
+
+def test_fit_checkpoint_format_and_resume(tmp_path):
+    tr = _trainer(str(tmp_path), epochs=3)
+    hist = tr.fit(_batches(4), _batches(2, seed=9))
+    assert hist["epoch"] == [0, 1, 2] and len(hist["total_loss"]) == 3
+    assert hist["total_loss"][2] < hist["total_loss"][0]
+    ck = torch.load(tmp_path / "best_model.pth", weights_only=False)
+    for key in ("epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "rmse", "history"):
+        assert key in ck                                            # trainer.py:410-417
+    assert set(ck["model_state_dict"]) == set(tr.model.state_dict())
+    # resume: a fresh trainer continues at the next epoch with the saved moments / scheduler / history
+    tr2 = _trainer(str(tmp_path), epochs=5)
+    tr2.load_checkpoint(str(tmp_path / "best_model.pth"))
+    assert tr2.start_epoch == ck["epoch"] + 1 and tr2.best_rmse == pytest.approx(ck["best_rmse"])
+    for k, v in ck["model_state_dict"].items():
+        assert torch.equal(tr2.model.state_dict()[k], v)
+    assert tr2.optimizer.state_dict()["state"][0]["step"] == ck["optimizer_state_dict"]["state"][0]["step"]
+    hist2 = tr2.fit(_batches(4), _batches(2, seed=9))
+    assert hist2["epoch"][-1] == 4 and len(hist2["epoch"]) == len(ck["history"]["epoch"]) + (5 - tr.best_epoch - 1)
+    # a checkpoint with only the reference's six keys loads too
+    ref_style = {k: ck[k] for k in ("epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict",
+                                    "rmse", "history")}
+    torch.save(ref_style, tmp_path / "ref_style.pth")
+    tr3 = _trainer(None, epochs=1)
+    tr3.load_checkpoint(str(tmp_path / "ref_style.pth"))
+    assert tr3.best_rmse == pytest.approx(ck["rmse"])
+
+
+def test_scheduler_and_early_stopping_drive_the_loop():
+    tr = _trainer(None, epochs=50, early_stopping_patience=2, scheduler_patience=0, scheduler_factor=0.5,
+                  learning_rate=0.0)                                # lr 0: the metric never improves
+    hist = tr.fit(_batches(2))
+    assert len(hist["epoch"]) == 3 and tr.early_stopping.early_stop   # best at epoch 0, then 2 stale epochs
+
+
+def test_nan_batch_is_skipped_like_the_reference():
+    tr = _trainer(None, epochs=1)
+    before = [p.detach().clone() for p in tr.model.parameters()]
+    assert tr.train_step(tuple(_batches(1, nan_at=0)[0])) is None and tr.skipped == 1   # trainer.py:306-308
+    assert all(torch.equal(a, b) for a, b in zip(before, tr.model.parameters()))
+    assert tr.train_step(tuple(_batches(1)[0])) is not None
+
+
+def _ddp_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                               # different init per rank: must be broadcast
+        tr = Trainer(TrainerConfig(scale_factor=2, epochs=2), device="cpu", model=_StubGen(), loss_module=_StubLoss())
+        # rank 1 sees a NaN batch at step 1: BOTH ranks must skip it (collective-safe), then keep training
+        data = _batches(3, seed=rank, B=1, nan_at=1 if rank == 1 else None)
+        tr.fit(data)
+        flat = torch.cat([p.detach().flatten() for p in tr.model.parameters()])
+        gathered = [torch.zeros_like(flat) for _ in range(world)]
+        torch.distributed.all_gather(gathered, flat)
+        if rank == 0:
+            ret["same"] = bool(torch.equal(gathered[0], gathered[1]))
+            ret["skipped"] = tr.skipped
+            ret["loss"] = tr.history["total_loss"]
+    finally:
+        torch.distributed.destroy_process_group()
+
+
+def test_trainer_world_size_2_gloo():
+    port = 29650 + os.getpid() % 200
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_ddp_worker, args=(2, port, ret), nprocs=2, join=True)
+        assert ret["same"], "ranks diverged"
+        assert ret["skipped"] == 2                                  # one skipped step in each of the 2 epochs
+        assert len(ret["loss"]) == 2
+
+
+def test_single_process_matches_two_rank_average():
+    """Gradient averaging over 2 ranks with batch 1 each == one process with the batch of 2 (mean losses)."""
+    torch.manual_seed(1)
+    tr = _trainer(None, epochs=1)
+    b0, b1 = _batches(1, seed=0, B=1)[0], _batches(1, seed=1, B=1)[0]
+    both = tuple(torch.cat([x, y]) if x.dim() > 2 else x for x, y in zip(b0, b1))
+    tr.train_step(both)
+    ref = [p.detach().clone() for p in tr.model.parameters()]
+    # emulate the two ranks by hand: mean of per-rank gradients
+    tr2 = _trainer(None, epochs=1)
+    grads = []
+    for b in (b0, b1):
+        loss, _ = tr2.loss_module(tr2.model(*b[:3]), b[0], b[3], b[4], 2.0)
+        grads.append(torch.autograd.grad(loss, list(tr2.model.parameters())))
+    tr2.reducer.zero_grad()
+    for p, g0, g1 in zip(tr2.model.parameters(), *grads):
+        p.grad.copy_((g0 + g1) / 2)
+    torch.nn.utils.clip_grad_norm_(tr2.trainable, 0.5)
+    tr2.optimizer.step()
+    for a, b in zip(ref, tr2.model.parameters()):
+        assert torch.allclose(a, b, atol=1e-7)
