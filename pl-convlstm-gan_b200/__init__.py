@@ -8,4 +8,4 @@ from .trainer import Trainer, TrainerConfig  # noqa: F401
 from .generator import Generator  # noqa: F401
 from .nn import ConvLSTMCell, ConvLSTMStack, EncoderForecaster  # noqa: F401
 from .rollout import NowcastGenerator, NowcastRunner  # noqa: F401
-from ._lib import PLC_MODE_BF16_TC, PLC_MODE_FP32  # noqa: F401
+from ._lib import PLC_MODE_BF16_TC, PLC_MODE_FP32, invalidate_packed_weights  # noqa: F401

@@ -101,3 +101,28 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().plc_last_error()
         raise RuntimeError(f"{what} failed (status {status}): {msg.decode() if msg else '?'}")
+
+
+# ---- packed-weight cache generation --------------------------------------------------------------------------
+# Packed weight images are cached per module, keyed on the parameters' autograd version counters.  Fused optimizers
+# (torch.optim.Adam(fused=True), ...) and writes through `.data` update parameters WITHOUT bumping that counter, so the
+# key also carries a process-wide generation number that every optimizer step advances (global post-step hook below).
+# Anything else that edits weights behind autograd's back must call `invalidate_packed_weights()`.
+_generation = 0
+
+
+def weight_generation() -> int:
+    return _generation
+
+
+def invalidate_packed_weights(*_args, **_kwargs) -> None:
+    global _generation
+    _generation += 1
+
+
+def _install_optimizer_hook() -> None:
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+    register_optimizer_step_post_hook(invalidate_packed_weights)
+
+
+_install_optimizer_hook()

@@ -301,7 +301,8 @@ class ConvParams:
 
     def packed(self, need_dgrad: bool):
         w, b = self.conv.weight, self.conv.bias
-        key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version), str(w.device))
+        key = (_lib.weight_generation(), w.data_ptr(), w._version,
+               None if b is None else (b.data_ptr(), b._version), str(w.device))
         pc = self._cache
         if pc is not None and pc[0] == key and (pc[3] is not None or not need_dgrad):
             return pc[1], pc[2], pc[3]

@@ -19,6 +19,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 import torch.nn as nn
 
+from . import _lib
 from . import functional as F
 from ._lib import PLC_MODE_BF16_TC, PLC_MODE_FP32
 
@@ -94,7 +95,8 @@ class ConvLSTMCell(nn.Module):
     # -- packed-weight cache, invalidated when the parameters change (optimizer step, load_state_dict, .to())
     def _packed(self, need_dgrad: bool) -> F.PackedWeights:
         w, b = self.conv.weight, self.conv.bias
-        key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version), self.mode, str(w.device))
+        key = (_lib.weight_generation(), w.data_ptr(), w._version,
+               None if b is None else (b.data_ptr(), b._version), self.mode, str(w.device))
         pc = self._pack_cache
         if pc is not None and pc[0] == key and (pc[1].dgrad is not None or not need_dgrad):
             return pc[1]

@@ -224,8 +224,13 @@ def gen_train(name, seed, steps, B, T, H, W, hd, scale, lu_ch, n_st):
         sf = fake.shape[-2] / rain.shape[-2]
         loss, parts = crit(fake, rain, coords, obs, sf)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(gen.parameters(), max_norm=0.5)       # trainer.py:311-314
+        if i == 0:
+            out.update({"g0." + k: np32(p.grad) for k, p in gen.named_parameters()})      # raw, before the clip
+        norm = torch.nn.utils.clip_grad_norm_(gen.parameters(), max_norm=0.5)  # trainer.py:311-314
+        out[f"gradnorm{i}"] = np32(norm)
         opt.step()
+        if i == 0:
+            out.update({"sdA." + k: np32(v) for k, v in gen.state_dict().items()})        # after ONE Adam step
         with torch.no_grad():                                                # trainer.py:225-268
             sc = ((coords.float() + 0.5) * sf - 0.5).long()
             at = fake[:, :, 0][:, :, sc[:, 0], sc[:, 1]]

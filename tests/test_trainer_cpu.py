@@ -180,3 +180,18 @@ def test_single_process_matches_two_rank_average():
     tr2.optimizer.step()
     for a, b in zip(ref, tr2.model.parameters()):
         assert torch.allclose(a, b, atol=1e-7)
+
+
+def test_fused_optimizer_step_invalidates_packed_weight_caches():
+    """torch's fused optimizers update parameters without bumping their autograd version counter, which the
+    packed-weight caches are keyed on; the global post-step hook must advance the cache generation instead."""
+    from plconv import _lib
+    p = torch.nn.Parameter(torch.randn(4))
+    opt = torch.optim.Adam([p], lr=1e-3, fused=True)
+    p.grad = torch.randn(4)
+    g0 = _lib.weight_generation()
+    opt.step()
+    assert _lib.weight_generation() > g0
+    g1 = _lib.weight_generation()
+    plconv.invalidate_packed_weights()
+    assert _lib.weight_generation() == g1 + 1
