@@ -97,40 +97,47 @@ def station_rmse(fake_hr: torch.Tensor, s_coords: torch.Tensor, s_values: torch.
 
 
 class DevicePrefetcher:
-    """Pinned host buffers -> device on a side stream, one batch ahead of the compute stream."""
+    """Pinned host batches -> two fixed sets of device buffers, filled on a side stream one batch ahead of the compute
+    stream.  The buffers are allocated once (per shape), so a step never touches the caching allocator across streams;
+    a slot is refilled only after the compute stream has finished the step that read it."""
 
     def __init__(self, loader: Iterable, device: torch.device):
         self.loader, self.device = loader, device
         self.stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self.slots = [None, None]
+        self.done = [None, None]
 
-    def _stage(self, batch):
+    def _stage(self, batch, s: int):
         if self.stream is None:
-            return tuple(t.to(self.device) for t in batch), None
+            return tuple(t.to(self.device) for t in batch), None, s
+        bufs = self.slots[s]
+        if bufs is None or any(b.shape != t.shape or b.dtype != t.dtype for b, t in zip(bufs, batch)):
+            bufs = self.slots[s] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in batch)
         with torch.cuda.stream(self.stream):
-            out = tuple((t if t.is_cuda or t.is_pinned() else t.pin_memory()).to(self.device, non_blocking=True)
-                        for t in batch)
+            if self.done[s] is not None:
+                self.stream.wait_event(self.done[s])
+            else:
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))   # the allocation above
+            for b, t in zip(bufs, batch):
+                b.copy_(t if t.is_cuda or t.is_pinned() else t.pin_memory(), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return out, ev
+        return bufs, ev, s
 
     def __iter__(self):
         it = iter(self.loader)
-        nxt = None
-        try:
-            nxt = self._stage(next(it))
-        except StopIteration:
-            return
-        while nxt is not None:
-            cur, ev = nxt
-            try:
-                nxt = self._stage(next(it))
-            except StopIteration:
-                nxt = None
+        first = next(it, None)
+        staged = self._stage(first, 0) if first is not None else None
+        while staged is not None:
+            cur, ev, s = staged
+            nxt = next(it, None)
+            staged = self._stage(nxt, 1 - s) if nxt is not None else None
             if ev is not None:
                 torch.cuda.current_stream(self.device).wait_event(ev)
-                for t in cur:
-                    t.record_stream(torch.cuda.current_stream(self.device))
             yield cur
+            if ev is not None:
+                self.done[s] = torch.cuda.Event()
+                self.done[s].record(torch.cuda.current_stream(self.device))
 
 
 class Trainer:
