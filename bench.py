@@ -33,6 +33,9 @@ sys.path.insert(0, ROOT)
 CFG = dict(B=32, H=128, W=128, hidden=[64, 64], k=3, t_in=10, t_out=10, in_channels=1)
 WORKLOAD = ("cfg2: ConvLSTM encoder-forecaster generator inference, 128x128, hidden [64,64], k3, T=10->10, "
             "batch 32 per GPU")
+RADAR_CFG = dict(B=16, H=256, W=256, hidden=[128, 128, 128], k=3, t_in=20, t_out=20, in_channels=1)
+RADAR_WORKLOAD = ("cfg4 (BASELINE configs[3]): radar-scale nowcasting inference, 256x256, 3-layer ConvLSTM hidden "
+                  "[128,128,128], k3, T=20->20, batch 16 per GPU")
 FALLBACK_PEAK_TFLOPS = 1590.0   # B200_PROFILING.md fallback (burst)
 
 
@@ -42,9 +45,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "radar"],
                     help="infer = BASELINE configs[1] (default, the headline line); train = configs[2]-style recurrence "
-                         "training step (global batch 64 sharded over the ranks, strong scaling)")
+                         "training step (global batch 64 sharded over the ranks, strong scaling); radar = configs[3] "
+                         "(256x256, 3 layers of hidden 128, T=20->20, batch 16 per GPU), same line format as infer")
     ap.add_argument("--cpu-sample", type=int, default=1, help="sequences per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -263,7 +267,10 @@ def run_train(args):
 
 
 def main():
+    global CFG, WORKLOAD
     args = parse()
+    if args.workload == "radar":
+        CFG, WORKLOAD = RADAR_CFG, RADAR_WORKLOAD
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -393,16 +400,17 @@ def main():
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": elapsed_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world} (batch shards, no collective)",
-                       "l2": "inputs larger than L2 (671 MB of bf16 features + 134 MB state per step vs 126 MB L2)",
+                       "l2": f"inputs larger than L2 ({B * H * W * (2 * 2 + 4) * CFG['hidden'][0] / 1e6:.0f} MB of bf16 "
+                             "x/h + fp32 c operands per cell step vs 126 MB L2)",
                        "cell_steps_per_sequence": runner.cell_launches_per_run},
             "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": frames_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": K * runner.launches_per_run,
-            "roofline": {"bound": "tensor", "kernel": "conv_igemm_tc_kernel<256,EPI_LSTM_FWD> (fused cell step 64->64)",
+            "roofline": {"bound": "tensor", "kernel": f"conv_igemm_tc_kernel<256,EPI_LSTM_FWD> (fused cell step {CFG['hidden'][0]}->{CFG['hidden'][0]})",
                          "achieved": achieved_tf, "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved_tf / peak_sus,
                          "frac_of_burst": achieved_tf / peak_burst, "peak_burst": peak_burst, "peak_source": peak_src,
                          "flops_per_launch": flops_full, "avg_launch_us": avg_ms * 1e3, "launches_timed": len(full),
-                         "traffic": committed_traffic(),
+                         "traffic": committed_traffic() if args.workload == "infer" else None,
                          "cell_kernels_share_of_step": cell_ms_total / elapsed_ms},
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
