@@ -148,6 +148,9 @@ int plc_debug_set_prof(void* device_buf_u64);
 /* Force the tensor-core kernels onto cta_group 1 or 2 (0 = automatic choice by problem size); used by the parity
  * tests to cover the CTA-pair path on small shapes.                                                          */
 int plc_debug_set_cta_group(int cta_group);
+/* Haloed-patch pipeline of the tensor-core conv kernels (one activation patch per tile serves all k*k taps as shifted
+ * UMMA views): -1 = automatic (default), 0 = never, 1 = whenever the kernel supports it.  Parity tests run both.   */
+int plc_debug_set_patch(int mode);
 
 /* ---- layout helpers (HBM-bound elementwise kernels) ---------------------------------------
  * The reference keeps NCHW fp32 tensors (generator.py:156-160).  These convert between that and

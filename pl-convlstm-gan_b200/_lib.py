@@ -59,6 +59,7 @@ SIGNATURES = {
     "plc_conv_bwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plc_debug_set_prof": (_int, [_vp]),
     "plc_debug_set_cta_group": (_int, [_int]),
+    "plc_debug_set_patch": (_int, [_int]),
     "plc_nchw_f32_to_nhwc_bf16": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),
     "plc_nhwc_bf16_to_nchw_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
     "plc_frontend_fwd": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _int, _int, _int, _vp, _vp]),

@@ -42,6 +42,13 @@ struct ConvTcParams {
   int num_boxes;             // ksize^2 * (chunks0 + chunks1) boxes of [kc ch x 128 px]
   int num_kb;                // K stages of 64 elements = ceil(num_boxes / (64/kc)); tail boxes repeat the last one
                              // against zero weights
+  // patch mode (kc == 64, tile = 16 rows x 8 pixels): ONE haloed [(th+2p) x (tw+2p) px][64 ch] box per (source,
+  // 64-channel chunk) serves all ksize^2 taps as shifted UMMA views (profiles/r01_umma_shift_probe.md), instead of
+  // ksize^2 separately loaded [128 px][64 ch] tiles: the A feed per K stage drops from 16 KB to 23 KB / 9.
+  int patch;                 // 0 = one A tile per K stage (default pipeline)
+  int patch_slots;           // resident patches (2 or 3)
+  int patch_slot_bytes;      // (th+2p)*(tw+2p)*128 rounded up to 1024
+  int b_stages;              // weight-tile ring depth in patch mode
   // LSTM epilogues
   int Ch;                    // hidden channels
   int Cin;                   // EPI_PLAIN: first Cin output columns go to out0, the rest to out1
@@ -156,11 +163,16 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   uint8_t* stage_out = smem + kStages * Cfg::kStageBytes;                 // TMA-store staging (1024-aligned)
   float* bias_s = reinterpret_cast<float*>(stage_out + Cfg::kStoreBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + Cfg::kStoreBytes + 4096);
-  uint64_t* full_bar = bars;                       // [kStages]
-  uint64_t* empty_bar = bars + kStages;            // [kStages]
-  uint64_t* tmem_full = bars + 2 * kStages;        // [2]
-  uint64_t* tmem_empty = bars + 2 * kStages + 2;   // [2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* tmem_full = bars;                      // [2]
+  uint64_t* tmem_empty = bars + 2;                 // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* full_bar = bars + 6;                   // [kStages]
+  uint64_t* empty_bar = bars + 6 + kStages;        // [kStages]
+  // patch mode carves the same regions differently: <= 3 patch slots + <= 8 weight stages (<= 28 barriers of 32)
+  uint64_t* patch_full = bars + 6;                 // [3]
+  uint64_t* patch_empty = bars + 9;                // [3]
+  uint64_t* bfull_bar = bars + 12;                 // [8]
+  uint64_t* bempty_bar = bars + 20;                // [8]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -174,9 +186,13 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     tma_prefetch_desc(&tmap_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    if (p.patch) {
+      for (int s = 0; s < 22; ++s) mbar_init(&patch_full[s], 1);   // patch_full/empty[3] + bfull/bempty[8], contiguous
+    } else {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -257,7 +273,75 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         }
       }
     };
-    if (p.kc == 64) produce(IntC<1>{});
+    // patch mode: per tile and (source, 64-channel chunk) "unit" ONE haloed activation patch, then ksize^2 weight tiles
+    auto produce_patch = [&]() {
+      const uint32_t pf_base = smem_u32(patch_full), bf_base = smem_u32(bfull_bar);
+      const uint32_t wb_base = a_base + p.patch_slots * p.patch_slot_bytes;      // weight ring behind the patch slots
+      const int units = p.chunks0 + p.chunks1, taps = p.ksize * p.ksize;
+      const uint32_t patch_tx = (p.tw + 2 * p.pad) * (p.th + 2 * p.pad) * (kBlockK * 2);
+      // the patch stream runs ONE unit ahead of the weight stream (also across tile boundaries)
+      int tA = tile0, uA = 0, nA = 0, bA = 0, yA = 0, xA = 0;
+      uint32_t ps = 0, pphase = 0;
+      if (tA < num_tiles) decode_tile<kCta>(p, tA, rank, nA, bA, yA, xA);
+      auto issue_patch = [&]() {
+        if (tA >= num_tiles) return;
+        mbar_wait(&patch_empty[ps], pphase ^ 1);
+        if (elect_one()) {
+          const int src = uA >= p.chunks0;
+          const int ck = src ? uA - p.chunks0 : uA;
+          const uint32_t dst = a_base + ps * p.patch_slot_bytes;
+          if constexpr (kCta == 1) {
+            mbar_arrive_expect_tx(&patch_full[ps], patch_tx);
+            tma_load_4d_s(dst, src ? &tmap_a1 : &tmap_a0, pf_base + ps * 8, ck * kBlockK, xA - p.pad, yA - p.pad, bA);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(&patch_full[ps], 2 * patch_tx);
+            tma_load_4d_cg2(dst, src ? &tmap_a1 : &tmap_a0, mapa_u32(pf_base + ps * 8, 0), ck * kBlockK, xA - p.pad,
+                            yA - p.pad, bA);
+          }
+        }
+        __syncwarp();
+        if (++ps == static_cast<uint32_t>(p.patch_slots)) { ps = 0; pphase ^= 1; }
+        if (++uA == units) {
+          uA = 0;
+          tA += tile_step;
+          if (tA < num_tiles) decode_tile<kCta>(p, tA, rank, nA, bA, yA, xA);
+        }
+      };
+      issue_patch();
+      // With 3 slots the next unit's patch is requested before this unit's weights.  With only 2 slots its slot is
+      // still being read by the previous unit's MMAs, which are certainly done once the weight ring has wrapped
+      // (weight tile t of this unit can only be requested after tile t - b_stages was consumed).
+      const int ahead_tap = p.patch_slots >= 3 ? 0 : (p.b_stages < taps - 1 ? p.b_stages : taps - 1);
+      uint32_t bs = 0, bphase = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        int n_tile, b, y0, x0;
+        decode_tile<kCta>(p, tile, rank, n_tile, b, y0, x0);
+        const int n_row = n_tile * N_TILE + rank * (N_TILE / kCta);
+        for (int u = 0; u < units; ++u) {
+          const int src = u >= p.chunks0;
+          const int cks = src ? p.chunks1 : p.chunks0;
+          int kb = (src ? taps * p.chunks0 + (u - p.chunks0) : u);     // packed K order: source, tap, chunk
+          for (int t = 0; t < taps; ++t, kb += cks) {
+            if (t == ahead_tap) issue_patch();
+            mbar_wait(&bempty_bar[bs], bphase ^ 1);
+            if (elect_one()) {
+              const uint32_t b_dst = wb_base + bs * Cfg::kBBytes;
+              if constexpr (kCta == 1) {
+                mbar_arrive_expect_tx(&bfull_bar[bs], Cfg::kBBytes);
+                tma_load_2d_s(b_dst, &tmap_b, bf_base + bs * 8, kb * kBlockK, n_row);
+              } else {
+                if (rank == 0) mbar_arrive_expect_tx(&bfull_bar[bs], 2 * Cfg::kBBytes);
+                tma_load_2d_cg2(b_dst, &tmap_b, mapa_u32(bf_base + bs * 8, 0), kb * kBlockK, n_row);
+              }
+            }
+            __syncwarp();
+            if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bphase ^= 1; }
+          }
+        }
+      }
+    };
+    if (p.patch) produce_patch();
+    else if (p.kc == 64) produce(IntC<1>{});
     else if (p.kc == 32) produce(IntC<2>{});
     else produce(IntC<4>{});
   } else if (warp == 1 && rank == 0) {
@@ -271,7 +355,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
 #pragma unroll
     for (int k = 0; k < kBlockK / 16; ++k)
       aoff[k] = (((16 * k) / p.kc) * (kTileM * p.kc * 2) + ((16 * k) % p.kc) * 2) >> 4;
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, bstage = 0, bphase = 0;
     int it = 0;
     long long t_empty = 0, t_full = 0, t0 = clock64();
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
@@ -282,6 +366,49 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       tc_fence_after();
       if ((kProfEnabled && p.prof)) t_empty += clock64() - ta;
       const uint32_t d_tmem = tmem_base + as * N_TILE;
+      if (p.patch) {
+        // shifted views: tap (ky, kx) of the tile = the patch read from pixel row ky, pixel kx on (start address
+        // + (ky * (tw+2p) + kx) * 128 B), 8-pixel groups (tile rows) one patch row = (tw+2p) * 128 B apart
+        const int units = p.chunks0 + p.chunks1, pw = p.tw + 2 * p.pad;
+        const uint64_t pdesc0 = make_smem_desc(smem_u32(smem_a), 0, pw * (kBlockK * 2));
+        const uint64_t wdesc0 = make_smem_desc(smem_u32(smem_a) + p.patch_slots * p.patch_slot_bytes, 0, 1024);
+        for (int u = 0; u < units; ++u) {
+          long long tb = (kProfEnabled && p.prof) ? clock64() : 0;
+          mbar_wait(&patch_full[stage], phase);
+          tc_fence_after();
+          if ((kProfEnabled && p.prof)) t_full += clock64() - tb;
+          const uint64_t pdesc = pdesc0 + stage * (p.patch_slot_bytes >> 4);
+          for (int ky = 0; ky < p.ksize; ++ky) {
+            for (int kx = 0; kx < p.ksize; ++kx) {
+              tb = (kProfEnabled && p.prof) ? clock64() : 0;
+              mbar_wait(&bfull_bar[bstage], bphase);
+              tc_fence_after();
+              if ((kProfEnabled && p.prof)) t_full += clock64() - tb;
+              const bool last_tap = (ky == p.ksize - 1) && (kx == p.ksize - 1);
+              if (elect_one()) {
+                const uint64_t adesc = pdesc + ((ky * pw + kx) * (kBlockK * 2) >> 4);
+                const uint64_t bdesc = wdesc0 + bstage * (Cfg::kBBytes >> 4);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_bf16<kCta>(d_tmem, adesc + 2u * k, bdesc + 2 * k, idesc, (u | ky | kx | k) != 0);
+                if constexpr (kCta == 1) {
+                  umma_commit<1>(&bempty_bar[bstage]);
+                  if (last_tap) umma_commit<1>(&patch_empty[stage]);
+                  if (last_tap && u == units - 1) umma_commit<1>(&tmem_full[as]);
+                } else {
+                  umma_commit_mc2(&bempty_bar[bstage], 0b11);
+                  if (last_tap) umma_commit_mc2(&patch_empty[stage], 0b11);
+                  if (last_tap && u == units - 1) umma_commit_mc2(&tmem_full[as], 0b11);
+                }
+              }
+              __syncwarp();
+              if (++bstage == static_cast<uint32_t>(p.b_stages)) { bstage = 0; bphase ^= 1; }
+            }
+          }
+          if (++stage == static_cast<uint32_t>(p.patch_slots)) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       for (int kb = 0; kb < p.num_kb; ++kb) {
         long long tb = (kProfEnabled && p.prof) ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);

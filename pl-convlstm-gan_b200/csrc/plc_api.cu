@@ -351,6 +351,13 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
     p.div_tiles_x = small ? magic(p.tiles_x) : 0;
     p.div_tiles_y = small ? magic(p.tiles_y) : 0;
   }
+  if (p.patch) {   // carve the pipeline region into patch slots + weight stages
+    const int region = Cfg::kStages * Cfg::kStageBytes;
+    p.patch_slots = (region - 3 * p.patch_slot_bytes) / Cfg::kBBytes >= 4 ? 3 : 2;
+    int nb = (region - p.patch_slots * p.patch_slot_bytes) / Cfg::kBBytes;
+    if (nb < 2) return fail(PLC_ERR_UNSUPPORTED, "patch mode does not fit (N_TILE=%d cta=%d)", NT, CTA);
+    p.b_stages = nb > 8 ? 8 : nb;
+  }
   PLC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int tiles = CTA == 2 ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_tiles;
   const int slots = sm_count() / CTA;
@@ -405,6 +412,37 @@ void set_kgeom(plc::ConvTcParams* p, const KGeom& kg) {
   p->kc = kg.kc; p->chunks0 = kg.chunks0; p->chunks1 = kg.chunks1; p->num_boxes = kg.num_boxes; p->num_kb = kg.num_kb;
 }
 
+// Haloed-patch pipeline (conv_igemm_tc.cuh, "patch mode"): applies when every K stage is one 64-channel box (kc == 64)
+// and the kernel is 3x3 or 5x5; it needs 16 x 8-pixel tiles, so it is skipped when that tiling wastes > 5 % more
+// pixels than the default one.  PLC_PATCH=0|1 / plc_debug_set_patch override (A/B runs, parity tests of both paths).
+int g_patch_override = -1;   // plc_debug_set_patch
+void maybe_patch(TcGeom* g, plc::ConvTcParams* p) {
+  static int env_mode = -2;
+  if (env_mode == -2) {
+    const char* e = getenv("PLC_PATCH");
+    env_mode = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
+  }
+  const int mode = g_patch_override >= 0 ? g_patch_override : env_mode;
+  p->patch = 0;
+  if (mode == 0 || p->kc != 64 || (p->ksize != 3 && p->ksize != 5)) return;
+  const long area_def = static_cast<long>(g->tiles_x) * g->tw * g->tiles_y * g->th;
+  const long area_patch = static_cast<long>(cdiv(p->W, 8)) * 8 * cdiv(p->H, 16) * 16;
+  if (mode != 1 && area_patch * 100 > area_def * 105) return;
+  g->tw = 8; g->th = 16; g->tw_log2 = 3;
+  g->tiles_x = cdiv(p->W, 8); g->tiles_y = cdiv(p->H, 16);
+  p->tw = 8; p->th = 16; p->tw_log2 = 3;
+  p->tiles_x = g->tiles_x; p->tiles_y = g->tiles_y;
+  p->num_m_tiles = p->B * g->tiles_x * g->tiles_y;
+  p->num_tiles = p->num_m_tiles * p->num_n_tiles;
+  p->patch = 1;
+  p->patch_slot_bytes = ((16 + 2 * p->pad) * (8 + 2 * p->pad) * 128 + 1023) / 1024 * 1024;
+}
+// activation tensor map of an A source: the plain [kc ch, tw, th] tile box, or the haloed patch box in patch mode
+int make_tmap_src(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, const plc::ConvTcParams& p) {
+  const int halo = p.patch ? 2 * p.pad : 0;
+  return make_tmap_act(tm, ptr, B, H, W, C, p.tw + halo, p.th + halo, 2, p.kc, swizzle_for_kc(p.kc));
+}
+
 int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p) {
   g->ch_tile = pick_ch_tile(d->Ch);
   g->n_tile = 4 * g->ch_tile;
@@ -413,6 +451,7 @@ int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p) {
   p->num_n_tiles = d->Ch / g->ch_tile;
   p->num_tiles = p->num_m_tiles * p->num_n_tiles;
   set_kgeom(p, kgeom(d->Cin, d->Ch, d->k));
+  maybe_patch(g, p);
   return PLC_OK;
 }
 
@@ -593,9 +632,9 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   p.h_out = static_cast<__nv_bfloat16*>(h_out);
   p.gates_out = static_cast<__nv_bfloat16*>(gates_out);
   CUtensorMap ta0, ta1, tb;
-  if ((rc = make_tmap_act(&ta1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, p.kc, swizzle_for_kc(p.kc)))) return rc;
+  if ((rc = make_tmap_src(&ta1, h_prev, d->B, d->H, d->W, d->Ch, p))) return rc;
   if (d->Cin > 0) {
-    if ((rc = make_tmap_act(&ta0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th, 2, p.kc, swizzle_for_kc(p.kc)))) return rc;
+    if ((rc = make_tmap_src(&ta0, x, d->B, d->H, d->W, d->Cin, p))) return rc;
   } else {
     ta0 = ta1;
   }
@@ -702,9 +741,9 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   p.dc_prev = dc_prev;
   p.dz = static_cast<__nv_bfloat16*>(workspace);
   CUtensorMap ta0, ta1, tb;
-  if ((rc = make_tmap_act(&ta1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, p.kc, swizzle_for_kc(p.kc)))) return rc;
+  if ((rc = make_tmap_src(&ta1, h_prev, d->B, d->H, d->W, d->Ch, p))) return rc;
   if (d->Cin > 0) {
-    if ((rc = make_tmap_act(&ta0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th, 2, p.kc, swizzle_for_kc(p.kc)))) return rc;
+    if ((rc = make_tmap_src(&ta0, x, d->B, d->H, d->W, d->Cin, p))) return rc;
   } else {
     ta0 = ta1;
   }
@@ -722,20 +761,23 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   // 2) dgrad: conv of dZ (4Ch channels) with the flipped/transposed image -> dx, dh_prev
   if (dx || dh_prev) {
     plc::ConvTcParams q;
-    fill_geom(d, g, &q);
+    TcGeom gq;
+    pick_spatial_tile(d->H, d->W, &gq);
+    fill_geom(d, gq, &q);
     const int n_total = d->Cin + d->Ch;
     const int nt = pick_plain_n_tile(n_total);
     q.num_n_tiles = cdiv(n_total, nt);
     q.num_tiles = q.num_m_tiles * q.num_n_tiles;
     set_kgeom(&q, kgeom(4 * d->Ch, 0, d->k));
+    maybe_patch(&gq, &q);
     q.n_total = n_total;
     q.out0 = static_cast<__nv_bfloat16*>(dx);
     q.out1 = static_cast<__nv_bfloat16*>(dh_prev);
+    const int ctaq = pick_cta_group(q.num_m_tiles);
     CUtensorMap tz, tbd;
-    if ((rc = make_tmap_act(&tz, workspace, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th, 2, q.kc, swizzle_for_kc(q.kc))))
-      return rc;
-    if ((rc = make_tmap_mat(&tbd, w_packed_dgrad, n_total, (long)q.num_kb * 64, 64, nt / cta))) return rc;
-    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tbd, tz, tz, st))) return rc;
+    if ((rc = make_tmap_src(&tz, workspace, d->B, d->H, d->W, 4 * d->Ch, q))) return rc;
+    if ((rc = make_tmap_mat(&tbd, w_packed_dgrad, n_total, (long)q.num_kb * 64, 64, nt / ctaq))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, ctaq, q, tz, tz, tbd, tz, tz, st))) return rc;
   }
 
   // 3) wgrad + bias grad
@@ -829,6 +871,7 @@ int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, 
   q.num_n_tiles = cdiv(d->Cout, nt);
   q.num_tiles = q.num_m_tiles * q.num_n_tiles;
   set_kgeom(&q, kgeom(d->Cin, 0, d->k));
+  maybe_patch(&g, &q);
   q.n_total = d->Cout;
   q.Cin = d->Cout;                     // no column split: everything goes to out0
   q.out0 = static_cast<__nv_bfloat16*>(out);
@@ -837,7 +880,7 @@ int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, 
   q.plain_shuffle = d->pixel_shuffle;
   const int cta = pick_cta_group(q.num_m_tiles);
   CUtensorMap ta, tb;
-  if ((rc = make_tmap_act(&ta, x, d->B, d->H, d->W, d->Cin, g.tw, g.th, 2, q.kc, swizzle_for_kc(q.kc)))) return rc;
+  if ((rc = make_tmap_src(&ta, x, d->B, d->H, d->W, d->Cin, q))) return rc;
   if ((rc = make_tmap_mat(&tb, w_packed_fwd, d->Cout, (long)q.num_kb * 64, 64, nt / cta))) return rc;
   return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, ta, ta, static_cast<cudaStream_t>(stream));
 }
@@ -883,12 +926,13 @@ int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void
     q.num_n_tiles = cdiv(d->Cin, nt);
     q.num_tiles = q.num_m_tiles * q.num_n_tiles;
     set_kgeom(&q, kgeom(d->Cout, 0, d->k));
+    maybe_patch(&g, &q);
     q.n_total = d->Cin;
     q.Cin = d->Cin;
     q.out0 = static_cast<__nv_bfloat16*>(dx);
     const int cta = pick_cta_group(q.num_m_tiles);
     CUtensorMap tz, tb;
-    if ((rc = make_tmap_act(&tz, dz, d->B, d->H, d->W, d->Cout, g.tw, g.th, 2, q.kc, swizzle_for_kc(q.kc)))) return rc;
+    if ((rc = make_tmap_src(&tz, dz, d->B, d->H, d->W, d->Cout, q))) return rc;
     if ((rc = make_tmap_mat(&tb, w_packed_dgrad, d->Cin, (long)q.num_kb * 64, 64, nt / cta))) return rc;
     if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tb, tz, tz, st))) return rc;
   }
@@ -896,6 +940,12 @@ int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void
     WgradShape w{d->B, d->H, d->W, d->k, d->Cin, 0, d->Cout};
     if ((rc = launch_wgrad_tc_shape(&w, x, nullptr, dz, dW_acc, d->has_bias ? db_acc : nullptr, st))) return rc;
   }
+  return PLC_OK;
+}
+
+int plc_debug_set_patch(int mode) {
+  if (mode < -1 || mode > 1) return fail(PLC_ERR_BAD_DESC, "plc_debug_set_patch: mode must be -1 (auto), 0 or 1");
+  g_patch_override = mode;
   return PLC_OK;
 }
 

@@ -272,3 +272,58 @@ def test_pair_path_forward_and_backward_vs_oracle(shape, force_pair, cuda_device
         bad = [report(n_, got, ref[n_]) for n_, got in (("dx", dx), ("dh_prev", dhp), ("dc_prev", dcp), ("dW", dW),
                                                          ("db", db)) if rel_err(got, ref[n_]) >= 2e-2]
         assert not bad, " | ".join(bad)
+
+
+# ---- haloed-patch pipeline (one activation patch per tile serves all k*k taps as shifted UMMA views) ------------
+# Forced ON (plc_debug_set_patch(1)) so that ragged / tiny images also take it; crossed with both cta_group paths.
+PATCH_SHAPES = [
+    (2, 64, 64, 16, 8, 3),       # exactly one 16x8 tile per image
+    (2, 64, 64, 20, 13, 3),      # ragged in both directions
+    (1, 128, 64, 33, 17, 3),     # 3 units (x: 2 chunks, h: 1)
+    (3, 0, 64, 8, 8, 3),         # no input tensor, image smaller than a tile
+    (1, 64, 64, 19, 21, 5),      # k = 5 (patch 20 x 12)
+    (1, 64, 128, 16, 16, 3),     # 2 N tiles re-read the same patches
+    (2, 72, 80, 18, 9, 3),       # channel tails inside the last 64-channel chunk
+]
+
+
+@pytest.fixture(params=[1, 2], ids=["cta1", "cta2"])
+def force_patch(request):
+    import plconv
+    lib = plconv._lib.load()
+    lib.plc_debug_set_patch(1)
+    lib.plc_debug_set_cta_group(request.param)
+    yield
+    lib.plc_debug_set_patch(-1)
+    lib.plc_debug_set_cta_group(0)
+
+
+@pytest.mark.parametrize("shape", PATCH_SHAPES, ids=lambda s: "B%d_Cin%d_Ch%d_%dx%d_k%d" % s)
+def test_patch_pipeline_forward_and_backward_vs_oracle(shape, force_patch, cuda_device):
+    test_pair_path_forward_and_backward_vs_oracle.__wrapped__(shape, None, cuda_device) \
+        if hasattr(test_pair_path_forward_and_backward_vs_oracle, "__wrapped__") else \
+        test_pair_path_forward_and_backward_vs_oracle(shape, None, cuda_device)
+
+
+def test_patch_pipeline_matches_default_pipeline_closely(cuda_device):
+    """Same inputs through both pipelines: identical products, different fp32 accumulation order only."""
+    plconv, F = _plconv()
+    lib = plconv._lib.load()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    B, H, W, C = 4, 48, 40, 64
+    w = torch.randn(4 * C, 2 * C, 3, 3, generator=g) * 0.05
+    pw = F.pack_weights(w.to(dev), None, C, C, 3, plconv.PLC_MODE_BF16_TC)
+    x = torch.randn(B, H, W, C, generator=g).to(dev).to(torch.bfloat16)
+    h = torch.randn(B, H, W, C, generator=g).to(dev).to(torch.bfloat16)
+    c = torch.randn(B, H, W, C, generator=g).to(dev)
+    outs = []
+    for mode in (0, 1):
+        lib.plc_debug_set_patch(mode)
+        try:
+            h2, c2 = F.cell_forward(x, h, c, pw)
+            outs.append((h2.float().clone(), c2.clone()))
+        finally:
+            lib.plc_debug_set_patch(-1)
+    assert float((outs[0][1] - outs[1][1]).abs().max()) <= 2e-5
+    assert float((outs[0][0] - outs[1][0]).abs().max()) <= 2 ** -7      # at most one bf16 ulp near |h| <= 1
