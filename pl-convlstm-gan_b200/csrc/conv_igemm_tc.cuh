@@ -68,6 +68,8 @@ struct ConvTcParams {
   const float* plain_bias;   // PLAIN: [n_total] fp32 in packed column order, or nullptr
   int plain_relu;            // PLAIN: apply max(x, 0)
   int plain_shuffle;         // PLAIN: PixelShuffle(2) store: column n' = sub*(n_total/4) + c -> out0[b, 2y+sub/2, 2x+sub%2, c]
+  int plain_tma;             // PLAIN: outputs leave through smem staging + TMA tensor stores (tmap_o0 / tmap_o1 valid;
+                             // needs no shuffle and 64-channel-aligned out0 / out1); 0 = per-thread 16-byte stores
   unsigned long long* prof;  // debug: per-CTA cycle counters [gridDim][16] or nullptr (plc_debug_set_prof)
 };
 
@@ -92,7 +94,8 @@ struct ConvTcCfg {
   static constexpr bool kTmaStore = tma_store_epilogue<N_TILE, EPI>();
   // staging (forward): c' fp32 as two [128 px][32 ch] boxes (2 x 16 KB) + h' bf16 as one [128 px][64 ch] box (16 KB)
   // staging (bwd gates, per 32-channel half): dZ bf16 as four [128 px][32 ch] boxes (4 x 8 KB) + dc_prev fp32 (16 KB)
-  static constexpr int kStoreBytes = kTmaStore ? 3 * 16384 : 0;
+  // staging (plain): one [128 px][64 ch] bf16 box (16 KB) per 64 output columns
+  static constexpr int kStoreBytes = kTmaStore ? 3 * 16384 : (EPI == 2 /*EPI_PLAIN*/ ? (N_TILE / 64) * 16384 : 0);
   // cta_group::2: the CTA pair shares one 256 x N_TILE accumulator tile; each CTA stages its own 128 pixels of A
   // and HALF of the B tile (N_TILE/2 packed-weight rows), so the per-SM operand feed drops from 48 to 32 KB / K-block.
   static constexpr int kBBytes = (N_TILE / kCta) * kBlockK * 2;
@@ -890,6 +893,58 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
             }
           }
         }
+      } else if (p.plain_tma) {
+        // EPI_PLAIN through shared memory: the tile leaves as N_TILE/64 bulk tensor stores issued by one thread
+        // (per-thread NHWC stores put 32 scattered 16-byte pieces into every store instruction)
+        const bool issuer = (warp == 4) && (lane == 0);
+        if (issuer) tma_store_wait_read();         // previous tile's bulk stores have finished reading the staging
+        named_bar_sync(1, 32 * kEpiWarps);
+        const uint32_t so = smem_u32(stage_out);
+#pragma unroll 1
+        for (int cc = half; cc < N_TILE / 16; cc += kChunkStep) {
+          uint32_t v[16];
+          tmem_ld16(t_acc + cc * 16, v);
+          tmem_ld_wait();
+          if (cc + kChunkStep >= N_TILE / 16) release();
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const int nl = cc * 16 + hlf * 8;                  // column inside the tile
+            const int n0 = n_tile * N_TILE + nl;
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[hlf * 8 + e]);
+            if (p.plain_bias && n0 < p.n_total) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.plain_bias + n0));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.plain_bias + n0) + 1);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (p.plain_relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            // box nl/64 = [128 px][64 ch] bf16, 128-byte rows, SWIZZLE_128B: chunk ^= row & 7
+            const uint32_t dst = so + (nl >> 6) * 16384 + row * 128 + ((((nl >> 3) & 7) ^ (row & 7)) << 4);
+            st_shared_v4(dst, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                         pack_bf16x2(f[6], f[7]));
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 32 * kEpiWarps);
+        if (issuer) {
+#pragma unroll
+          for (int j = 0; j < N_TILE / 64; ++j) {
+            const int col0 = n_tile * N_TILE + 64 * j;
+            if (col0 >= p.n_total) break;
+            // pixels outside the image / batch and channels past the tensor are clipped by the TMA unit
+            if (col0 < p.Cin) {
+              if (p.out0) tma_store_4d(&tmap_o0, so + j * 16384, col0, x0, y0, b);
+            } else {
+              if (p.out1) tma_store_4d(&tmap_o1, so + j * 16384, col0 - p.Cin, x0, y0, b);
+            }
+          }
+          tma_store_commit();
+        }
       } else {  // EPI_PLAIN: D -> bf16, columns [0,Cin) -> out0, [Cin, n_total) -> out1
 #pragma unroll 1
         for (int cc = half; cc < N_TILE / 16; cc += kChunkStep) {
@@ -940,7 +995,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       }
       if (!released) release();   // warps without a chunk for this tile shape
     }
-    if constexpr (Cfg::kTmaStore) {
+    if (Cfg::kTmaStore || (EPI == EPI_PLAIN && p.plain_tma)) {
       if (warp == 4 && lane == 0) tma_store_wait_all();   // bulk stores complete before the CTA retires
     }
     if ((kProfEnabled && p.prof) && warp == 4 && lane == 0) {

@@ -443,6 +443,20 @@ int make_tmap_src(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, 
   return make_tmap_act(tm, ptr, B, H, W, C, p.tw + halo, p.th + halo, 2, p.kc, swizzle_for_kc(p.kc));
 }
 
+// EPI_PLAIN outputs through TMA tensor stores: needs 64-channel-aligned destinations (the staging boxes are
+// [128 px][64 ch]) and no PixelShuffle.  q.out0 / q.out1 / q.Cin / q.n_total / tile geometry must be final.
+int setup_plain_stores(plc::ConvTcParams* q, int B, int H, int W, CUtensorMap* o0, CUtensorMap* o1) {
+  q->plain_tma = 0;
+  const int c0 = q->Cin < q->n_total ? q->Cin : q->n_total, c1 = q->n_total - c0;
+  if (q->plain_shuffle || (c0 % 64) || (c1 % 64)) return PLC_OK;
+  if ((c0 > 0 && !q->out0) && (c1 == 0 || !q->out1)) return PLC_OK;   // nothing to store
+  int rc;
+  if (c0 > 0 && q->out0 && (rc = make_tmap_act(o0, q->out0, B, H, W, c0, q->tw, q->th, 2, 64))) return rc;
+  if (c1 > 0 && q->out1 && (rc = make_tmap_act(o1, q->out1, B, H, W, c1, q->tw, q->th, 2, 64))) return rc;
+  q->plain_tma = 1;
+  return PLC_OK;
+}
+
 int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p) {
   g->ch_tile = pick_ch_tile(d->Ch);
   g->n_tile = 4 * g->ch_tile;
@@ -777,7 +791,9 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     CUtensorMap tz, tbd;
     if ((rc = make_tmap_src(&tz, workspace, d->B, d->H, d->W, 4 * d->Ch, q))) return rc;
     if ((rc = make_tmap_mat(&tbd, w_packed_dgrad, n_total, (long)q.num_kb * 64, 64, nt / ctaq))) return rc;
-    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, ctaq, q, tz, tz, tbd, tz, tz, st))) return rc;
+    CUtensorMap tq0 = tz, tq1 = tz;
+    if ((rc = setup_plain_stores(&q, d->B, d->H, d->W, &tq0, &tq1))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, ctaq, q, tz, tz, tbd, tq0, tq1, st))) return rc;
   }
 
   // 3) wgrad + bias grad
@@ -882,7 +898,9 @@ int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, 
   CUtensorMap ta, tb;
   if ((rc = make_tmap_src(&ta, x, d->B, d->H, d->W, d->Cin, q))) return rc;
   if ((rc = make_tmap_mat(&tb, w_packed_fwd, d->Cout, (long)q.num_kb * 64, 64, nt / cta))) return rc;
-  return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, ta, ta, static_cast<cudaStream_t>(stream));
+  CUtensorMap to0 = ta, to1 = ta;
+  if ((rc = setup_plain_stores(&q, d->B, d->H, d->W, &to0, &to1))) return rc;
+  return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, to0, to1, static_cast<cudaStream_t>(stream));
 }
 
 size_t plc_conv_wgrad_acc_bytes(const PlcConvDesc* d) {
@@ -934,7 +952,9 @@ int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void
     CUtensorMap tz, tb;
     if ((rc = make_tmap_src(&tz, dz, d->B, d->H, d->W, d->Cout, q))) return rc;
     if ((rc = make_tmap_mat(&tb, w_packed_dgrad, d->Cin, (long)q.num_kb * 64, 64, nt / cta))) return rc;
-    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tb, tz, tz, st))) return rc;
+    CUtensorMap to0 = tz, to1 = tz;
+    if ((rc = setup_plain_stores(&q, d->B, d->H, d->W, &to0, &to1))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tb, to0, to1, st))) return rc;
   }
   if (dW_acc) {
     WgradShape w{d->B, d->H, d->W, d->k, d->Cin, 0, d->Cout};
