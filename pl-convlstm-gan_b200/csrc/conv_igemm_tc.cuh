@@ -95,18 +95,26 @@ struct ConvTcCfg {
   // staging (forward): c' fp32 as two [128 px][32 ch] boxes (2 x 16 KB) + h' bf16 as one [128 px][64 ch] box (16 KB)
   // staging (bwd gates, per 32-channel half): dZ bf16 as four [128 px][32 ch] boxes (4 x 8 KB) + dc_prev fp32 (16 KB)
   // staging (plain): one [128 px][64 ch] bf16 box (16 KB) per 64 output columns
-  static constexpr int kStoreBytes = kTmaStore ? 3 * 16384 : (EPI == 2 /*EPI_PLAIN*/ ? (N_TILE / 64) * 16384 : 0);
+  // (double-buffered up to N_TILE = 128: short-K convs finish a tile faster than its bulk stores drain)
+  static constexpr int kPlainBufs = N_TILE <= 128 ? 2 : 1;
+  static constexpr int kPlainBufBytes = (N_TILE / 64) * 16384;
+  static constexpr int kStoreBytes = kTmaStore ? 3 * 16384 : (EPI == 2 /*EPI_PLAIN*/ ? kPlainBufs * kPlainBufBytes : 0);
   // cta_group::2: the CTA pair shares one 256 x N_TILE accumulator tile; each CTA stages its own 128 pixels of A
   // and HALF of the B tile (N_TILE/2 packed-weight rows), so the per-SM operand feed drops from 48 to 32 KB / K-block.
   static constexpr int kBBytes = (N_TILE / kCta) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kAuxBytes = 4096 + 256;  // bias (<= 1024 floats) + barriers
+  static constexpr int kAuxBytes = 4096 + 512;  // bias (<= 1024 floats) + barriers
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - kAuxBytes - kStoreBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kAuxBytes + 1024;
-  static constexpr int kTmemCols = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64) ? 64 : (2 * N_TILE <= 128) ? 128
-                                   : (2 * N_TILE <= 256) ? 256 : 512;
+  // accumulator stages in TMEM: 2 for the wide LSTM tiles (2 x 256 columns); 4 for N_TILE <= 128, where a short-K
+  // tile is over in less time than the commit -> epilogue -> release round trip, so the MMA warp must be able to
+  // run several tiles ahead of the epilogue
+  static constexpr int kAccStages = N_TILE <= 128 ? 4 : 2;
+  static constexpr int kAccCols = kAccStages * N_TILE;
+  static constexpr int kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128
+                                   : kAccCols <= 256 ? 256 : 512;
   static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128/256");
   static_assert(kCta == 1 || kCta == 2, "cta_group is 1 or 2");
   static_assert(kStages >= 2, "need at least a double buffer");
@@ -167,15 +175,15 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   float* bias_s = reinterpret_cast<float*>(stage_out + Cfg::kStoreBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + Cfg::kStoreBytes + 4096);
   uint64_t* tmem_full = bars;                      // [2]
-  uint64_t* tmem_empty = bars + 2;                 // [2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 4);
-  uint64_t* full_bar = bars + 6;                   // [kStages]
-  uint64_t* empty_bar = bars + 6 + kStages;        // [kStages]
-  // patch mode carves the same regions differently: <= 3 patch slots + <= 8 weight stages (<= 28 barriers of 32)
-  uint64_t* patch_full = bars + 6;                 // [3]
-  uint64_t* patch_empty = bars + 9;                // [3]
-  uint64_t* bfull_bar = bars + 12;                 // [8]
-  uint64_t* bempty_bar = bars + 20;                // [8]
+  uint64_t* tmem_empty = bars + 4;                 // [kAccStages <= 4]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* full_bar = bars + 10;                  // [kStages]
+  uint64_t* empty_bar = bars + 10 + kStages;       // [kStages]
+  // patch mode carves the same regions differently: <= 8 patch slots + <= 8 weight stages (38 barriers of 64)
+  uint64_t* patch_full = bars + 10;                // [8]
+  uint64_t* patch_empty = bars + 18;               // [8]
+  uint64_t* bfull_bar = bars + 26;                 // [8]
+  uint64_t* bempty_bar = bars + 34;                // [8]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -190,14 +198,14 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   }
   if (warp == 1 && lane == 0) {
     if (p.patch) {
-      for (int s = 0; s < 22; ++s) mbar_init(&patch_full[s], 1);   // patch_full/empty[3] + bfull/bempty[8], contiguous
+      for (int s = 0; s < 32; ++s) mbar_init(&patch_full[s], 1);   // patch_full/empty[8] + bfull/bempty[8], contiguous
     } else {
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < Cfg::kAccStages; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiWarps * kCta);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
@@ -281,6 +289,11 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       const uint32_t pf_base = smem_u32(patch_full), bf_base = smem_u32(bfull_bar);
       const uint32_t wb_base = a_base + p.patch_slots * p.patch_slot_bytes;      // weight ring behind the patch slots
       const int units = p.chunks0 + p.chunks1, taps = p.ksize * p.ksize;
+      // weight stages per unit: one per tap with 64-channel boxes; with a single narrow source (kc < 64, one unit)
+      // a 64-element K stage holds G = 64/kc consecutive taps
+      const int G = kBlockK / p.kc;
+      const int kb_per_unit = (taps + G - 1) / G;
+      // patch rows are always 128 B (64-channel boxes; a narrow source is zero-filled by TMA beyond its channels)
       const uint32_t patch_tx = (p.tw + 2 * p.pad) * (p.th + 2 * p.pad) * (kBlockK * 2);
       // the patch stream runs ONE unit ahead of the weight stream (also across tile boundaries)
       int tA = tile0, uA = 0, nA = 0, bA = 0, yA = 0, xA = 0;
@@ -295,10 +308,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           const uint32_t dst = a_base + ps * p.patch_slot_bytes;
           if constexpr (kCta == 1) {
             mbar_arrive_expect_tx(&patch_full[ps], patch_tx);
-            tma_load_4d_s(dst, src ? &tmap_a1 : &tmap_a0, pf_base + ps * 8, ck * kBlockK, xA - p.pad, yA - p.pad, bA);
+            tma_load_4d_s(dst, src ? &tmap_a1 : &tmap_a0, pf_base + ps * 8, ck * p.kc, xA - p.pad, yA - p.pad, bA);
           } else {
             if (rank == 0) mbar_arrive_expect_tx(&patch_full[ps], 2 * patch_tx);
-            tma_load_4d_cg2(dst, src ? &tmap_a1 : &tmap_a0, mapa_u32(pf_base + ps * 8, 0), ck * kBlockK, xA - p.pad,
+            tma_load_4d_cg2(dst, src ? &tmap_a1 : &tmap_a0, mapa_u32(pf_base + ps * 8, 0), ck * p.kc, xA - p.pad,
                             yA - p.pad, bA);
           }
         }
@@ -310,11 +323,13 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           if (tA < num_tiles) decode_tile<kCta>(p, tA, rank, nA, bA, yA, xA);
         }
       };
-      issue_patch();
-      // With 3 slots the next unit's patch is requested before this unit's weights.  With only 2 slots its slot is
+      // prologue: keep (slots - 1) patches in flight -- a narrow single-unit tile is over in less than one TMA round trip,
+      // so the patch stream must run several tiles ahead (64-channel units last ~9 weight stages: one ahead is enough)
+      for (int i = 0; i < (p.patch_slots >= 3 ? p.patch_slots - 1 : 1); ++i) issue_patch();
+      // With >= 3 slots the next patch is requested before this unit's weights.  With only 2 slots its slot is
       // still being read by the previous unit's MMAs, which are certainly done once the weight ring has wrapped
-      // (weight tile t of this unit can only be requested after tile t - b_stages was consumed).
-      const int ahead_tap = p.patch_slots >= 3 ? 0 : (p.b_stages < taps - 1 ? p.b_stages : taps - 1);
+      // (weight stage t of this unit can only be requested after stage t - b_stages was consumed).
+      const int ahead = p.patch_slots >= 3 ? 0 : (p.b_stages < kb_per_unit - 1 ? p.b_stages : kb_per_unit - 1);
       uint32_t bs = 0, bphase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         int n_tile, b, y0, x0;
@@ -323,9 +338,11 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         for (int u = 0; u < units; ++u) {
           const int src = u >= p.chunks0;
           const int cks = src ? p.chunks1 : p.chunks0;
-          int kb = (src ? taps * p.chunks0 + (u - p.chunks0) : u);     // packed K order: source, tap, chunk
-          for (int t = 0; t < taps; ++t, kb += cks) {
-            if (t == ahead_tap) issue_patch();
+          // packed K order: source, tap, chunk (kc == 64); a single narrow unit simply walks its stages in order
+          int kb = G > 1 ? 0 : (src ? taps * p.chunks0 + (u - p.chunks0) : u);
+          const int kb_step = G > 1 ? 1 : cks;
+          for (int t = 0; t < kb_per_unit; ++t, kb += kb_step) {
+            if (t == ahead) issue_patch();
             mbar_wait(&bempty_bar[bs], bphase ^ 1);
             if (elect_one()) {
               const uint32_t b_dst = wb_base + bs * Cfg::kBBytes;
@@ -360,10 +377,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       aoff[k] = (((16 * k) / p.kc) * (kTileM * p.kc * 2) + ((16 * k) % p.kc) * 2) >> 4;
     uint32_t stage = 0, phase = 0, bstage = 0, bphase = 0;
     int it = 0;
-    long long t_empty = 0, t_full = 0, t0 = clock64();
+    long long t_empty = 0, t_full = 0, t_patch = 0, t_mma = 0, t0 = clock64();
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % Cfg::kAccStages;
+      const uint32_t aphase = (it / Cfg::kAccStages) & 1;
       long long ta = (kProfEnabled && p.prof) ? clock64() : 0;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tc_fence_after();
@@ -372,41 +389,93 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       if (p.patch) {
         // shifted views: tap (ky, kx) of the tile = the patch read from pixel row ky, pixel kx on (start address
         // + (ky * (tw+2p) + kx) * 128 B), 8-pixel groups (tile rows) one patch row = (tw+2p) * 128 B apart
-        const int units = p.chunks0 + p.chunks1, pw = p.tw + 2 * p.pad;
-        const uint64_t pdesc0 = make_smem_desc(smem_u32(smem_a), 0, pw * (kBlockK * 2));
+        const int units = p.chunks0 + p.chunks1, pw = p.tw + 2 * p.pad, taps = p.ksize * p.ksize;
+        const int G = kBlockK / p.kc, ksteps = p.kc / 16;           // taps per weight stage, UMMA_K slices per tap
+        const int kb_per_unit = (taps + G - 1) / G;
+        const uint32_t row_bytes = kBlockK * 2;    // 128-byte SWIZZLE_128B patch rows also for narrow sources
+        const uint64_t pdesc0 = make_smem_desc_kmajor_sbo(smem_u32(smem_a), row_bytes, pw * row_bytes);
         const uint64_t wdesc0 = make_smem_desc(smem_u32(smem_a) + p.patch_slots * p.patch_slot_bytes, 0, 1024);
         for (int u = 0; u < units; ++u) {
           long long tb = (kProfEnabled && p.prof) ? clock64() : 0;
           mbar_wait(&patch_full[stage], phase);
           tc_fence_after();
-          if ((kProfEnabled && p.prof)) t_full += clock64() - tb;
+          if ((kProfEnabled && p.prof)) t_patch += clock64() - tb;
           const uint64_t pdesc = pdesc0 + stage * (p.patch_slot_bytes >> 4);
-          for (int ky = 0; ky < p.ksize; ++ky) {
-            for (int kx = 0; kx < p.ksize; ++kx) {
-              tb = (kProfEnabled && p.prof) ? clock64() : 0;
-              mbar_wait(&bfull_bar[bstage], bphase);
-              tc_fence_after();
-              if ((kProfEnabled && p.prof)) t_full += clock64() - tb;
-              const bool last_tap = (ky == p.ksize - 1) && (kx == p.ksize - 1);
-              if (elect_one()) {
-                const uint64_t adesc = pdesc + ((ky * pw + kx) * (kBlockK * 2) >> 4);
-                const uint64_t bdesc = wdesc0 + bstage * (Cfg::kBBytes >> 4);
+          if (wide) {
+            // 64-channel boxes: one weight stage per tap, four UMMA_K slices, fully unrolled issue sequence (this loop
+            // must stay well below the 256..512 cycles the tensor core needs per stage)
+            for (int ky = 0; ky < p.ksize; ++ky) {
+              for (int kx = 0; kx < p.ksize; ++kx) {
+                tb = (kProfEnabled && p.prof) ? clock64() : 0;
+                mbar_wait(&bfull_bar[bstage], bphase);
+                tc_fence_after();
+                if ((kProfEnabled && p.prof)) t_full += clock64() - tb;
+                const bool last_tap = (ky == p.ksize - 1) && (kx == p.ksize - 1);
+                if (elect_one()) {
+                  const uint64_t adesc = pdesc + ((ky * pw + kx) * (kBlockK * 2) >> 4);
+                  const uint64_t bdesc = wdesc0 + bstage * (Cfg::kBBytes >> 4);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k)
-                  umma_bf16<kCta>(d_tmem, adesc + 2u * k, bdesc + 2 * k, idesc, (u | ky | kx | k) != 0);
-                if constexpr (kCta == 1) {
-                  umma_commit<1>(&bempty_bar[bstage]);
-                  if (last_tap) umma_commit<1>(&patch_empty[stage]);
-                  if (last_tap && u == units - 1) umma_commit<1>(&tmem_full[as]);
-                } else {
-                  umma_commit_mc2(&bempty_bar[bstage], 0b11);
-                  if (last_tap) umma_commit_mc2(&patch_empty[stage], 0b11);
-                  if (last_tap && u == units - 1) umma_commit_mc2(&tmem_full[as], 0b11);
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_bf16<kCta>(d_tmem, adesc + 2u * k, bdesc + 2 * k, idesc, (u | ky | kx | k) != 0);
+                  if constexpr (kCta == 1) {
+                    umma_commit<1>(&bempty_bar[bstage]);
+                    if (last_tap) umma_commit<1>(&patch_empty[stage]);
+                    if (last_tap && u == units - 1) umma_commit<1>(&tmem_full[as]);
+                  } else {
+                    umma_commit_mc2(&bempty_bar[bstage], 0b11);
+                    if (last_tap) umma_commit_mc2(&patch_empty[stage], 0b11);
+                    if (last_tap && u == units - 1) umma_commit_mc2(&tmem_full[as], 0b11);
+                  }
                 }
+                __syncwarp();
+                if (++bstage == static_cast<uint32_t>(p.b_stages)) { bstage = 0; bphase ^= 1; }
               }
-              __syncwarp();
-              if (++bstage == static_cast<uint32_t>(p.b_stages)) { bstage = 0; bphase ^= 1; }
             }
+            if (++stage == static_cast<uint32_t>(p.patch_slots)) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          int ky = 0, kx = 0, tap = 0;
+          for (int t = 0; t < kb_per_unit; ++t) {
+            tb = (kProfEnabled && p.prof) ? clock64() : 0;
+            mbar_wait(&bfull_bar[bstage], bphase);
+            tc_fence_after();
+            if ((kProfEnabled && p.prof)) t_full += clock64() - tb;
+            const bool last = t == kb_per_unit - 1;
+            const uint64_t bdesc = wdesc0 + bstage * (Cfg::kBBytes >> 4);
+            long long tm0 = (kProfEnabled && p.prof) ? clock64() : 0;
+            const int ntap = (taps - tap) < G ? (taps - tap) : G;
+            if (elect_one()) {       // ONE elected region per stage: all its taps' MMAs and the commits back to back
+              int ky2 = ky, kx2 = kx;
+              // kprof trace: raw timestamps of one tile's issue sequence (leader CTA 0, 6th tile)
+              const bool trace = (kProfEnabled && p.prof) && blockIdx.x == 0 && it == 5;
+              unsigned long long* tr = p.prof + 148 * 16 + t * 16;
+              if (trace) tr[0] = clock64();
+              for (int g = 0; g < ntap; ++g) {
+                const uint64_t adesc = pdesc + (((ky2 * pw + kx2) * row_bytes) >> 4);
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16<kCta>(d_tmem, adesc + 2u * k, bdesc + 2u * (g * ksteps + k), idesc,
+                                  (u | (tap + g) | k) != 0);
+                if (++kx2 == p.ksize) { kx2 = 0; ++ky2; }
+                if (trace) tr[1 + g] = clock64();
+              }
+              if constexpr (kCta == 1) {
+                umma_commit<1>(&bempty_bar[bstage]);
+                if (last) umma_commit<1>(&patch_empty[stage]);
+                if (last && u == units - 1) umma_commit<1>(&tmem_full[as]);
+              } else {
+                umma_commit_mc2(&bempty_bar[bstage], 0b11);
+                if (trace) tr[6] = clock64();
+                if (last) umma_commit_mc2(&patch_empty[stage], 0b11);
+                if (last && u == units - 1) umma_commit_mc2(&tmem_full[as], 0b11);
+                if (trace) tr[7] = clock64();
+              }
+            }
+            for (int g = 0; g < ntap; ++g)
+              if (++kx == p.ksize) { kx = 0; ++ky; }
+            tap += ntap;
+            if ((kProfEnabled && p.prof)) t_mma += clock64() - tm0;
+            __syncwarp();
+            if (++bstage == static_cast<uint32_t>(p.b_stages)) { bstage = 0; bphase ^= 1; }
           }
           if (++stage == static_cast<uint32_t>(p.patch_slots)) { stage = 0; phase ^= 1; }
         }
@@ -444,6 +513,8 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       p.prof[blockIdx.x * 16 + 1] = t_empty;          //           waiting for the epilogue to free TMEM
       p.prof[blockIdx.x * 16 + 2] = t_full;           //           waiting for TMA data
       p.prof[blockIdx.x * 16 + 3] = it;               //           tiles
+      p.prof[blockIdx.x * 16 + 13] = t_patch;         //           waiting for an activation patch (patch mode)
+      p.prof[blockIdx.x * 16 + 14] = t_mma;           //           narrow patch mode: inside the MMA issue loop
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
@@ -457,8 +528,8 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     long long epi_t0 = 0, pa_wait = 0, pa_busy = 0, pa_barA = 0, pa_ld = 0, pa_math = 0, pa_barB = 0, pa_pre = 0, pa_iss = 0, pa_top = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const long long tTop = ((kProfEnabled && p.prof) && warp == 4 && lane == 0) ? clock64() : 0;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % Cfg::kAccStages;
+      const uint32_t aphase = (it / Cfg::kAccStages) & 1;
       int n_tile, b, y0, x0;
       decode_tile<kCta>(p, tile, rank, n_tile, b, y0, x0);
       const int y = y0 + ty, x = x0 + tx;
@@ -897,9 +968,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         // EPI_PLAIN through shared memory: the tile leaves as N_TILE/64 bulk tensor stores issued by one thread
         // (per-thread NHWC stores put 32 scattered 16-byte pieces into every store instruction)
         const bool issuer = (warp == 4) && (lane == 0);
-        if (issuer) tma_store_wait_read();         // previous tile's bulk stores have finished reading the staging
+        // the bulk stores that last read this staging buffer (kPlainBufs tiles ago) have finished reading it
+        if (issuer) tma_store_wait_read_n<Cfg::kPlainBufs - 1>();
         named_bar_sync(1, 32 * kEpiWarps);
-        const uint32_t so = smem_u32(stage_out);
+        const uint32_t so = smem_u32(stage_out) + (it % Cfg::kPlainBufs) * Cfg::kPlainBufBytes;
 #pragma unroll 1
         for (int cc = half; cc < N_TILE / 16; cc += kChunkStep) {
           uint32_t v[16];

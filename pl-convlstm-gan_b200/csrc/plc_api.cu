@@ -353,7 +353,8 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
   }
   if (p.patch) {   // carve the pipeline region into patch slots + weight stages
     const int region = Cfg::kStages * Cfg::kStageBytes;
-    p.patch_slots = (region - 3 * p.patch_slot_bytes) / Cfg::kBBytes >= 4 ? 3 : 2;
+    if (p.kc < 64) p.patch_slots = 4;    // narrow single-unit tiles are short: several tiles of look-ahead
+    else p.patch_slots = (region - 3 * p.patch_slot_bytes) / Cfg::kBBytes >= 4 ? 3 : 2;
     int nb = (region - p.patch_slots * p.patch_slot_bytes) / Cfg::kBBytes;
     if (nb < 2) return fail(PLC_ERR_UNSUPPORTED, "patch mode does not fit (N_TILE=%d cta=%d)", NT, CTA);
     p.b_stages = nb > 8 ? 8 : nb;
@@ -412,8 +413,8 @@ void set_kgeom(plc::ConvTcParams* p, const KGeom& kg) {
   p->kc = kg.kc; p->chunks0 = kg.chunks0; p->chunks1 = kg.chunks1; p->num_boxes = kg.num_boxes; p->num_kb = kg.num_kb;
 }
 
-// Haloed-patch pipeline (conv_igemm_tc.cuh, "patch mode"): applies when every K stage is one 64-channel box (kc == 64)
-// and the kernel is 3x3 or 5x5; it needs 16 x 8-pixel tiles, so it is skipped when that tiling wastes > 5 % more
+// Haloed-patch pipeline (conv_igemm_tc.cuh, "patch mode"): applies to 3x3 / 5x5 kernels whose sources are read as
+// 64-channel boxes (kc == 64), or as ONE narrower box (a single source of <= 32 channels, e.g. the frame front-end); it needs 16 x 8-pixel tiles, so it is skipped when that tiling wastes > 5 % more
 // pixels than the default one.  PLC_PATCH=0|1 / plc_debug_set_patch override (A/B runs, parity tests of both paths).
 int g_patch_override = -1;   // plc_debug_set_patch
 void maybe_patch(TcGeom* g, plc::ConvTcParams* p) {
@@ -424,7 +425,9 @@ void maybe_patch(TcGeom* g, plc::ConvTcParams* p) {
   }
   const int mode = g_patch_override >= 0 ? g_patch_override : env_mode;
   p->patch = 0;
-  if (mode == 0 || p->kc != 64 || (p->ksize != 3 && p->ksize != 5)) return;
+  if (mode == 0 || (p->ksize != 3 && p->ksize != 5)) return;
+  // 64-channel boxes: any number of (source, chunk) units; narrower boxes: a single unit (one narrow source)
+  if (p->kc != 64 && p->chunks0 + p->chunks1 != 1) return;
   const long area_def = static_cast<long>(g->tiles_x) * g->tw * g->tiles_y * g->th;
   const long area_patch = static_cast<long>(cdiv(p->W, 8)) * 8 * cdiv(p->H, 16) * 16;
   if (mode != 1 && area_patch * 100 > area_def * 105) return;
@@ -439,8 +442,10 @@ void maybe_patch(TcGeom* g, plc::ConvTcParams* p) {
 }
 // activation tensor map of an A source: the plain [kc ch, tw, th] tile box, or the haloed patch box in patch mode
 int make_tmap_src(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, const plc::ConvTcParams& p) {
-  const int halo = p.patch ? 2 * p.pad : 0;
-  return make_tmap_act(tm, ptr, B, H, W, C, p.tw + halo, p.th + halo, 2, p.kc, swizzle_for_kc(p.kc));
+  // patch boxes are always 64 channels wide (128-byte SWIZZLE_128B rows): narrow sources (kc < 64) are zero-filled
+  // beyond their channels -- the 32/64-byte swizzle modes cost ~4x the tensor-core issue time per UMMA
+  if (p.patch) return make_tmap_act(tm, ptr, B, H, W, C, p.tw + 2 * p.pad, p.th + 2 * p.pad, 2, 64);
+  return make_tmap_act(tm, ptr, B, H, W, C, p.tw, p.th, 2, p.kc, swizzle_for_kc(p.kc));
 }
 
 // EPI_PLAIN outputs through TMA tensor stores: needs 64-channel-aligned destinations (the staging boxes are

@@ -138,6 +138,11 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 // wait until the bulk stores of this thread have finished READING shared memory (buffer reusable)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // wait until they are complete (global writes done)
+// wait until at most N of this thread's bulk-store groups still have to read their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -254,6 +259,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_kmajor(uint32_t smem_addr, ui
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
   d |= static_cast<uint64_t>(((8 * row_bytes) >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= layout << 61;
+  return d;
+}
+// K-major operand with `row_bytes`-wide swizzled rows and an explicit 8-row group stride (patch views: one patch row)
+__device__ __forceinline__ uint64_t make_smem_desc_kmajor_sbo(uint32_t smem_addr, uint32_t row_bytes, uint32_t sbo) {
+  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= layout << 61;
   return d;

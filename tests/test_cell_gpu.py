@@ -284,6 +284,8 @@ PATCH_SHAPES = [
     (1, 64, 64, 19, 21, 5),      # k = 5 (patch 20 x 12)
     (1, 64, 128, 16, 16, 3),     # 2 N tiles re-read the same patches
     (2, 72, 80, 18, 9, 3),       # channel tails inside the last 64-channel chunk
+    (2, 0, 32, 20, 13, 3),       # single narrow source: 32-channel patch boxes (SWIZZLE_64B), 2 taps per K stage
+    (1, 0, 16, 17, 9, 5),        # 16-channel patch boxes (SWIZZLE_32B), 4 taps per K stage, k = 5
 ]
 
 

@@ -166,6 +166,26 @@ def test_generic_conv_forward_backward_vs_torch(cfg, cuda_device):
     assert rel_err(conv.bias.grad, br.grad) < 2e-2
 
 
+@pytest.mark.parametrize("cta", [1, 2])
+@pytest.mark.parametrize("cfg", [(3, 20, 13, 3, 64, 3, True, False), (2, 16, 8, 64, 64, 3, True, False),
+                                 (1, 33, 17, 128, 64, 3, False, False), (2, 18, 11, 16, 32, 5, True, False),
+                                 (1, 16, 16, 64, 128, 3, True, True), (2, 24, 16, 256, 128, 3, False, False)],
+                         ids=lambda c: "B%d_%dx%d_%d-%d_k%d_relu%d_ps%d" % tuple(int(v) for v in c))
+def test_generic_conv_patch_pipeline_vs_torch(cfg, cta, cuda_device):
+    """The same layer checks with the haloed-patch pipeline forced on (narrow single-source boxes for the frame
+    front-end shape 3(+pad) -> 64, 64-channel units otherwise) and both cta_group paths; outputs that are multiples of
+    64 channels leave through the staged TMA-store epilogue, the others through per-thread stores."""
+    import plconv
+    lib = plconv._lib.load()
+    lib.plc_debug_set_patch(1)
+    lib.plc_debug_set_cta_group(cta)
+    try:
+        test_generic_conv_forward_backward_vs_torch(cfg, cuda_device)
+    finally:
+        lib.plc_debug_set_patch(-1)
+        lib.plc_debug_set_cta_group(0)
+
+
 def test_cuda_graph_replay_matches_eager(cuda_device):
     """The rollout captured in a CUDA graph (tensor maps baked in as kernel parameters) replays bit-identically
     on new inputs."""
