@@ -323,9 +323,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           if (tA < num_tiles) decode_tile<kCta>(p, tA, rank, nA, bA, yA, xA);
         }
       };
-      // prologue: keep (slots - 1) patches in flight -- a narrow single-unit tile is over in less than one TMA round trip,
-      // so the patch stream must run several tiles ahead (64-channel units last ~9 weight stages: one ahead is enough)
-      for (int i = 0; i < (p.patch_slots >= 3 ? p.patch_slots - 1 : 1); ++i) issue_patch();
+      // prologue: a narrow single-unit tile is over in less than one TMA round trip, so its patch stream runs
+      // (slots - 1) tiles ahead; 64-channel units last ~9 weight stages: ONE unit ahead (a deeper look-ahead would wait
+      // for the slot the MMAs are still reading, and stall the weight stream behind it)
+      for (int i = 0; i < (p.kc < 64 ? p.patch_slots - 1 : 1); ++i) issue_patch();
       // With >= 3 slots the next patch is requested before this unit's weights.  With only 2 slots its slot is
       // still being read by the previous unit's MMAs, which are certainly done once the weight ring has wrapped
       // (weight stage t of this unit can only be requested after stage t - b_stages was consumed).
