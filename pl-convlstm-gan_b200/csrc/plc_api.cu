@@ -417,7 +417,29 @@ void set_kgeom(plc::ConvTcParams* p, const KGeom& kg) {
 // 64-channel boxes (kc == 64), or as ONE narrower box (a single source of <= 32 channels, e.g. the frame front-end); it needs 16 x 8-pixel tiles, so it is skipped when that tiling wastes > 5 % more
 // pixels than the default one.  PLC_PATCH=0|1 / plc_debug_set_patch override (A/B runs, parity tests of both paths).
 int g_patch_override = -1;   // plc_debug_set_patch
-void maybe_patch(TcGeom* g, plc::ConvTcParams* p) {
+// bytes of the operand pipeline region of one instantiation (what patch mode re-carves into patch slots + weight stages)
+template <int EPI, int CTA>
+int pipeline_region_nt(int nt, int* b_bytes) {
+#define PLC_REGION(NT)                                       \
+  case NT: {                                                 \
+    using Cfg = plc::ConvTcCfg<NT, CTA, EPI>;                \
+    *b_bytes = Cfg::kBBytes;                                 \
+    return Cfg::kStages * Cfg::kStageBytes;                  \
+  }
+  switch (nt) { PLC_REGION(64) PLC_REGION(128) PLC_REGION(192) PLC_REGION(256) }
+#undef PLC_REGION
+  *b_bytes = 1;
+  return 0;
+}
+int pipeline_region(int epi, int nt, int cta, int* b_bytes) {
+  if (epi == plc::EPI_LSTM_FWD)
+    return cta == 2 ? pipeline_region_nt<plc::EPI_LSTM_FWD, 2>(nt, b_bytes) : pipeline_region_nt<plc::EPI_LSTM_FWD, 1>(nt, b_bytes);
+  if (epi == plc::EPI_LSTM_BWD_GATES)
+    return cta == 2 ? pipeline_region_nt<plc::EPI_LSTM_BWD_GATES, 2>(nt, b_bytes)
+                    : pipeline_region_nt<plc::EPI_LSTM_BWD_GATES, 1>(nt, b_bytes);
+  return cta == 2 ? pipeline_region_nt<plc::EPI_PLAIN, 2>(nt, b_bytes) : pipeline_region_nt<plc::EPI_PLAIN, 1>(nt, b_bytes);
+}
+void maybe_patch(TcGeom* g, plc::ConvTcParams* p, int epi, int n_tile) {
   static int env_mode = -2;
   if (env_mode == -2) {
     const char* e = getenv("PLC_PATCH");
@@ -431,6 +453,12 @@ void maybe_patch(TcGeom* g, plc::ConvTcParams* p) {
   const long area_def = static_cast<long>(g->tiles_x) * g->tw * g->tiles_y * g->th;
   const long area_patch = static_cast<long>(cdiv(p->W, 8)) * 8 * cdiv(p->H, 16) * 16;
   if (mode != 1 && area_patch * 100 > area_def * 105) return;
+  const int slot_bytes = ((16 + 2 * p->pad) * (8 + 2 * p->pad) * 128 + 1023) / 1024 * 1024;
+  if (mode != 1) {   // needs room for 2 patch slots + at least 3 weight stages (single-CTA N_TILE = 256 tiles do not)
+    int b_bytes = 1;
+    const int region = pipeline_region(epi, n_tile, pick_cta_group(p->B * cdiv(p->W, 8) * cdiv(p->H, 16)), &b_bytes);
+    if ((region - 2 * slot_bytes) / b_bytes < 3) return;
+  }
   g->tw = 8; g->th = 16; g->tw_log2 = 3;
   g->tiles_x = cdiv(p->W, 8); g->tiles_y = cdiv(p->H, 16);
   p->tw = 8; p->th = 16; p->tw_log2 = 3;
@@ -438,7 +466,7 @@ void maybe_patch(TcGeom* g, plc::ConvTcParams* p) {
   p->num_m_tiles = p->B * g->tiles_x * g->tiles_y;
   p->num_tiles = p->num_m_tiles * p->num_n_tiles;
   p->patch = 1;
-  p->patch_slot_bytes = ((16 + 2 * p->pad) * (8 + 2 * p->pad) * 128 + 1023) / 1024 * 1024;
+  p->patch_slot_bytes = slot_bytes;
 }
 // activation tensor map of an A source: the plain [kc ch, tw, th] tile box, or the haloed patch box in patch mode
 int make_tmap_src(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, const plc::ConvTcParams& p) {
@@ -462,7 +490,7 @@ int setup_plain_stores(plc::ConvTcParams* q, int B, int H, int W, CUtensorMap* o
   return PLC_OK;
 }
 
-int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p) {
+int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p, int epi) {
   g->ch_tile = pick_ch_tile(d->Ch);
   g->n_tile = 4 * g->ch_tile;
   pick_spatial_tile(d->H, d->W, g);
@@ -470,7 +498,7 @@ int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p) {
   p->num_n_tiles = d->Ch / g->ch_tile;
   p->num_tiles = p->num_m_tiles * p->num_n_tiles;
   set_kgeom(p, kgeom(d->Cin, d->Ch, d->k));
-  maybe_patch(g, p);
+  maybe_patch(g, p, epi, g->n_tile);
   return PLC_OK;
 }
 
@@ -644,7 +672,7 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     return fail(PLC_ERR_ALIGNMENT, "plc_cell_fwd: all device pointers must be 16-byte aligned");
   TcGeom g;
   plc::ConvTcParams p;
-  lstm_tc_setup(d, &g, &p);
+  lstm_tc_setup(d, &g, &p, plc::EPI_LSTM_FWD);
   p.bias = d->has_bias ? bias : nullptr;
   p.c_prev = static_cast<const float*>(c_prev);
   p.c_out = static_cast<float*>(c_out);
@@ -750,7 +778,7 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     return fail(PLC_ERR_ALIGNMENT, "plc_cell_bwd: all device pointers must be 16-byte aligned");
   TcGeom g;
   plc::ConvTcParams p;
-  lstm_tc_setup(d, &g, &p);
+  lstm_tc_setup(d, &g, &p, plc::EPI_LSTM_BWD_GATES);
   // 1) gate recompute (same mainloop as the forward) + dZ / dc_prev epilogue
   p.bias = d->has_bias ? bias : nullptr;
   p.c_prev = static_cast<const float*>(c_prev);
@@ -788,7 +816,7 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     q.num_n_tiles = cdiv(n_total, nt);
     q.num_tiles = q.num_m_tiles * q.num_n_tiles;
     set_kgeom(&q, kgeom(4 * d->Ch, 0, d->k));
-    maybe_patch(&gq, &q);
+    maybe_patch(&gq, &q, plc::EPI_PLAIN, nt);
     q.n_total = n_total;
     q.out0 = static_cast<__nv_bfloat16*>(dx);
     q.out1 = static_cast<__nv_bfloat16*>(dh_prev);
@@ -892,7 +920,7 @@ int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, 
   q.num_n_tiles = cdiv(d->Cout, nt);
   q.num_tiles = q.num_m_tiles * q.num_n_tiles;
   set_kgeom(&q, kgeom(d->Cin, 0, d->k));
-  maybe_patch(&g, &q);
+  maybe_patch(&g, &q, plc::EPI_PLAIN, nt);
   q.n_total = d->Cout;
   q.Cin = d->Cout;                     // no column split: everything goes to out0
   q.out0 = static_cast<__nv_bfloat16*>(out);
@@ -949,7 +977,7 @@ int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void
     q.num_n_tiles = cdiv(d->Cin, nt);
     q.num_tiles = q.num_m_tiles * q.num_n_tiles;
     set_kgeom(&q, kgeom(d->Cout, 0, d->k));
-    maybe_patch(&g, &q);
+    maybe_patch(&g, &q, plc::EPI_PLAIN, nt);
     q.n_total = d->Cin;
     q.Cin = d->Cin;
     q.out0 = static_cast<__nv_bfloat16*>(dx);
