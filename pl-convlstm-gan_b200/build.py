@@ -63,8 +63,24 @@ def build_kprof() -> str:
     return out
 
 
+def build_variant(defines, name: str) -> str:
+    """Developer A/B build with extra -D flags -> tools/ubench/<name>.so (select it with PLC_LIB=...)."""
+    out = os.path.join(os.path.dirname(HERE), "tools", "ubench", name + ".so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v"] + ["-D" + d for d in defines] + _sources() + ["-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    with open(out + ".ptxas.log", "w") as f:
+        f.write(r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    if "--kprof" in sys.argv:
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 2:], sys.argv[i + 1]))
+    elif "--kprof" in sys.argv:
         print(build_kprof())
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
