@@ -85,6 +85,12 @@ int plc_pack_weight(const PlcCellDesc* d, int pack_kind, const float* w_oihw, vo
  *   h_out  [B,H,W,Ch]   c_out [B,H,W,Ch]   (must not alias h_prev / c_prev may alias c_out)
  *   gates_out: optional [B,H,W,4Ch] (i,f,o,g activations, mode dtype for x) or NULL.
  * dtypes: PLC_MODE_BF16_TC: x,h bf16, c fp32.  PLC_MODE_FP32: all fp32.                     */
+/* Zero-initial-state form of plc_cell_fwd: every sequence of the reference starts from h = c = 0
+ * (generator.py:156-160).  When this returns 1 for the descriptor, plc_cell_fwd accepts h_prev = c_prev = NULL and
+ * skips the h taps (half of the K loop) and the c_prev read instead of multiplying by zero tensors; results are
+ * bit-identical to passing zeros.  Returns 0 when the shape/mode needs the zero tensors (fp32 mode, Cin = 0, or
+ * narrow channel boxes whose x taps do not end on a K-stage boundary).                                        */
+int plc_cell_fwd_zero_state_ok(const PlcCellDesc* d);
 int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
                  const void* w_packed_fwd, const float* bias, void* h_out, void* c_out, void* gates_out,
                  void* stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "plc_packed_weight_bytes": (_sz, [_dp, _int]),
     "plc_pack_weight": (_int, [_dp, _int, _vp, _vp, _vp]),
     "plc_cell_fwd": (_int, [_dp] + [_vp] * 9),
+    "plc_cell_fwd_zero_state_ok": (_int, [_dp]),
     "plc_bwd_workspace_bytes": (_sz, [_dp]),
     "plc_wgrad_acc_bytes": (_sz, [_dp]),
     "plc_wgrad_unpack": (_int, [_dp, _vp, _vp, _vp]),

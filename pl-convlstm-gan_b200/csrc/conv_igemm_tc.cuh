@@ -558,10 +558,15 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         for (int m = 0; m < kMaxGran; ++m) {
           const int g = half + m * kChunkStep;
           if (valid && g < kGran) {
-            const float4* src = reinterpret_cast<const float4*>(p.c_prev + pix * p.Ch + n_tile * CH_TILE + g * 8);
-            const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
-            cpre[m][0] = t0.x; cpre[m][1] = t0.y; cpre[m][2] = t0.z; cpre[m][3] = t0.w;
-            cpre[m][4] = t1.x; cpre[m][5] = t1.y; cpre[m][6] = t1.z; cpre[m][7] = t1.w;
+            if (p.c_prev) {
+              const float4* src = reinterpret_cast<const float4*>(p.c_prev + pix * p.Ch + n_tile * CH_TILE + g * 8);
+              const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
+              cpre[m][0] = t0.x; cpre[m][1] = t0.y; cpre[m][2] = t0.z; cpre[m][3] = t0.w;
+              cpre[m][4] = t1.x; cpre[m][5] = t1.y; cpre[m][6] = t1.z; cpre[m][7] = t1.w;
+            } else {                 // zero initial state (generator.py:156-160): c_prev == 0
+#pragma unroll
+              for (int e = 0; e < 8; ++e) cpre[m][e] = 0.f;
+            }
           }
         }
       }

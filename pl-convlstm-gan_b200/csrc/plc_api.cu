@@ -636,12 +636,24 @@ int plc_pack_weight(const PlcCellDesc* d, int pack_kind, const float* w_oihw, vo
   return PLC_OK;
 }
 
+int plc_cell_fwd_zero_state_ok(const PlcCellDesc* d) {
+  if (check_desc(d) != PLC_OK) return 0;
+  if (d->mode != PLC_MODE_BF16_TC || d->Cin <= 0) return 0;
+  const KGeom kg = kgeom(d->Cin, d->Ch, d->k);
+  return (d->k * d->k * kg.chunks0) % (64 / kg.kc) == 0;   // the x taps fill whole K stages
+}
+
 int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
                  const void* w_packed_fwd, const float* bias, void* h_out, void* c_out, void* gates_out,
                  void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
-  if ((d->Cin > 0 && !x) || !h_prev || !c_prev || !w_packed_fwd || !h_out || !c_out)
+  // zero-initial-state form (generator.py:156-160 starts every sequence from h = c = 0): h_prev == c_prev == NULL
+  const bool zero_state = !h_prev && !c_prev;
+  if (zero_state && !plc_cell_fwd_zero_state_ok(d))
+    return fail(PLC_ERR_UNSUPPORTED, "plc_cell_fwd: the zero-state form (h_prev = c_prev = NULL) is not available for "
+                                     "this shape/mode (see plc_cell_fwd_zero_state_ok); pass zero tensors");
+  if ((d->Cin > 0 && !x) || (!zero_state && (!h_prev || !c_prev)) || !w_packed_fwd || !h_out || !c_out)
     return fail(PLC_ERR_NULL_ARG, "plc_cell_fwd: null pointer");
   if (d->has_bias && !bias) return fail(PLC_ERR_NULL_ARG, "plc_cell_fwd: has_bias set but bias is null");
   if (h_out == h_prev) return fail(PLC_ERR_BAD_DESC, "h_out must not alias h_prev (halo reads)");
@@ -678,15 +690,24 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   p.c_out = static_cast<float*>(c_out);
   p.h_out = static_cast<__nv_bfloat16*>(h_out);
   p.gates_out = static_cast<__nv_bfloat16*>(gates_out);
+  const long full_kb = p.num_kb;               // K extent of the packed weight image (both sources)
+  if (zero_state) {
+    // h_prev == 0: its taps contribute nothing.  The packed K order is source-major, so the x part is the leading
+    // num_boxes0 / G stages (plc_cell_fwd_zero_state_ok guarantees it ends on a stage boundary): skip the rest.
+    p.chunks1 = 0;
+    p.num_boxes = d->k * d->k * p.chunks0;
+    p.num_kb = p.num_boxes / (64 / p.kc);
+  }
   CUtensorMap ta0, ta1, tb;
-  if ((rc = make_tmap_src(&ta1, h_prev, d->B, d->H, d->W, d->Ch, p))) return rc;
-  if (d->Cin > 0) {
-    if ((rc = make_tmap_src(&ta0, x, d->B, d->H, d->W, d->Cin, p))) return rc;
+  if (d->Cin > 0 && (rc = make_tmap_src(&ta0, x, d->B, d->H, d->W, d->Cin, p))) return rc;
+  if (zero_state) {
+    ta1 = ta0;
   } else {
-    ta0 = ta1;
+    if ((rc = make_tmap_src(&ta1, h_prev, d->B, d->H, d->W, d->Ch, p))) return rc;
+    if (d->Cin == 0) ta0 = ta1;
   }
   const int cta = pick_cta_group(p.num_m_tiles);
-  if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile / cta))) return rc;
+  if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, full_kb * 64, 64, g.n_tile / cta))) return rc;
   CUtensorMap to0 = ta1, to1 = ta1;
   if (plc::tma_store_epilogue<256, plc::EPI_LSTM_FWD>() && g.n_tile == 256) {
     if ((rc = make_tmap_act(&to0, c_out, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;

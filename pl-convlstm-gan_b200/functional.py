@@ -110,6 +110,33 @@ def cell_forward(x: Optional[Tensor], h: Tensor, c: Tensor, pw: PackedWeights,
     return h_out, c_out
 
 
+def zero_state_supported(pw: PackedWeights) -> bool:
+    """True if :func:`cell_forward_zero_state` is available for these weights (plc_cell_fwd_zero_state_ok)."""
+    lib = _lib.load()
+    d = make_desc(1, 16, 16, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)
+    return bool(lib.plc_cell_fwd_zero_state_ok(ctypes.byref(d)))
+
+
+def cell_forward_zero_state(x: Tensor, pw: PackedWeights, h_out: Optional[Tensor] = None,
+                            c_out: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """First step of a sequence: h_prev = c_prev = 0 (generator.py:156-160) without materialising the zero tensors --
+    the h taps (half of the K loop) and the c_prev read are skipped.  Bit-identical to :func:`cell_forward` on zeros."""
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    B, H, W, cin = x.shape
+    adt = _act_dtype(pw.mode)
+    if x.dtype != adt or cin != pw.Cin:
+        raise RuntimeError(f"x must be {adt} [B,H,W,{pw.Cin}], got {x.dtype} {tuple(x.shape)}")
+    if h_out is None:
+        h_out = torch.empty(B, H, W, pw.Ch, dtype=adt, device=x.device)
+    if c_out is None:
+        c_out = torch.empty(B, H, W, pw.Ch, dtype=torch.float32, device=x.device)
+    d = make_desc(B, H, W, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)
+    _lib.check(lib.plc_cell_fwd(ctypes.byref(d), _ptr(x), None, None, _ptr(pw.fwd), _ptr(pw.bias), _ptr(h_out),
+                                _ptr(c_out), None, _stream()), "plc_cell_fwd (zero state)")
+    return h_out, c_out
+
+
 def bwd_workspace(B: int, H: int, W: int, pw: PackedWeights, device) -> Tensor:
     lib = _lib.load()
     d = make_desc(B, H, W, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)

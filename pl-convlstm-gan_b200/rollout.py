@@ -87,6 +87,7 @@ class NowcastRunner:
         self.h_top = torch.zeros(model.t_out, B, H, W, hd[-1], dtype=adt, device=device)
         self.out = torch.zeros(model.t_out, B, H, W, dtype=torch.float32, device=device)
         self.enc_pw = [c._packed(False) for c in model.encoder.cells]
+        self.zero_state = [F.zero_state_supported(pw) for pw in self.enc_pw]
         self.fc_pw = [c._packed(False) for c in model.forecaster.cells]
         self.cell_launches_per_run = L * (model.t_in + model.t_out)
         self.launches_per_run = (2 if self.tc_frontend else 1) + self.cell_launches_per_run + 1
@@ -118,7 +119,10 @@ class NowcastRunner:
         if events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        F.cell_forward(x, h_prev, c, pw, h_out=h_out, c_out=c)
+        if h_prev is None:
+            F.cell_forward_zero_state(x, pw, h_out=h_out, c_out=c)
+        else:
+            F.cell_forward(x, h_prev, c, pw, h_out=h_out, c_out=c)
         if events is not None:
             e1.record()
             events.append((e0, e1, pw))
@@ -138,15 +142,19 @@ class NowcastRunner:
             fr = frames.transpose(0, 1).reshape(T_in * B, m.in_channels, self.H, self.W).contiguous()
             F.frontend_forward(fr, m.init_conv.weight, m.init_conv.bias, self.mode, c_stride=self.feat.shape[-1],
                                out=self.feat)
-        for l in range(L):                                   # generator.py:156-160: zero initial state
-            self.h[l][0].zero_()
-            self.c[l].zero_()
+        # generator.py:156-160: zero initial state.  Where the library offers the zero-state form, the first step skips
+        # the h taps and the c read instead of zero-filling the state buffers and multiplying by them.
+        for l in range(L):
+            if not self.zero_state[l]:
+                self.h[l][0].zero_()
+                self.c[l].zero_()
         cur = [0] * L
         for t in range(T_in):                                # generator.py:164
             x = self.feat[t * B:(t + 1) * B]
             for l in range(L):                               # generator.py:170-171
                 dst = self.h[l][cur[l] ^ 1]
-                self._cell(self.enc_pw[l], x, self.h[l][cur[l]], self.c[l], dst, events)
+                self._cell(self.enc_pw[l], x, None if (t == 0 and self.zero_state[l]) else self.h[l][cur[l]],
+                           self.c[l], dst, events)
                 cur[l] ^= 1
                 x = dst
         for t in range(T_out):

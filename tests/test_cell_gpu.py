@@ -329,3 +329,38 @@ def test_patch_pipeline_matches_default_pipeline_closely(cuda_device):
             lib.plc_debug_set_patch(-1)
     assert float((outs[0][1] - outs[1][1]).abs().max()) <= 2e-5
     assert float((outs[0][0] - outs[1][0]).abs().max()) <= 2 ** -7      # at most one bf16 ulp near |h| <= 1
+
+
+@pytest.mark.parametrize("patch", [0, 1], ids=["default-pipeline", "patch-pipeline"])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 20, 13, 3), (1, 128, 64, 16, 16, 3), (2, 64, 128, 9, 17, 5),
+                                   (2, 16, 16, 12, 12, 1), (1, 32, 32, 10, 10, 3)],
+                         ids=lambda s: "B%d_Cin%d_Ch%d_%dx%d_k%d" % s)
+def test_zero_state_form_is_bit_identical_to_zero_tensors(shape, patch, cuda_device):
+    """plc_cell_fwd(h_prev = c_prev = NULL) (first step of every sequence, generator.py:156-160) == the same call on
+    zero tensors, bit for bit; shapes the form does not cover must say so through plc_cell_fwd_zero_state_ok."""
+    plconv, F = _plconv()
+    lib = plconv._lib.load()
+    B, cin, ch, H, W, k = shape
+    dev = cuda_device
+    g = torch.Generator().manual_seed(sum(shape))
+    w = torch.randn(4 * ch, cin + ch, k, k, generator=g) * 0.1
+    b = torch.randn(4 * ch, generator=g) * 0.3
+    pw = F.pack_weights(w.to(dev), b.to(dev), cin, ch, k, plconv.PLC_MODE_BF16_TC)
+    x = torch.randn(B, H, W, cin, generator=g).to(dev).to(torch.bfloat16)
+    lib.plc_debug_set_patch(patch)
+    try:
+        ok = F.zero_state_supported(pw)
+        # 64-channel boxes always qualify; 16/32-channel boxes only if the x taps fill whole 64-element K stages
+        # (1 tap of 16 channels, 9 taps of 32 channels: they do not)
+        assert ok == (cin % 64 == 0)
+        if not ok:
+            with pytest.raises(RuntimeError, match="zero-state"):
+                F.cell_forward_zero_state(x, pw)
+            return
+        h0 = torch.zeros(B, H, W, ch, device=dev, dtype=torch.bfloat16)
+        c0 = torch.zeros(B, H, W, ch, device=dev)
+        h_ref, c_ref = F.cell_forward(x, h0, c0, pw)
+        h_z, c_z = F.cell_forward_zero_state(x, pw)
+    finally:
+        lib.plc_debug_set_patch(-1)
+    assert torch.equal(h_z, h_ref) and torch.equal(c_z, c_ref)
