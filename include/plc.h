@@ -177,6 +177,15 @@ int plc_frontend_fwd(const float* frames, int N, int Cf, int H, int W, const flo
 int plc_head_fwd(const void* h, long npix, int C, const float* w, const float* bias, int mode, float* out,
                  void* stream);
 
+/* The same front-end (generator.py:166-168 + coordconv.py:3-10, all T frames of a batch in one launch) on the tensor
+ * cores with the im2col done by the kernel's producer warps: frames [B,T,Cf,H,W] fp32 -> out [T*B,H,W,64] bf16 =
+ * relu(conv3x3(cat(frame, row/(H-1), col/(W-1)))) with w_oihw = init_conv.weight [64,Cf+2,3,3] fp32 (read directly, no
+ * packing step), bias [64] or NULL.  Available for 1..3 frame channels and C = C_stride = 64
+ * (plc_frontend_tc_supported); other shapes use plc_frames_to_nhwc + plc_conv_fwd.                              */
+int plc_frontend_tc_supported(int Cf, int C, int C_stride);
+int plc_frontend_tc_fwd(const float* frames, int B, int T, int Cf, int H, int W, const float* w_oihw, const float* bias,
+                        int C, void* out, void* stream);
+
 /* frames [B,T,Cf,H,W] fp32 (layout of the reference's rain_lr, generator.py:96) -> [T*B,H,W,Cp] bf16, T-major, with
  * the coordinate planes of add_coord_channels (coordconv.py:3-10) appended and zero padding to Cp (Cp % 8 == 0,
  * Cp >= Cf+2): the NHWC input of init_conv when it runs on the tensor-core conv (plc_conv_fwd).                */

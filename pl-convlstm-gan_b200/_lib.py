@@ -64,6 +64,8 @@ SIGNATURES = {
     "plc_nchw_f32_to_nhwc_bf16": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),
     "plc_nhwc_bf16_to_nchw_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _vp]),
     "plc_frontend_fwd": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _int, _int, _int, _vp, _vp]),
+    "plc_frontend_tc_supported": (_int, [_int, _int, _int]),
+    "plc_frontend_tc_fwd": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp, _int, _vp, _vp]),
     "plc_head_fwd": (_int, [_vp, ctypes.c_long, _int, _vp, _vp, _int, _vp, _vp]),
     "plc_frames_to_nhwc": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp]),
     "plc_head_bwd": (_int, [_vp, ctypes.c_long, _int, _vp, _vp, _vp, _vp, _vp, _vp]),

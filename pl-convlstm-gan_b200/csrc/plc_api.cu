@@ -15,6 +15,7 @@
 #include "conv_igemm_tc.cuh"
 #include "conv_simt.cuh"
 #include "frame_io.cuh"
+#include "frontend_tc.cuh"
 #include "loss.cuh"
 #include "wgrad_tc.cuh"
 
@@ -1202,6 +1203,41 @@ int plc_combined_loss(const PlcLossDesc* d, const float* pred, const float* lr_i
     if (dpred) plc::loss_point_grad_kernel<<<blocks(n_obs), 256, 0, st>>>(p);
   }
   plc::loss_finalize_kernel<<<1, 1, 0, st>>>(p, terms_out);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+int plc_frontend_tc_supported(int Cf, int C, int C_stride) {
+  return (Cf >= 1 && Cf <= 3 && C == plc::kFeN && C_stride == plc::kFeN) ? 1 : 0;
+}
+
+int plc_frontend_tc_fwd(const float* frames, int B, int T, int Cf, int H, int W, const float* w_oihw, const float* bias,
+                        int C, void* out, void* stream) {
+  if (!frames || !w_oihw || !out) return fail(PLC_ERR_NULL_ARG, "plc_frontend_tc_fwd: null pointer");
+  if (B <= 0 || T <= 0 || H <= 0 || W <= 0) return fail(PLC_ERR_BAD_DESC, "plc_frontend_tc_fwd: bad sizes");
+  if (!plc_frontend_tc_supported(Cf, C, C))
+    return fail(PLC_ERR_UNSUPPORTED, "plc_frontend_tc_fwd: needs 1..3 frame channels and C == 64 (got Cf=%d C=%d); use "
+                                     "plc_frames_to_nhwc + plc_conv_fwd", Cf, C);
+  const long long total = static_cast<long long>(B) * T * H * W;
+  if (total >= (1ll << 31) - 128) return fail(PLC_ERR_UNSUPPORTED, "plc_frontend_tc_fwd: B*T*H*W must be < 2^31");
+  if (!aligned16(out)) return fail(PLC_ERR_ALIGNMENT, "plc_frontend_tc_fwd: out must be 16-byte aligned");
+  int rc;
+  CUtensorMap tm;
+  if ((rc = make_tmap_mat(&tm, out, total, plc::kFeN, plc::kFeN, 128))) return rc;
+  plc::FrontendTcParams p;
+  p.B = B; p.T = T; p.H = H; p.W = W;
+  p.num_tiles = static_cast<int>((total + 127) / 128);
+  p.frames = frames; p.w = w_oihw; p.bias = bias;
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define PLC_FE(CF)                                                                                         \
+  case CF:                                                                                                 \
+    PLC_CUDA(cudaFuncSetAttribute(plc::frontend_tc_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  plc::kFeSmemBytes));                                                     \
+    plc::frontend_tc_kernel<CF><<<grid, plc::kFeThreads, plc::kFeSmemBytes, st>>>(p, tm);                  \
+    break;
+  switch (Cf) { PLC_FE(1) PLC_FE(2) PLC_FE(3) }
+#undef PLC_FE
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;
 }

@@ -424,6 +424,26 @@ def frames_to_nhwc(frames: Tensor, c_pad: int, out: Optional[Tensor] = None) -> 
     return out
 
 
+def frontend_tc_supported(cf: int, c: int, c_stride: int) -> bool:
+    return bool(_lib.load().plc_frontend_tc_supported(cf, c, c_stride))
+
+
+def frontend_tc(frames: Tensor, weight: Tensor, bias: Optional[Tensor], out: Tensor) -> Tensor:
+    """relu(init_conv(add_coord_channels(frame))) for all T frames (generator.py:166-168) in one tensor-core launch with
+    in-kernel im2col: frames [B,T,Cf,H,W] fp32, weight [64,Cf+2,3,3] fp32 -> out [T*B,H,W,64] bf16 (T-major)."""
+    lib = _lib.load()
+    B, T, Cf, H, W = frames.shape
+    _require_cuda(frames, "frames")
+    _require_cuda(out, "out")
+    if frames.dtype != torch.float32 or out.dtype != torch.bfloat16 or tuple(out.shape) != (T * B, H, W, 64):
+        raise RuntimeError("frontend_tc: frames must be fp32 [B,T,Cf,H,W], out bf16 [T*B,H,W,64]")
+    w = weight.detach().to(torch.float32).contiguous()
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    _lib.check(lib.plc_frontend_tc_fwd(_ptr(frames), B, T, Cf, H, W, _ptr(w), _ptr(b), 64, _ptr(out), _stream()),
+               "plc_frontend_tc_fwd")
+    return out
+
+
 def conv2d_same_into(x: Tensor, cp: ConvParams, out: Tensor) -> Tensor:
     """Inference-only conv into a preallocated buffer (no autograd node)."""
     lib = _lib.load()

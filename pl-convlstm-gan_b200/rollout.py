@@ -78,7 +78,13 @@ class NowcastRunner:
         self.feat = torch.zeros(model.t_in * B, H, W, model.encoder.cells[0].working_cin, dtype=adt, device=device)
         # bf16 mode: the front-end conv runs on the tensor-core conv (init_conv + ReLU), fed by a coord-plane prep kernel
         self.tc_frontend = model.mode == "bf16" and model.hidden_dims[0] % 8 == 0
-        if self.tc_frontend:
+        # ... or, for <= 3 frame channels into 64 features, on the dedicated kernel with in-kernel im2col
+        self.fused_frontend = (self.tc_frontend and
+                               F.frontend_tc_supported(model.in_channels, hd[0], self.feat.shape[-1]))
+        if self.fused_frontend:
+            self._fe_w = model.init_conv.weight.detach().to(torch.float32).contiguous()
+            self._fe_b = None if model.init_conv.bias is None else model.init_conv.bias.detach().float().contiguous()
+        elif self.tc_frontend:
             self.cp0 = model._init_cp()
             self.x8 = torch.zeros(model.t_in * B, H, W, self.cp0.cin_p, dtype=torch.bfloat16, device=device)
         # per layer: two h buffers (ping-pong; halo reads forbid in-place) and one c buffer (in-place is safe)
@@ -90,7 +96,8 @@ class NowcastRunner:
         self.zero_state = [F.zero_state_supported(pw) for pw in self.enc_pw]
         self.fc_pw = [c._packed(False) for c in model.forecaster.cells]
         self.cell_launches_per_run = L * (model.t_in + model.t_out)
-        self.launches_per_run = (2 if self.tc_frontend else 1) + self.cell_launches_per_run + 1
+        self.launches_per_run = (2 if (self.tc_frontend and not self.fused_frontend) else 1) + \
+            self.cell_launches_per_run + 1
 
     # ------------------------------------------------------------------ CUDA graph (launch-bound shapes)
     def capture(self, frames_like: Tensor):
@@ -135,7 +142,9 @@ class NowcastRunner:
         m, B, L = self.m, self.B, len(self.c)
         T_in, T_out = m.t_in, m.t_out
         # front-end for all T_in steps at once (T-major batch [T*B, ...])
-        if self.tc_frontend:
+        if self.fused_frontend:
+            F.frontend_tc(frames, self._fe_w, self._fe_b, self.feat)
+        elif self.tc_frontend:
             F.frames_to_nhwc(frames, self.cp0.cin_p, out=self.x8)
             F.conv2d_same_into(self.x8, self.cp0, self.feat)
         else:

@@ -232,3 +232,37 @@ def test_nowcast_generator_training_forward_and_grads_vs_eager_spec(cuda_device)
         if rel_err(p.grad, P[k].grad) >= 8e-2:
             bad.append(report(k, p.grad, P[k].grad))
     assert not bad, " | ".join(bad)
+
+
+@pytest.mark.parametrize("B,T,Cf,H,W", [(2, 3, 1, 20, 13), (1, 2, 2, 16, 16), (3, 1, 3, 9, 130), (1, 1, 1, 1, 7),
+                                        (32, 2, 1, 64, 64)])
+def test_frontend_tc_kernel_vs_torch(B, T, Cf, H, W, cuda_device):
+    """plc_frontend_tc_fwd (in-kernel im2col + coordinate planes + 3x3 conv + bias + ReLU for all T frames) against
+    the reference ops (coordconv.py:3-10, generator.py:166-168) on bf16-rounded operands: ragged sizes, tail tiles,
+    H = 1 (degenerate row coordinate), 1..3 frame channels."""
+    from plconv import functional as PF
+    dev = cuda_device
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    frames = (torch.rand(B, T, Cf, H, W, generator=g) * 4).to(dev)
+    w = (torch.randn(64, Cf + 2, 3, 3, generator=g) * 0.3).to(dev)
+    b = (torch.randn(64, generator=g) * 0.2).to(dev)
+    out = torch.full((T * B, H, W, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    PF.frontend_tc(frames, w, b, out)
+    # reference: T-major frames, coordinate planes row/(H-1), col/(W-1), conv on bf16-rounded inputs and weights
+    fr = frames.transpose(0, 1).reshape(T * B, Cf, H, W)
+    ys = torch.arange(H, device=dev, dtype=torch.float32) * (1.0 / (H - 1) if H > 1 else 0.0)
+    xs = torch.arange(W, device=dev, dtype=torch.float32) * (1.0 / (W - 1) if W > 1 else 0.0)
+    planes = torch.stack([ys.view(H, 1).expand(H, W), xs.view(1, W).expand(H, W)]).expand(T * B, 2, H, W)
+    xin = torch.cat([fr, planes], 1).to(torch.bfloat16).float()
+    ref = torch.relu(torch.nn.functional.conv2d(xin, w.to(torch.bfloat16).float(), b, padding=1))
+    got = out.float().permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref) < 1e-2, report("frontend", got, ref)
+
+
+def test_frontend_tc_loud_errors(cuda_device):
+    from plconv import functional as PF
+    frames = torch.rand(1, 1, 4, 8, 8, device=cuda_device)                       # 4 frame channels: not covered
+    with pytest.raises(RuntimeError, match="frame channels"):
+        PF.frontend_tc(frames, torch.zeros(64, 6, 3, 3, device=cuda_device), None,
+                       torch.empty(1, 8, 8, 64, device=cuda_device, dtype=torch.bfloat16))

@@ -36,3 +36,28 @@ if __name__ == "__main__":
     bench(320, 128, 128, 8, 64)
     bench(32, 128, 128, 256, 128)
     bench(32, 128, 128, 64, 64)
+
+
+def bench_fused(B=32, T=10, H=128, W=128, iters=20):
+    dev = torch.device("cuda:0")
+    frames = torch.rand(B, T, 1, H, W, device=dev)
+    w = torch.randn(64, 3, 3, 3, device=dev) * 0.2
+    b = torch.randn(64, device=dev) * 0.1
+    out = torch.empty(T * B, H, W, 64, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        F.frontend_tc(frames, w, b, out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(iters):
+        F.frontend_tc(frames, w, b, out)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / iters * 1e3
+    gb = (frames.numel() * 4 + out.numel() * 2) / 1e9
+    print(f"fused front-end (im2col in kernel) {B}x{T} frames {H}x{W} -> 64 ch: {us:.1f} us  ({gb / (us * 1e-6):.0f} GB/s "
+          f"in+out)")
+
+
+if __name__ == "__main__":
+    bench_fused()
