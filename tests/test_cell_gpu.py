@@ -364,3 +364,49 @@ def test_zero_state_form_is_bit_identical_to_zero_tensors(shape, patch, cuda_dev
     finally:
         lib.plc_debug_set_patch(-1)
     assert torch.equal(h_z, h_ref) and torch.equal(c_z, c_ref)
+
+
+def test_patch_vs_default_pipeline_random_shapes(cuda_device):
+    """Differential sweep: 40 seeded random shapes (ragged / tiny / multi-tile images, 1-3 units, both N-tile counts,
+    k = 3 and 5, both cta_group paths) through the haloed-patch pipeline and the default pipeline.  Same products,
+    different fp32 accumulation order: c within 3e-5, h within one bf16 ulp, gradients within 1e-2 of their max."""
+    plconv, F = _plconv()
+    lib = plconv._lib.load()
+    dev = cuda_device
+    rng = np.random.RandomState(1234)
+    for case in range(40):
+        B = int(rng.randint(1, 4))
+        H, W = int(rng.randint(1, 41)), int(rng.randint(1, 41))
+        cin = int(rng.choice([0, 64, 128]))
+        ch = int(rng.choice([64, 128]))
+        k = int(rng.choice([3, 5]))
+        cta = int(rng.choice([1, 2]))
+        g = torch.Generator().manual_seed(case)
+        w = torch.randn(4 * ch, cin + ch, k, k, generator=g) * (1.0 / ((cin + ch) * k * k) ** 0.5)
+        b = torch.randn(4 * ch, generator=g) * 0.2
+        pw = F.pack_weights(w.to(dev), b.to(dev), cin, ch, k, plconv.PLC_MODE_BF16_TC, with_dgrad=True)
+        x = torch.randn(B, H, W, cin, generator=g).to(dev).to(torch.bfloat16) if cin else None
+        h = torch.randn(B, H, W, ch, generator=g).to(dev).to(torch.bfloat16)
+        c = torch.randn(B, H, W, ch, generator=g).to(dev)
+        dh = (torch.randn(B, H, W, ch, generator=g) * 0.1).to(dev).to(torch.bfloat16)
+        dc = (torch.randn(B, H, W, ch, generator=g) * 0.1).to(dev)
+        res = []
+        lib.plc_debug_set_cta_group(cta)
+        try:
+            for mode in (0, 1):
+                lib.plc_debug_set_patch(mode)
+                h2, c2 = F.cell_forward(x, h, c, pw)
+                dW = torch.zeros(4 * ch, cin + ch, k, k, device=dev)
+                db = torch.zeros(4 * ch, device=dev)
+                dx, dhp, dcp = F.cell_backward(x, h, c, pw, dh, None, dc, dW, db, need_dx=cin > 0)
+                res.append([t.float().clone() for t in (h2, c2, dhp, dcp, dW, db) + ((dx,) if cin else ())])
+        finally:
+            lib.plc_debug_set_patch(-1)
+            lib.plc_debug_set_cta_group(0)
+        tag = f"case {case}: B{B} {H}x{W} Cin{cin} Ch{ch} k{k} cta{cta}"
+        a, p_ = res
+        assert float((a[0] - p_[0]).abs().max()) <= 2 ** -7, tag + " h"
+        assert float((a[1] - p_[1]).abs().max()) <= 3e-5 * max(1.0, float(a[1].abs().max())), tag + " c"
+        for i, nm in list(enumerate(("h", "c", "dh_prev", "dc_prev", "dW", "db", "dx")))[2:len(a)]:
+            err = float((a[i] - p_[i]).abs().max() / (a[i].abs().max() + 1e-20))
+            assert err <= 1e-2, f"{tag} {nm} {err:.3e}"
