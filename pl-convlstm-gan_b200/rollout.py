@@ -67,7 +67,10 @@ class NowcastGenerator(nn.Module):
 
 
 class NowcastRunner:
-    """Inference engine for :class:`NowcastGenerator` with every buffer preallocated."""
+    """Inference engine for :class:`NowcastGenerator` with every buffer preallocated.
+
+    The kernel-layout weight images (cells, front-end, head) are taken from the model when the runner is built:
+    build a new runner after the model's parameters change (training step, ``load_state_dict``)."""
 
     def __init__(self, model: NowcastGenerator, B: int, H: int, W: int, device):
         self.m, self.B, self.H, self.W, self.dev = model, B, H, W, device
