@@ -115,3 +115,34 @@ def test_product_generator_plus_product_loss_vs_reference(path, mode, tol, cuda_
         if rel_err(p.grad, ref) >= tol:
             bad.append(report(name, p.grad, ref))
     assert not bad, " | ".join(bad)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_generator_forward_graphed_matches_eager_and_tracks_weight_updates(mode, cuda_device):
+    """Generator.forward_graphed (whole inference forward replayed from a CUDA graph) == eager forward, bit for bit,
+    also after the weights changed through a FUSED optimizer step (which does not bump parameter versions: the key's
+    packed-weight generation must trigger the re-capture)."""
+    import plconv
+    torch.manual_seed(3)
+    gen = plconv.Generator(1, 1, 3, [16, 32], scale_factor=4, mode=mode).to(cuda_device)
+    gen.materialize(4, cuda_device)
+    gen.eval()
+    mk = lambda: (torch.rand(2, 3, 1, 15, 12, device=cuda_device) * 5, torch.rand(2, 1, 60, 48, device=cuda_device),
+                  torch.rand(2, 3, 60, 48, device=cuda_device))
+    a = mk()
+    with torch.no_grad():
+        want = gen(*a)
+    got = gen.forward_graphed(*a).clone()
+    assert torch.equal(got, want)
+    b = mk()                                                  # new inputs, same graph
+    with torch.no_grad():
+        want_b = gen(*b)
+    assert torch.equal(gen.forward_graphed(*b), want_b)
+    opt = torch.optim.Adam(gen.parameters(), lr=1e-2, fused=True)
+    for p_ in gen.parameters():
+        p_.grad = torch.randn_like(p_) * 0.1
+    opt.step()
+    with torch.no_grad():
+        want_c = gen(*b)
+    assert not torch.equal(want_c, want_b)
+    assert torch.equal(gen.forward_graphed(*b), want_c)       # re-captured with the new weights

@@ -76,3 +76,34 @@ if __name__ == "__main__":
         run(8, 5, 15, 12, [16, 32], 8, 5, mode)          # shipped default shapes (reference CPU: 415 ms/step, 19.3 seq/s)
     run(4, 10, 64, 64, [16, 32], 1, 5, "bf16")           # BASELINE cfg-1 shapes (reference CPU: 388 ms/step)
     run(16, 10, 64, 64, [64, 64], 4, 5, "bf16")          # hidden 64, x4 upsampling
+
+
+def run_infer(B, T, H, W, hd, scale, lu_ch, mode="bf16", iters=50):
+    """Inference forward: eager vs CUDA-graph replay (Generator.forward_graphed)."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    gen = plconv.Generator(1, 1, lu_ch, hd, scale_factor=scale, mode=mode).to(dev).eval()
+    gen.materialize(scale, dev)
+    a = (torch.rand(B, T, 1, H, W, device=dev) * 5, torch.rand(B, 1, H * scale, W * scale, device=dev),
+         torch.rand(B, lu_ch, H * scale, W * scale, device=dev))
+
+    def timeit(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / iters * 1e3
+
+    with torch.no_grad():
+        te = timeit(lambda: gen(*a))
+    tg = timeit(lambda: gen.forward_graphed(*a))
+    print(f"Generator inference   B{B} T{T} LR {H}x{W} hidden {hd} x{scale} mode={mode}: eager {te:.2f} ms, "
+          f"graph replay {tg:.2f} ms -> {B / tg * 1e3:.0f} sequences/s", flush=True)
+
+
+if __name__ == "__main__":
+    run_infer(8, 5, 15, 12, [16, 32], 8, 5)
+    run_infer(4, 10, 64, 64, [16, 32], 1, 5)
