@@ -32,10 +32,13 @@ __global__ void __launch_bounds__(128) probe(long long* out, int n_mma, int shif
     if (threadIdx.x == 0) {
       const long long t0 = clock64();
       for (int i = 0; i < n_mma; ++i) {
-        if (shifted) {   // conv patch views: A start shifted by (ky * 10 + kx) rows, 8-row groups 1280 B apart
+        if (shifted == 1) {   // conv patch views: A start shifted by (ky * 10 + kx) rows, 8-row groups 1280 B apart
           const int tap = i % 9;
           const uint64_t dav = make_smem_desc(smem_u32(smem) + ((tap / 3) * 10 + tap % 3) * 128, 0, 1280);
           umma_bf16<1>(tmem + (i % accs) * N, dav, db + 2 * (i & 3), idesc, i >= accs);
+        } else if (shifted >= 2) {   // one fixed view: start row = shifted >> 16, SBO = shifted & 0xffff
+          const uint64_t dav = make_smem_desc(smem_u32(smem) + (shifted >> 16) * 128, 0, shifted & 0xffff);
+          umma_bf16<1>(tmem + (i % accs) * N, dav + 2 * (i & 3), db + 2 * (i & 3), idesc, i >= accs);
         } else {
           umma_bf16<1>(tmem + (i % accs) * N, da + 2 * (i & 3), db + 2 * (i & 3), idesc, i >= accs);
         }
@@ -69,10 +72,12 @@ void run(int n_mma, int shifted = 0) {
   long long h[64];
   cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
   int slot = 0;
-  for (int accs = 1; accs <= 512 / N && accs <= 8; accs *= 2, ++slot)
+  for (int accs = 1; accs <= 512 / N && accs <= 8; accs *= 2, ++slot) {
+    if (shifted >= 2) printf("[start row %d, SBO %d] ", shifted >> 16, shifted & 0xffff);
     printf("%sM=128 N=%3d K=16, %3d MMAs round-robin over %d accumulator(s): issue %6.1f cyc/MMA, to completion %6.1f "
-           "cyc/MMA (ideal tensor time %d)\n", shifted ? "[shifted patch views] " : "", N, n_mma, accs, double(h[slot * 2]) / n_mma,
+           "cyc/MMA (ideal tensor time %d)\n", shifted == 1 ? "[shifted patch views] " : "", N, n_mma, accs, double(h[slot * 2]) / n_mma,
            double(h[slot * 2 + 1]) / n_mma, 128 * N * 16 * 2 / 8192);
+  }
   cudaFree(d);
 }
 
@@ -83,5 +88,8 @@ int main() {
   run<64>(63, 1);
   run<128>(63, 1);
   run<256>(63, 1);
+  // which property of a view is slow: the unaligned start row, or the group stride?
+  const int views[][2] = {{0, 1024}, {0, 1280}, {0, 2048}, {1, 1024}, {1, 2048}, {8, 1024}, {10, 1280}, {16, 2048}, {17, 2048}};
+  for (auto& v : views) run<128>(64, (v[0] << 16) | v[1]);
   return 0;
 }
