@@ -4,10 +4,10 @@
 //
 // Why a dedicated kernel: with CF + 2 = 3 input channels the generic implicit GEMM spends its time on operand plumbing
 // (one TMA box or one shifted UMMA view per tap, 9 short MMAs per tile behind a generic issue loop: ~2700 issue cycles
-// per 128 pixels, 570 us for 320 frames of 128 x 128).  Here K = 9 * (CF + 2) <= 64 fits ONE 128-byte row: eight producer warps read the raw
-// frames, generate the two coordinate planes analytically, and write each pixel's 9-tap row straight into a
-// SWIZZLE_128B K-major smem tile; the MMA warp needs K/16 <= 4 aligned MMAs per tile and the kernel becomes
-// output-bound (16 KB written per tile through a TMA tensor store).  Weights (<= 8 KB) stay resident in smem.
+// per 128 pixels, 570 us for 320 frames of 128 x 128).  Here K = 9 * (CF + 2) <= 64 fits ONE 128-byte row: eight
+// producer warps read the raw frames, generate the two coordinate planes analytically, and write each pixel's 9-tap
+// row straight into a SWIZZLE_128B K-major smem tile; the MMA warp needs K/16 <= 4 aligned MMAs per tile and the
+// kernel becomes output-bound (16 KB written per tile through a TMA tensor store).  Weights (<= 8 KB) stay resident.
 //
 // warp 0: MMA issuer + TMEM owner | warps 1-8: producers (two groups of 128 threads, one tile each) |
 // warps 9-12: epilogue (bias + ReLU + bf16, swizzled staging, TMA store)
