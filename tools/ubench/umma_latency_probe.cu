@@ -36,6 +36,10 @@ __global__ void __launch_bounds__(128) probe(long long* out, int n_mma, int shif
           const int tap = i % 9;
           const uint64_t dav = make_smem_desc(smem_u32(smem) + ((tap / 3) * 10 + tap % 3) * 128, 0, 1280);
           umma_bf16<1>(tmem + (i % accs) * N, dav, db + 2 * (i & 3), idesc, i >= accs);
+        } else if (shifted == -1) {   // MN-major A and B (the wgrad operand form): atoms 8 KB apart along M / N
+          umma_bf16<1>(tmem + (i % accs) * N, make_smem_desc(smem_u32(smem), 8192, 1024) + 128 * (i & 3),
+                       make_smem_desc(smem_u32(smem) + 16384, 8192, 1024) + 128 * (i & 3),
+                       make_idesc_bf16(128, N, 1, 1), i >= accs);
         } else if (shifted >= 2) {   // one fixed view: start row = shifted >> 16, SBO = shifted & 0xffff
           const uint64_t dav = make_smem_desc(smem_u32(smem) + (shifted >> 16) * 128, 0, shifted & 0xffff);
           umma_bf16<1>(tmem + (i % accs) * N, dav + 2 * (i & 3), db + 2 * (i & 3), idesc, i >= accs);
@@ -73,6 +77,7 @@ void run(int n_mma, int shifted = 0) {
   cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
   int slot = 0;
   for (int accs = 1; accs <= 512 / N && accs <= 8; accs *= 2, ++slot) {
+    if (shifted == -1) printf("[MN-major A and B] ");
     if (shifted >= 2) printf("[start row %d, SBO %d] ", shifted >> 16, shifted & 0xffff);
     printf("%sM=128 N=%3d K=16, %3d MMAs round-robin over %d accumulator(s): issue %6.1f cyc/MMA, to completion %6.1f "
            "cyc/MMA (ideal tensor time %d)\n", shifted == 1 ? "[shifted patch views] " : "", N, n_mma, accs, double(h[slot * 2]) / n_mma,
@@ -88,6 +93,9 @@ int main() {
   run<64>(63, 1);
   run<128>(63, 1);
   run<256>(63, 1);
+  run<64>(64, -1);
+  run<128>(64, -1);
+  run<256>(64, -1);
   // which property of a view is slow: the unaligned start row, or the group stride?
   const int views[][2] = {{0, 1024}, {0, 1280}, {0, 2048}, {1, 1024}, {1, 2048}, {8, 1024}, {10, 1280}, {16, 2048}, {17, 2048}};
   for (auto& v : views) run<128>(64, (v[0] << 16) | v[1]);
