@@ -447,17 +447,12 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
             const int ntap = (taps - tap) < G ? (taps - tap) : G;
             if (elect_one()) {       // ONE elected region per stage: all its taps' MMAs and the commits back to back
               int ky2 = ky, kx2 = kx;
-              // kprof trace: raw timestamps of one tile's issue sequence (leader CTA 0, 6th tile)
-              const bool trace = (kProfEnabled && p.prof) && blockIdx.x == 0 && it == 5;
-              unsigned long long* tr = p.prof + 148 * 16 + t * 16;
-              if (trace) tr[0] = clock64();
               for (int g = 0; g < ntap; ++g) {
                 const uint64_t adesc = pdesc + (((ky2 * pw + kx2) * row_bytes) >> 4);
                 for (int k = 0; k < ksteps; ++k)
                   umma_bf16<kCta>(d_tmem, adesc + 2u * k, bdesc + 2u * (g * ksteps + k), idesc,
                                   (u | (tap + g) | k) != 0);
                 if (++kx2 == p.ksize) { kx2 = 0; ++ky2; }
-                if (trace) tr[1 + g] = clock64();
               }
               if constexpr (kCta == 1) {
                 umma_commit<1>(&bempty_bar[bstage]);
@@ -465,10 +460,8 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                 if (last && u == units - 1) umma_commit<1>(&tmem_full[as]);
               } else {
                 umma_commit_mc2(&bempty_bar[bstage], 0b11);
-                if (trace) tr[6] = clock64();
                 if (last) umma_commit_mc2(&patch_empty[stage], 0b11);
                 if (last && u == units - 1) umma_commit_mc2(&tmem_full[as], 0b11);
-                if (trace) tr[7] = clock64();
               }
             }
             for (int g = 0; g < ntap; ++g)

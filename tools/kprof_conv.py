@@ -28,17 +28,12 @@ def main():
     out = torch.empty(N, H, W, cp.cout_p, device=dev, dtype=torch.bfloat16)
     for _ in range(3):
         F.conv2d_same_into(x, cp, out)
-    buf = torch.zeros(148 * 16 + 256, dtype=torch.int64, device=dev)
+    buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
     lib.plc_debug_set_prof(ctypes.c_void_p(buf.data_ptr()))
     F.conv2d_same_into(x, cp, out)
     torch.cuda.synchronize()
     lib.plc_debug_set_prof(None)
-    tr = buf[148 * 16:].view(16, 16).cpu()
-    for t in range(4):
-        row = tr[t]
-        if int(row[0]):
-            print('  trace stage', t, 'deltas:', [int(row[i] - row[0]) for i in range(1, 8) if int(row[i])])
-    p = buf[:148 * 16].view(148, 16).cpu().double()
+    p = buf.view(148, 16).cpu().double()
     lead = p[p[:, 0] > 0]
     tot, te, tf, tiles, tp = (lead[:, i].mean() for i in (0, 1, 2, 3, 13))
     print(f"leader CTAs {len(lead)}; MMA warp: total {tot:.0f} cyc, tiles {tiles:.1f}, per tile {tot / tiles:.0f}")
