@@ -12,7 +12,26 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import plconv  # noqa: E402
-from oracle import loss_oracle as L  # noqa: E402   (tools/ is developer infrastructure, like tests/)
+
+
+def eager_combined_loss(pred, lr, coords, obs, scale, lambdas=(1.0, 1.0, 0.1, 0.05)):
+    """The reference's loss as plain eager torch ops (combined_loss.py:64-191, log weights) -- the comparison arm of
+    this benchmark (written out here: only tests/ and bench.py may use oracle/)."""
+    import torch.nn.functional as F
+    b, t, c, h, w = pred.shape
+    hl, wl = lr.shape[-2:]
+    pooled = F.interpolate(pred.reshape(b * t, c, h, w), size=(hl, wl), mode="area").reshape(b, t, c, hl, wl)
+    cons = (pooled - lr).abs().mean()
+    sc = ((coords.float() + 0.5) * scale - 0.5).long()
+    ok = (sc[:, 0] >= 0) & (sc[:, 0] < h) & (sc[:, 1] >= 0) & (sc[:, 1] < w)
+    at = pred[:, :, 0][:, :, sc[ok, 0], sc[ok, 1]]
+    o = obs[:, ok].unsqueeze(0).expand(b, -1, -1)
+    m = ~torch.isnan(o)
+    point = ((at[m] - o[m]).abs() * (1.0 + torch.log1p(o[m]))).mean()
+    smooth = (pred[..., :, :-1] - pred[..., :, 1:]).abs().mean() + (pred[..., :-1, :] - pred[..., 1:, :]).abs().mean()
+    temp = (pred[:, :-1] - pred[:, 1:]).abs().mean()
+    lp, lc, ls, lt = lambdas
+    return lp * point + lc * cons + ls * smooth + lt * temp
 
 
 def timeit(fn, n=20):
@@ -48,7 +67,7 @@ def main():
 
         def eager():
             pred.grad = None
-            total, _ = L.combined_loss(pred, lr, coords, obs, scale_factor=s)
+            total = eager_combined_loss(pred, lr, coords, obs, s)
             total.backward()
 
         tf, te = timeit(fused), timeit(eager)
