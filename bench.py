@@ -6,8 +6,8 @@
 Workload (BASELINE.json configs[1], the largest single-GPU config the metric is quoted on):
   encoder-forecaster generator inference, 128x128 frames, hidden [64, 64], kernel 3, T = 10 -> 10,
   batch 32 sequences per GPU, bf16 tensor-core mode, synthetic radar-like frames, random-init weights.
-One "step" = one batch through front-end conv -> 20 encoder cell steps -> 20 forecaster cell steps -> head
-(42 kernel launches).  N > 1: every rank runs its own batch (weak scaling, no data-path collective:
+One "step" = one batch through the front-end kernel -> 20 encoder cell steps -> 20 forecaster cell steps -> head
+(42 kernel launches).  `--workload train` = configs[2]-style training step, `--workload radar` = configs[3].  N > 1: every rank runs its own batch (weak scaling, no data-path collective:
 inference shards by batch).
 
 Prints ONE JSON line (rank 0).  `value` = sequences/s with inputs resident in HBM; `e2e` = the same through
