@@ -185,3 +185,38 @@ def test_loss_oracle_terms_and_gradient_match_reference_golden(path):
         assert abs(float(parts[k]) - float(g[k])) <= 1e-6 * max(1.0, abs(float(g[k]))), k
     assert abs(float(total) - float(g["total"])) <= 1e-6 * abs(float(g["total"]))
     assert torch.allclose(pred.grad, T(g["dpred"]), rtol=1e-6, atol=1e-9)
+
+
+def test_loss_oracle_matches_live_reference_random_configs():
+    """Random shapes / strategies / lambdas against the LIVE reference CombinedLoss (only where /root/reference
+    exists; the committed loss_*.npz fixtures pin the same thing on the GPU box)."""
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, REF)
+    sys.dont_write_bytecode = True
+    from src.losses.combined_loss import CombinedLoss
+    from oracle import loss_oracle as L
+    rng = np.random.RandomState(7)
+    for case in range(8):
+        B, Tn = int(rng.randint(1, 4)), int(rng.randint(2, 5))
+        H, W, s = int(rng.randint(3, 9)), int(rng.randint(3, 9)), int(rng.choice([1, 2, 3, 4]))
+        n_st = int(rng.randint(1, 9))
+        strategy = str(rng.choice(["log", "sqrt", "stratified", "none"]))
+        weighted = bool(rng.randint(0, 2))
+        lambdas = tuple(float(v) for v in rng.rand(4) * 2)
+        torch.manual_seed(case)
+        pred = (torch.rand(B, Tn, 1, H * s, W * s) * 6).requires_grad_(True)
+        pred2 = pred.detach().clone().requires_grad_(True)
+        lr = torch.rand(B, Tn, 1, H, W) * 6
+        coords = torch.stack([torch.randint(-1, H + 1, (n_st,)), torch.randint(-1, W + 1, (n_st,))], 1)
+        obs = torch.rand((B, Tn, n_st) if case % 2 else (Tn, n_st)) * 60
+        obs[..., 0] = float("nan") if case % 3 == 0 else obs[..., 0]
+        ref_total, ref_parts = CombinedLoss(*lambdas, use_weighted_loss=weighted, weight_strategy=strategy)(
+            pred, lr, coords, obs, scale_factor=s)
+        got_total, got_parts = L.combined_loss(pred2, lr, coords, obs, scale_factor=s, lambdas=lambdas,
+                                               strategy=strategy, use_weighted=weighted)
+        for k in ("point", "conserve", "smooth", "temporal"):
+            assert torch.allclose(got_parts[k], ref_parts[k], rtol=1e-6, atol=1e-7), (case, k)
+        ref_total.backward()
+        got_total.backward()
+        assert torch.allclose(pred2.grad, pred.grad, rtol=1e-6, atol=1e-9), case
