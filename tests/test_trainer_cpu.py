@@ -195,3 +195,83 @@ def test_fused_optimizer_step_invalidates_packed_weight_caches():
     g1 = _lib.weight_generation()
     plconv.invalidate_packed_weights()
     assert _lib.weight_generation() == g1 + 1
+
+
+class _LazyStubGen(_StubGen):
+    """Like the reference Generator: one block only exists after ``materialize`` (generator.py:129-130)."""
+
+    def __init__(self):
+        super().__init__()
+        self.up = None
+
+    def materialize(self, scale_factor, device=None):
+        if self.up is None:
+            torch.manual_seed(77)
+            self.up = torch.nn.Conv2d(1, 1, 3, padding=1)
+        return 1
+
+    def forward(self, rain, dem, lu):
+        out = super().forward(rain, dem, lu)
+        B, T = out.shape[:2]
+        return self.up(out.flatten(0, 1)).view_as(out)
+
+
+def _quirk_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(5)
+        tr = Trainer(TrainerConfig(scale_factor=2, epochs=1, optimizer_sees_upsample=False), device="cpu",
+                     model=_LazyStubGen(), loss_module=_StubLoss())
+        up0 = [p.detach().clone() for p in tr.model.up.parameters()]
+        data = _batches(3, seed=10 + rank, B=1)
+        for b in data:
+            tr.train_step(tuple(b))
+        flat = torch.cat([p.detach().flatten() for p in tr.model.parameters()])
+        fg = tr.frozen_reducer.buckets[0]["flat"].clone()
+        both, bothg = [torch.zeros_like(flat) for _ in range(world)], [torch.zeros_like(fg) for _ in range(world)]
+        torch.distributed.all_gather(both, flat)
+        torch.distributed.all_gather(bothg, fg)
+        if rank == 0:
+            ret["params_same"] = bool(torch.equal(both[0], both[1]))
+            ret["frozen_grads_same"] = bool(torch.allclose(bothg[0], bothg[1], rtol=1e-6, atol=1e-9))
+            ret["frozen_untouched"] = all(torch.equal(a, b) for a, b in zip(up0, tr.model.up.parameters()))
+            ret["frozen_grad_norm"] = float(fg.norm())
+    finally:
+        torch.distributed.destroy_process_group()
+
+
+def test_reference_quirk_mode_under_data_parallelism():
+    """optimizer_sees_upsample=False with 2 ranks: the never-optimised block stays at its initial values, its
+    never-zeroed gradient buffer is averaged consistently (so every rank computes the same clip coefficient), and the
+    trained parameters stay identical across ranks."""
+    port = 29850 + os.getpid() % 100
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_quirk_worker, args=(2, port, ret), nprocs=2, join=True)
+        assert ret["params_same"] and ret["frozen_grads_same"] and ret["frozen_untouched"]
+        assert ret["frozen_grad_norm"] > 0
+
+
+def test_reference_quirk_mode_single_process_accumulates_and_clips_frozen_grads():
+    """Same quirk, one process, against a hand-rolled replay of trainer.py:290-315 with a late-created block."""
+    torch.manual_seed(5)
+    tr = Trainer(TrainerConfig(scale_factor=2, epochs=1, optimizer_sees_upsample=False), device="cpu",
+                 model=_LazyStubGen(), loss_module=_StubLoss())
+    torch.manual_seed(5)
+    ref = _LazyStubGen()
+    opt = torch.optim.Adam(ref.parameters(), lr=5e-4)          # built BEFORE the block exists, as the reference does
+    ref.materialize(2)
+    ref.load_state_dict(tr.model.state_dict())
+    loss_mod = _StubLoss()
+    for b in _batches(3, seed=3):
+        tr.train_step(tuple(b))
+        opt.zero_grad()
+        loss, _ = loss_mod(ref(*b[:3]), b[0], b[3], b[4], 2.0)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.5)
+        opt.step()
+    for (n, a), (_, b_) in zip(tr.model.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(a, b_, atol=1e-7), n
+    for a, b_ in zip(tr.model.up.parameters(), ref.up.parameters()):
+        assert torch.allclose(a.grad, b_.grad, rtol=1e-5, atol=1e-8)      # accumulated and rescaled by every clip
