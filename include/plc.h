@@ -146,6 +146,31 @@ int plc_conv_wgrad_unpack(const PlcConvDesc* d, const float* dW_acc, float* dW_o
 int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void* w_packed_dgrad, void* dx,
                  float* dW_acc, float* db_acc, void* stream);
 
+/* ---- per-launch timing (bench.py's roofline / step breakdown) -------------------------------------
+ * plc_timing_enable(1) clears the record and makes every kernel launch of the library record a CUDA event pair on
+ * its launching stream, tagged with a PlcKernelKind; plc_timing_enable(0) stops recording (and clears).
+ * plc_timing_collect synchronises the recorded events, writes up to `capacity` (kind, milliseconds) pairs in launch
+ * order, clears the record and returns the number of launches recorded (which may exceed `capacity`).  A kind groups
+ * the launches one ABI call makes for that purpose (normally exactly one kernel).  Never enable it inside a region
+ * whose time is reported: the events cost host time and serialise nothing but are not free.                    */
+typedef enum PlcKernelKind {
+  PLC_K_CELL_FWD = 0,       /* fused cell step, full K loop (x and h taps)                                    */
+  PLC_K_CELL_FWD_ZERO = 1,  /* fused cell step, zero-initial-state form (x taps only)                          */
+  PLC_K_BWD_GATES = 2,      /* gate recompute + dZ / dc_prev                                                   */
+  PLC_K_BWD_DGRAD = 3,      /* dx, dh_prev                                                                     */
+  PLC_K_BWD_WGRAD = 4,      /* dW, db                                                                          */
+  PLC_K_CONV_FWD = 5,       /* plain / strided / 3-D conv forward (generator body, discriminator)             */
+  PLC_K_CONV_DGRAD = 6,
+  PLC_K_CONV_WGRAD = 7,
+  PLC_K_FRONTEND = 8,
+  PLC_K_HEAD = 9,
+  PLC_K_LOSS = 10,
+  PLC_K_PACK = 11,          /* weight packing                                                                  */
+  PLC_K_ELEMENTWISE = 12    /* layout conversions, gradient masks, accumulator unpack                          */
+} PlcKernelKind;
+int plc_timing_enable(int on);
+int plc_timing_collect(int* kinds, float* ms, int capacity);
+
 /* ---- debug ---------------------------------------------------------------------------------
  * Developer aid (tools/kprof.py): when set to a zeroed device buffer of at least 148*16 uint64, the tensor-core conv
  * kernels record per-CTA cycle counters (MMA warp total / waiting for TMEM / waiting for TMA, epilogue busy / idle).

@@ -58,6 +58,8 @@ SIGNATURES = {
     "plc_conv_fwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "plc_conv_grad_mask": (_int, [_cp, _vp, _vp, _vp, _vp]),
     "plc_conv_bwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "plc_timing_enable": (_int, [_int]),
+    "plc_timing_collect": (_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float), _int]),
     "plc_debug_set_prof": (_int, [_vp]),
     "plc_debug_set_cta_group": (_int, [_int]),
     "plc_debug_set_patch": (_int, [_int]),

@@ -4,12 +4,14 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/plc.h"
 #include "conv_igemm_tc.cuh"
@@ -57,38 +59,142 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+constexpr int kMaxDevices = 64;
+
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
 
-// NHWC bf16 activation [B,H,W,C] as a 4-D tensor map; box = [64 ch, tw, th, 1], SWIZZLE_128B.
+// SM count of the CURRENT device (one process per GPU is the normal deployment, but nothing here assumes device 0)
+int sm_count() {
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device) instead of once per launch.
+// `Tag` makes the flag array unique per call site / template instantiation.
+template <int V> struct IntTag {};
+struct TagW1 {};
+struct TagW2 {};
+template <typename Tag, typename Fn>
+cudaError_t set_smem_once(Fn fn, int bytes) {
+  static std::atomic<int> done[kMaxDevices];
+  const int dev = current_device();
+  if (done[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[dev].store(bytes, std::memory_order_release);
+  return e;
+}
+
+// ------------------------------------------------------------------ per-launch timing (plc_timing_*)
+// When enabled, every kernel launch of the library is bracketed by a pair of CUDA events on the launching stream and
+// tagged with its kind; bench.py reads the list back to attribute the step time to kernels and to compute the
+// roofline of the dominant one from live per-launch durations.  Off by default: zero cost beyond one relaxed load.
+std::atomic<int> g_timing_on{0};
+std::mutex g_timing_mu;
+struct TimedLaunch { cudaEvent_t e0, e1; int kind; };
+std::vector<TimedLaunch> g_timed;
+
+struct LaunchTimer {
+  cudaStream_t st;
+  int kind;
+  cudaEvent_t e0 = nullptr;
+  LaunchTimer(int kind_, cudaStream_t st_) : st(st_), kind(kind_) {
+    if (g_timing_on.load(std::memory_order_relaxed)) {
+      if (cudaEventCreate(&e0) != cudaSuccess || cudaEventRecord(e0, st) != cudaSuccess) { cudaGetLastError(); e0 = nullptr; }
+    }
+  }
+  ~LaunchTimer() {
+    if (!e0) return;
+    cudaEvent_t e1 = nullptr;
+    if (cudaEventCreate(&e1) != cudaSuccess || cudaEventRecord(e1, st) != cudaSuccess) {
+      cudaGetLastError();
+      cudaEventDestroy(e0);
+      return;
+    }
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timed.push_back({e0, e1, kind});
+  }
+};
+
+// ------------------------------------------------------------------ tensor-map cache
+// cuTensorMapEncodeTiled is a pure host-side encoder of (pointer, dims, strides, box, swizzle): the result can be
+// reused whenever the same buffer is passed with the same geometry -- which is every call of a rollout after the first
+// (state rings, workspaces and packed weights are preallocated).  Thread-local, direct-mapped, no eviction policy.
+struct TmapKey {
+  const void* ptr;
+  long long a, b;       // leading dims (B / rows, cols)
+  int v[8];
+};
+struct TmapEntry { TmapKey key; CUtensorMap tm; bool valid; };
+constexpr int kTmapCacheSize = 1024;
+thread_local TmapEntry g_tmap_cache[kTmapCacheSize];
+
+inline unsigned tmap_hash(const TmapKey& k) {
+  unsigned long long h = reinterpret_cast<unsigned long long>(k.ptr) * 0x9E3779B97F4A7C15ull;
+  h ^= static_cast<unsigned long long>(k.a) * 0xC2B2AE3D27D4EB4Full + static_cast<unsigned long long>(k.b) * 0x165667B19E3779F9ull;
+  for (int i = 0; i < 8; ++i) h = (h ^ static_cast<unsigned>(k.v[i])) * 0x100000001B3ull;
+  return static_cast<unsigned>(h >> 40) & (kTmapCacheSize - 1);
+}
+inline bool tmap_lookup(const TmapKey& k, CUtensorMap* tm) {
+  const TmapEntry& e = g_tmap_cache[tmap_hash(k)];
+  if (e.valid && memcmp(&e.key, &k, sizeof(TmapKey)) == 0) { *tm = e.tm; return true; }
+  return false;
+}
+inline void tmap_store(const TmapKey& k, const CUtensorMap& tm) {
+  TmapEntry& e = g_tmap_cache[tmap_hash(k)];
+  e.key = k; e.tm = tm; e.valid = true;
+}
+
+// NHWC activation [B,(T,)H,W,C] as a 4-D (T == 0) or 5-D tensor map [C, W, H, (T,) B]; box = [box_c, tw, th, 1(, 1)]
+// pixels.  `estride` > 1 makes the box pick every estride-th pixel along W and H (strided convolutions: the box of a
+// filter tap covers tw x th OUTPUT pixels, i.e. an input extent of tw*estride x th*estride).
 int make_tmap_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int tw, int th, int esize = 2,
-                  int box_c = 64, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                  int box_c = 64, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int estride = 1, int T = 0) {
+  TmapKey key{};
+  key.ptr = ptr; key.a = B; key.b = T;
+  key.v[0] = H; key.v[1] = W; key.v[2] = C; key.v[3] = tw; key.v[4] = th; key.v[5] = esize | (estride << 8);
+  key.v[6] = box_c; key.v[7] = static_cast<int>(swz) | 0x100;
+  if (tmap_lookup(key, tm)) return PLC_OK;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t es = (cuuint64_t)esize;
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
-  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)tw, (cuuint32_t)th, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 1};
+  cuuint64_t strides[4] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es, 0};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(tw * estride), (cuuint32_t)(th * estride), 1, 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
+  int rank = 4;
+  if (T > 0) {
+    rank = 5;
+    dims[3] = (cuuint64_t)T; dims[4] = (cuuint64_t)B;
+    strides[3] = (cuuint64_t)T * H * W * C * es;
+  }
+  if (box[1] > 256 || box[2] > 256) return fail(PLC_ERR_UNSUPPORTED, "TMA box %ux%u exceeds 256", box[1], box[2]);
+  CUresult r = enc(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
                    const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled(act B=%d H=%d W=%d C=%d box=%dx%d) -> %d", B, H, W, C, tw, th,
-                (int)r);
+    return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled(act B=%d T=%d H=%d W=%d C=%d box=%dx%d stride=%d) -> %d", B, T, H,
+                W, C, tw, th, estride, (int)r);
+  tmap_store(key, *tm);
   return PLC_OK;
 }
 
 // row-major bf16 matrix [rows, cols] (cols contiguous); box = [box_cols, box_rows], SWIZZLE_128B.
 int make_tmap_mat(CUtensorMap* tm, const void* ptr, long rows, long cols, int box_cols, int box_rows) {
+  TmapKey key{};
+  key.ptr = ptr; key.a = rows; key.b = cols;
+  key.v[0] = box_cols; key.v[1] = box_rows; key.v[7] = 0x200;
+  if (tmap_lookup(key, tm)) return PLC_OK;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -101,6 +207,7 @@ int make_tmap_mat(CUtensorMap* tm, const void* ptr, long rows, long cols, int bo
   if (r != CUDA_SUCCESS)
     return fail(PLC_ERR_CUDA, "cuTensorMapEncodeTiled(mat %ldx%ld box=%dx%d) -> %d", rows, cols, box_rows, box_cols,
                 (int)r);
+  tmap_store(key, *tm);
   return PLC_OK;
 }
 
@@ -325,14 +432,14 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ s
 // cta_group choice: a CTA pair (cta_group::2) halves the per-SM weight-tile traffic and wins once there are
 // enough 128-pixel tiles to keep all 74 pairs busy; tiny problems keep 148 independent CTAs.
 // PLC_CTA_GROUP=1|2 overrides (used by the benchmarks to A/B the two paths).
-int g_cta_override = 0;   // plc_debug_set_cta_group
+std::atomic<int> g_cta_override{0};   // plc_debug_set_cta_group (process-wide on purpose: backward runs on autograd threads)
 int pick_cta_group(int num_m_tiles) {
-  static int forced = -1;
-  if (forced < 0) {
+  static const int forced = [] {
     const char* e = getenv("PLC_CTA_GROUP");
-    forced = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
-  }
-  if (g_cta_override) return g_cta_override;
+    return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  }();
+  const int ov = g_cta_override.load(std::memory_order_relaxed);
+  if (ov) return ov;
   if (forced) return forced;
   return num_m_tiles >= 2 * sm_count() ? 2 : 1;
 }
@@ -340,7 +447,7 @@ int pick_cta_group(int num_m_tiles) {
 
 template <int NT, int EPI, int CTA>
 int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                        const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st) {
+                        const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st, int kind) {
   using Cfg = plc::ConvTcCfg<NT, CTA, EPI>;
   plc::ConvTcParams p = p_in;
   p.prof = g_prof_buf;
@@ -360,7 +467,7 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
     if (nb < 2) return fail(PLC_ERR_UNSUPPORTED, "patch mode does not fit (N_TILE=%d cta=%d)", NT, CTA);
     p.b_stages = nb > 8 ? 8 : nb;
   }
-  PLC_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  PLC_CUDA(set_smem_once<Cfg>(kfn, Cfg::kSmemBytes));
   const int tiles = CTA == 2 ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_tiles;
   const int slots = sm_count() / CTA;
   const int grid = (tiles < slots ? tiles : slots) * CTA;
@@ -377,6 +484,7 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  LaunchTimer timer(kind, st);
   PLC_CUDA(cudaLaunchKernelEx(&cfg, kfn, p, a0, a1, b, o0, o1));
   return PLC_OK;
 }
@@ -384,11 +492,11 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
 // o0 / o1: output tensor maps of the TMA-store epilogue (forward, N_TILE = 256); ignored by the other instantiations
 template <int EPI>
 int launch_conv_tc(int n_tile, int cta, const plc::ConvTcParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
-                   const CUtensorMap& b, const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st) {
+                   const CUtensorMap& b, const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st, int kind) {
 #define PLC_LAUNCH_TC(NT)                                                                     \
   case NT:                                                                                    \
-    return cta == 2 ? launch_conv_tc_inst<NT, EPI, 2>(p, a0, a1, b, o0, o1, st)               \
-                    : launch_conv_tc_inst<NT, EPI, 1>(p, a0, a1, b, o0, o1, st);
+    return cta == 2 ? launch_conv_tc_inst<NT, EPI, 2>(p, a0, a1, b, o0, o1, st, kind)         \
+                    : launch_conv_tc_inst<NT, EPI, 1>(p, a0, a1, b, o0, o1, st, kind);
   switch (n_tile) {
     PLC_LAUNCH_TC(64)
     PLC_LAUNCH_TC(128)
@@ -417,7 +525,7 @@ void set_kgeom(plc::ConvTcParams* p, const KGeom& kg) {
 // Haloed-patch pipeline (conv_igemm_tc.cuh, "patch mode"): applies to 3x3 / 5x5 kernels whose sources are read as
 // 64-channel boxes (kc == 64), or as ONE narrower box (a single source of <= 32 channels, e.g. the frame front-end); it needs 16 x 8-pixel tiles, so it is skipped when that tiling wastes > 5 % more
 // pixels than the default one.  PLC_PATCH=0|1 / plc_debug_set_patch override (A/B runs, parity tests of both paths).
-int g_patch_override = -1;   // plc_debug_set_patch
+std::atomic<int> g_patch_override{-1};   // plc_debug_set_patch
 // bytes of the operand pipeline region of one instantiation (what patch mode re-carves into patch slots + weight stages)
 template <int EPI, int CTA>
 int pipeline_region_nt(int nt, int* b_bytes) {
@@ -441,12 +549,12 @@ int pipeline_region(int epi, int nt, int cta, int* b_bytes) {
   return cta == 2 ? pipeline_region_nt<plc::EPI_PLAIN, 2>(nt, b_bytes) : pipeline_region_nt<plc::EPI_PLAIN, 1>(nt, b_bytes);
 }
 void maybe_patch(TcGeom* g, plc::ConvTcParams* p, int epi, int n_tile) {
-  static int env_mode = -2;
-  if (env_mode == -2) {
+  static const int env_mode = [] {
     const char* e = getenv("PLC_PATCH");
-    env_mode = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
-  }
-  const int mode = g_patch_override >= 0 ? g_patch_override : env_mode;
+    return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
+  }();
+  const int ov = g_patch_override.load(std::memory_order_relaxed);
+  const int mode = ov >= 0 ? ov : env_mode;
   p->patch = 0;
   if (mode == 0 || (p->ksize != 3 && p->ksize != 5)) return;
   // 64-channel boxes: any number of (source, chunk) units; narrower boxes: a single unit (one narrow source)
@@ -507,16 +615,16 @@ int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p, int epi
 struct WgradShape { int B, H, W, k, Cin, Ch, N; };   // sources x [.,Cin] and h [.,Ch]; N = dZ channels
 
 int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev, const void* dz, float* dW, float* db,
-                          cudaStream_t st);
+                          cudaStream_t st, int kind);
 
 int launch_wgrad_tc(const PlcCellDesc* d, const void* x, const void* h_prev, const void* dz, float* dW, float* db,
                     cudaStream_t st) {
   WgradShape w{d->B, d->H, d->W, d->k, d->Cin, d->Ch, 4 * d->Ch};
-  return launch_wgrad_tc_shape(&w, x, h_prev, dz, dW, db, st);
+  return launch_wgrad_tc_shape(&w, x, h_prev, dz, dW, db, st, PLC_K_BWD_WGRAD);
 }
 
 int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev, const void* dz, float* dW, float* db,
-                          cudaStream_t st) {
+                          cudaStream_t st, int kind) {
   int rc;
   TcGeom g;
   pick_spatial_tile(d->H, d->W, &g, 6);   // 64-pixel blocks
@@ -555,8 +663,9 @@ int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev
     t0 = t1;
   }
   if (d->Ch == 0) t1 = t0;
+  LaunchTimer timer(kind, st);
   if (pair) {
-    PLC_CUDA(cudaFuncSetAttribute(plc::wgrad_tc_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, plc::kW2SmemBytes));
+    PLC_CUDA(set_smem_once<TagW2>(plc::wgrad_tc_kernel2, plc::kW2SmemBytes));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * tiles * S);
@@ -570,7 +679,7 @@ int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev
     cfg.numAttrs = 1;
     PLC_CUDA(cudaLaunchKernelEx(&cfg, plc::wgrad_tc_kernel2, p, tz, t0, t1));
   } else {
-    PLC_CUDA(cudaFuncSetAttribute(plc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plc::kWgSmemBytes));
+    PLC_CUDA(set_smem_once<TagW1>(plc::wgrad_tc_kernel, plc::kWgSmemBytes));
     plc::wgrad_tc_kernel<<<tiles * S, 256, plc::kWgSmemBytes, st>>>(p, tz, t0, t1);
     PLC_CUDA(cudaGetLastError());
   }
@@ -617,6 +726,7 @@ int plc_pack_weight(const PlcCellDesc* d, int pack_kind, const float* w_oihw, vo
   if (!w_oihw || !w_packed) return fail(PLC_ERR_NULL_ARG, "plc_pack_weight: null pointer");
   if (pack_kind != PLC_PACK_FWD && pack_kind != PLC_PACK_DGRAD) return fail(PLC_ERR_BAD_DESC, "bad pack kind");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchTimer timer(PLC_K_PACK, st);
   const int threads = 256, blocks = 148 * 4;
   if (d->mode == PLC_MODE_FP32) {
     if (pack_kind == PLC_PACK_FWD)
@@ -714,7 +824,8 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     if ((rc = make_tmap_act(&to0, c_out, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
     if ((rc = make_tmap_act(&to1, h_out, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, 64))) return rc;
   }
-  return launch_conv_tc<plc::EPI_LSTM_FWD>(g.n_tile, cta, p, ta0, ta1, tb, to0, to1, st);
+  return launch_conv_tc<plc::EPI_LSTM_FWD>(g.n_tile, cta, p, ta0, ta1, tb, to0, to1, st,
+                                           zero_state ? PLC_K_CELL_FWD_ZERO : PLC_K_CELL_FWD);
 }
 
 size_t plc_bwd_workspace_bytes(const PlcCellDesc* d) {
@@ -825,7 +936,8 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
       return rc;
     if ((rc = make_tmap_act(&tdc, dc_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
   }
-  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, tzo, tdc, st))) return rc;
+  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, tzo, tdc, st, PLC_K_BWD_GATES)))
+    return rc;
 
   // 2) dgrad: conv of dZ (4Ch channels) with the flipped/transposed image -> dx, dh_prev
   if (dx || dh_prev) {
@@ -848,7 +960,7 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     if ((rc = make_tmap_mat(&tbd, w_packed_dgrad, n_total, (long)q.num_kb * 64, 64, nt / ctaq))) return rc;
     CUtensorMap tq0 = tz, tq1 = tz;
     if ((rc = setup_plain_stores(&q, d->B, d->H, d->W, &tq0, &tq1))) return rc;
-    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, ctaq, q, tz, tz, tbd, tq0, tq1, st))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, ctaq, q, tz, tz, tbd, tq0, tq1, st, PLC_K_BWD_DGRAD))) return rc;
   }
 
   // 3) wgrad + bias grad
@@ -866,6 +978,7 @@ static size_t wgrad_acc_elems(int mode, int Cin, int Ch, int N, int k) {
 }
 static int wgrad_unpack(int mode, int Cin, int Ch, int N, int k, const float* acc, float* dW, cudaStream_t st) {
   if (!acc || !dW) return fail(PLC_ERR_NULL_ARG, "wgrad unpack: null pointer");
+  LaunchTimer timer(PLC_K_ELEMENTWISE, st);
   if (mode == PLC_MODE_FP32)
     plc::add_inplace_kernel<<<148 * 4, 256, 0, st>>>(acc, dW, wgrad_acc_elems(mode, Cin, Ch, N, k));
   else
@@ -914,6 +1027,7 @@ int plc_conv_pack_weight(const PlcConvDesc* d, int pack_kind, const float* w_oih
   if (!w_oihw || !w_packed) return fail(PLC_ERR_NULL_ARG, "plc_conv_pack_weight: null pointer");
   if (!aligned16(w_packed) || !aligned16(bias_packed)) return fail(PLC_ERR_ALIGNMENT, "packed buffers must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchTimer timer(PLC_K_PACK, st);
   if (pack_kind == PLC_PACK_FWD)
     pack_w_conv_fwd_kernel<<<148 * 4, 256, 0, st>>>(w_oihw, bias, static_cast<__nv_bfloat16*>(w_packed), bias_packed,
                                                     d->Cin, d->Cout, d->k, kgeom(d->Cin, 0, d->k), d->pixel_shuffle);
@@ -955,7 +1069,8 @@ int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, 
   if ((rc = make_tmap_mat(&tb, w_packed_fwd, d->Cout, (long)q.num_kb * 64, 64, nt / cta))) return rc;
   CUtensorMap to0 = ta, to1 = ta;
   if ((rc = setup_plain_stores(&q, d->B, d->H, d->W, &to0, &to1))) return rc;
-  return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, to0, to1, static_cast<cudaStream_t>(stream));
+  return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, to0, to1, static_cast<cudaStream_t>(stream),
+                                        PLC_K_CONV_FWD);
 }
 
 size_t plc_conv_wgrad_acc_bytes(const PlcConvDesc* d) {
@@ -973,6 +1088,7 @@ int plc_conv_grad_mask(const PlcConvDesc* d, const void* y, const void* dy, void
   if (rc) return rc;
   if (!y || !dy || !dz) return fail(PLC_ERR_NULL_ARG, "plc_conv_grad_mask: null pointer");
   const size_t npix = static_cast<size_t>(d->B) * d->H * d->W;
+  LaunchTimer timer(PLC_K_ELEMENTWISE, static_cast<cudaStream_t>(stream));
   conv_grad_mask_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dz), npix,
       d->H, d->W, d->Cout, d->relu, d->pixel_shuffle);
@@ -1009,25 +1125,52 @@ int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void
     if ((rc = make_tmap_mat(&tb, w_packed_dgrad, d->Cin, (long)q.num_kb * 64, 64, nt / cta))) return rc;
     CUtensorMap to0 = tz, to1 = tz;
     if ((rc = setup_plain_stores(&q, d->B, d->H, d->W, &to0, &to1))) return rc;
-    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tb, to0, to1, st))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tb, to0, to1, st, PLC_K_CONV_DGRAD))) return rc;
   }
   if (dW_acc) {
     WgradShape w{d->B, d->H, d->W, d->k, d->Cin, 0, d->Cout};
-    if ((rc = launch_wgrad_tc_shape(&w, x, nullptr, dz, dW_acc, d->has_bias ? db_acc : nullptr, st))) return rc;
+    if ((rc = launch_wgrad_tc_shape(&w, x, nullptr, dz, dW_acc, d->has_bias ? db_acc : nullptr, st, PLC_K_CONV_WGRAD)))
+      return rc;
   }
   return PLC_OK;
 }
 
 int plc_debug_set_patch(int mode) {
   if (mode < -1 || mode > 1) return fail(PLC_ERR_BAD_DESC, "plc_debug_set_patch: mode must be -1 (auto), 0 or 1");
-  g_patch_override = mode;
+  g_patch_override.store(mode);
   return PLC_OK;
 }
 
 int plc_debug_set_cta_group(int cta_group) {
   if (cta_group < 0 || cta_group > 2) return fail(PLC_ERR_BAD_DESC, "cta_group must be 0 (auto), 1 or 2");
-  g_cta_override = cta_group;
+  g_cta_override.store(cta_group);
   return PLC_OK;
+}
+
+int plc_timing_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (auto& t : g_timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  g_timed.clear();
+  g_timing_on.store(on ? 1 : 0);
+  return PLC_OK;
+}
+
+int plc_timing_collect(int* kinds, float* ms, int capacity) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  int n = 0;
+  for (auto& t : g_timed) {
+    float v = 0.f;
+    if (cudaEventSynchronize(t.e1) != cudaSuccess || cudaEventElapsedTime(&v, t.e0, t.e1) != cudaSuccess) {
+      cudaGetLastError();
+      v = -1.f;
+    }
+    if (n < capacity && kinds && ms) { kinds[n] = t.kind; ms[n] = v; }
+    ++n;
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  g_timed.clear();
+  return n;
 }
 
 int plc_debug_set_prof(void* device_buf_u64) {
@@ -1040,6 +1183,7 @@ int plc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C_src, int
   if (!src || !dst) return fail(PLC_ERR_NULL_ARG, "null pointer");
   if (B <= 0 || C_src <= 0 || C_dst < C_src || H <= 0 || W <= 0) return fail(PLC_ERR_BAD_DESC, "bad sizes");
   dim3 grid(cdiv(H * W, 32), cdiv(C_dst, 32), B), block(32, 8);
+  LaunchTimer timer(PLC_K_ELEMENTWISE, static_cast<cudaStream_t>(stream));
   nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), C_src, C_dst, H * W);
   PLC_CUDA(cudaGetLastError());
@@ -1050,6 +1194,7 @@ int plc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int C, int H, 
   if (!src || !dst) return fail(PLC_ERR_NULL_ARG, "null pointer");
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(PLC_ERR_BAD_DESC, "bad sizes");
   dim3 grid(cdiv(H * W, 32), cdiv(C, 32), B), block(32, 8);
+  LaunchTimer timer(PLC_K_ELEMENTWISE, static_cast<cudaStream_t>(stream));
   nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(src), dst, C, H * W);
   PLC_CUDA(cudaGetLastError());
@@ -1071,6 +1216,7 @@ int plc_frontend_fwd(const float* frames, int N, int Cf, int H, int W, const flo
   dim3 grid(static_cast<unsigned>(groups < max_blocks ? groups : max_blocks)), block(G, P);
   const size_t smem = (static_cast<size_t>(Cf + 2) * 9 * C + C) * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchTimer timer(PLC_K_FRONTEND, st);
   if (mode == PLC_MODE_BF16_TC) {
     PLC_CUDA(cudaFuncSetAttribute(plc::frontend_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
@@ -1091,6 +1237,7 @@ int plc_head_fwd(const void* h, long npix, int C, const float* w, const float* b
   if (npix <= 0 || C <= 0 || C % 8) return fail(PLC_ERR_BAD_DESC, "plc_head_fwd: need C %% 8 == 0");
   if (!aligned16(h)) return fail(PLC_ERR_ALIGNMENT, "plc_head_fwd: h must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchTimer timer(PLC_K_HEAD, st);
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((npix + threads - 1) / threads);
   if (mode == PLC_MODE_BF16_TC) {
@@ -1117,6 +1264,7 @@ int plc_frames_to_nhwc(const float* frames, int B, int T, int Cf, int H, int W, 
   if (B <= 0 || T <= 0 || Cf <= 0 || H <= 0 || W <= 0 || Cp < Cf + 2 || Cp % 8)
     return fail(PLC_ERR_BAD_DESC, "plc_frames_to_nhwc: need Cp %% 8 == 0 and Cp >= Cf + 2 (got Cf=%d Cp=%d)", Cf, Cp);
   if (!aligned16(out)) return fail(PLC_ERR_ALIGNMENT, "plc_frames_to_nhwc: out must be 16-byte aligned");
+  LaunchTimer timer(PLC_K_ELEMENTWISE, static_cast<cudaStream_t>(stream));
   plc::frames_to_nhwc_kernel<<<sm_count() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       frames, static_cast<__nv_bfloat16*>(out), B, T, Cf, H, W, Cp);
   PLC_CUDA(cudaGetLastError());
@@ -1133,6 +1281,7 @@ int plc_head_bwd(const void* h, long npix, int C, const float* w, const float* d
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* hb = static_cast<const __nv_bfloat16*>(h);
   __nv_bfloat16* dhb = static_cast<__nv_bfloat16*>(dh);
+  LaunchTimer timer(PLC_K_HEAD, st);
   const int blocks = sm_count() * 8;
 #define PLC_HB(GG) case GG: plc::head_bwd_kernel_bf16<GG><<<blocks, 256, 0, st>>>(hb, w, dy, dhb, dw_acc, db_acc, (size_t)npix); break;
   switch (G) { PLC_HB(1) PLC_HB(2) PLC_HB(4) PLC_HB(8) PLC_HB(16) PLC_HB(32) }
@@ -1166,6 +1315,7 @@ int plc_combined_loss(const PlcLossDesc* d, const float* pred, const float* lr_i
   if (d->n_stations > 0 && (!s_coords || !s_values))
     return fail(PLC_ERR_NULL_ARG, "plc_combined_loss: n_stations > 0 needs s_coords and s_values");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchTimer timer(PLC_K_LOSS, st);
   plc::LossParams p{};
   p.B = d->B; p.T = d->T; p.H = d->H; p.W = d->W; p.s = d->scale;
   p.Hs = d->H * d->scale; p.Ws = d->W * d->scale;
@@ -1230,10 +1380,10 @@ int plc_frontend_tc_fwd(const float* frames, int B, int T, int Cf, int H, int W,
   p.frames = frames; p.w = w_oihw; p.bias = bias;
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchTimer timer(PLC_K_FRONTEND, st);
 #define PLC_FE(CF)                                                                                         \
   case CF:                                                                                                 \
-    PLC_CUDA(cudaFuncSetAttribute(plc::frontend_tc_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  plc::kFeSmemBytes));                                                     \
+    PLC_CUDA(set_smem_once<IntTag<CF>>(plc::frontend_tc_kernel<CF>, plc::kFeSmemBytes));                   \
     plc::frontend_tc_kernel<CF><<<grid, plc::kFeThreads, plc::kFeSmemBytes, st>>>(p, tm);                  \
     break;
   switch (Cf) { PLC_FE(1) PLC_FE(2) PLC_FE(3) }

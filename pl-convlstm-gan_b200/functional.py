@@ -21,8 +21,21 @@ def _ptr(t: Optional[Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(dev=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _call(t: Tensor, fn, what: str, *args) -> None:
+    """Run one launching ABI call with `t`'s device current and that device's current stream appended as the last
+    argument.  The library launches on the CURRENT device, so a tensor living elsewhere (``Trainer(device='cuda:1')``
+    without ``torch.cuda.set_device``) must switch devices around the call -- never launch on cuda:0 with cuda:1
+    pointers."""
+    dev = t.device
+    if dev.index == torch.cuda.current_device():
+        _lib.check(fn(*args, _stream(dev)), what)
+    else:
+        with torch.cuda.device(dev):
+            _lib.check(fn(*args, _stream(dev)), what)
 
 
 def _require_cuda(t: Tensor, name: str):
@@ -73,7 +86,7 @@ def pack_weights(weight: Tensor, bias: Optional[Tensor], Cin: int, Ch: int, k: i
         if nbytes == 0:
             _lib.check(-1, "plc_packed_weight_bytes")
         buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-        _lib.check(lib.plc_pack_weight(ctypes.byref(d), kind, _ptr(w), _ptr(buf), _stream()), "plc_pack_weight")
+        _call(w, lib.plc_pack_weight, "plc_pack_weight", ctypes.byref(d), kind, _ptr(w), _ptr(buf))
         out[kind] = buf
     b = None if bias is None else bias.detach().to(torch.float32).contiguous()
     return PackedWeights(out[PLC_PACK_FWD], out[PLC_PACK_DGRAD], b, mode, Cin, Ch, k)
@@ -104,9 +117,8 @@ def cell_forward(x: Optional[Tensor], h: Tensor, c: Tensor, pw: PackedWeights,
     if c_out is None:
         c_out = torch.empty_like(c)
     d = make_desc(B, H, W, pw.Cin, Ch, pw.k, pw.mode, pw.bias is not None)
-    _lib.check(lib.plc_cell_fwd(ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h), _ptr(c), _ptr(pw.fwd),
-                                _ptr(pw.bias), _ptr(h_out), _ptr(c_out), _ptr(gates_out), _stream()),
-               "plc_cell_fwd")
+    _call(h, lib.plc_cell_fwd, "plc_cell_fwd", ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h), _ptr(c), _ptr(pw.fwd),
+                                _ptr(pw.bias), _ptr(h_out), _ptr(c_out), _ptr(gates_out))
     return h_out, c_out
 
 
@@ -132,8 +144,8 @@ def cell_forward_zero_state(x: Tensor, pw: PackedWeights, h_out: Optional[Tensor
     if c_out is None:
         c_out = torch.empty(B, H, W, pw.Ch, dtype=torch.float32, device=x.device)
     d = make_desc(B, H, W, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)
-    _lib.check(lib.plc_cell_fwd(ctypes.byref(d), _ptr(x), None, None, _ptr(pw.fwd), _ptr(pw.bias), _ptr(h_out),
-                                _ptr(c_out), None, _stream()), "plc_cell_fwd (zero state)")
+    _call(x, lib.plc_cell_fwd, "plc_cell_fwd (zero state)", ctypes.byref(d), _ptr(x), None, None, _ptr(pw.fwd), _ptr(pw.bias), _ptr(h_out),
+                                _ptr(c_out), None)
     return h_out, c_out
 
 
@@ -154,7 +166,7 @@ def wgrad_unpack(acc: Tensor, pw: PackedWeights, dW: Tensor) -> Tensor:
     """dW [4Ch, Cin+Ch, k, k] fp32 (reference layout, Cin = pw.Cin) += unpack(acc)."""
     lib = _lib.load()
     d = make_desc(1, 1, 1, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)
-    _lib.check(lib.plc_wgrad_unpack(ctypes.byref(d), _ptr(acc), _ptr(dW), _stream()), "plc_wgrad_unpack")
+    _call(acc, lib.plc_wgrad_unpack, "plc_wgrad_unpack", ctypes.byref(d), _ptr(acc), _ptr(dW))
     return dW
 
 
@@ -179,11 +191,10 @@ def cell_backward_acc(x: Optional[Tensor], h_prev: Tensor, c_prev: Tensor, pw: P
     if dc_prev is None:
         dc_prev = torch.empty_like(c_prev)
     d = make_desc(B, H, W, pw.Cin, Ch, pw.k, pw.mode, pw.bias is not None)
-    _lib.check(lib.plc_cell_bwd(ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h_prev), _ptr(c_prev),
+    _call(h_prev, lib.plc_cell_bwd, "plc_cell_bwd", ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h_prev), _ptr(c_prev),
                                 _ptr(pw.fwd), _ptr(pw.dgrad), _ptr(pw.bias), _ptr(dh), _ptr(dh2), _ptr(dc_next),
                                 _ptr(dx), _ptr(dh_prev), _ptr(dc_prev), _ptr(dW_img), _ptr(db_acc),
-                                _ptr(workspace), workspace.numel(), _stream()),
-               "plc_cell_bwd")
+                                _ptr(workspace), workspace.numel())
     return dx, dh_prev, dc_prev
 
 
@@ -212,7 +223,7 @@ def nchw_to_nhwc(src: Tensor, mode: int, c_pad: Optional[int] = None) -> Tensor:
     lib = _lib.load()
     s = src.to(torch.float32).contiguous()
     out = torch.empty(B, H, W, cd, dtype=torch.bfloat16, device=src.device)
-    _lib.check(lib.plc_nchw_f32_to_nhwc_bf16(_ptr(s), _ptr(out), B, C, cd, H, W, _stream()), "plc_nchw_f32_to_nhwc_bf16")
+    _call(s, lib.plc_nchw_f32_to_nhwc_bf16, "plc_nchw_f32_to_nhwc_bf16", _ptr(s), _ptr(out), B, C, cd, H, W)
     return out
 
 
@@ -223,8 +234,7 @@ def nhwc_to_nchw(src: Tensor) -> Tensor:
         return src.permute(0, 3, 1, 2).contiguous()
     lib = _lib.load()
     out = torch.empty(B, C, H, W, dtype=torch.float32, device=src.device)
-    _lib.check(lib.plc_nhwc_bf16_to_nchw_f32(_ptr(src.contiguous()), _ptr(out), B, C, H, W, _stream()),
-               "plc_nhwc_bf16_to_nchw_f32")
+    _call(src, lib.plc_nhwc_bf16_to_nchw_f32, "plc_nhwc_bf16_to_nchw_f32", _ptr(src.contiguous()), _ptr(out), B, C, H, W)
     return out
 
 
@@ -244,8 +254,7 @@ def frontend_forward(frames: Tensor, weight: Tensor, bias: Optional[Tensor], mod
         out = (torch.zeros if cs != C else torch.empty)(N, H, W, cs, dtype=_act_dtype(mode), device=frames.device)
     w = weight.detach().to(torch.float32).contiguous()
     b = None if bias is None else bias.detach().to(torch.float32).contiguous()
-    _lib.check(lib.plc_frontend_fwd(_ptr(frames), N, Cf, H, W, _ptr(w), _ptr(b), C, cs, mode, _ptr(out), _stream()),
-               "plc_frontend_fwd")
+    _call(frames, lib.plc_frontend_fwd, "plc_frontend_fwd", _ptr(frames), N, Cf, H, W, _ptr(w), _ptr(b), C, cs, mode, _ptr(out))
     return out
 
 
@@ -260,7 +269,7 @@ def head_forward(h: Tensor, weight: Tensor, bias: Optional[Tensor], mode: int, o
     b = None if bias is None else bias.detach().to(torch.float32).reshape(-1).contiguous()
     if out is None:
         out = torch.empty(h.shape[:-1], dtype=torch.float32, device=h.device)
-    _lib.check(lib.plc_head_fwd(_ptr(h), npix, C, _ptr(w), _ptr(b), mode, _ptr(out), _stream()), "plc_head_fwd")
+    _call(h, lib.plc_head_fwd, "plc_head_fwd", _ptr(h), npix, C, _ptr(w), _ptr(b), mode, _ptr(out))
     return out
 
 
@@ -291,8 +300,7 @@ class _HeadFn(torch.autograd.Function):
         dh = torch.empty_like(h)
         dw = torch.zeros(C, dtype=torch.float32, device=h.device)
         db = torch.zeros(1, dtype=torch.float32, device=h.device) if ctx.has_bias else None
-        _lib.check(lib.plc_head_bwd(_ptr(h), npix, C, _ptr(w), _ptr(dyc), _ptr(dh), _ptr(dw), _ptr(db), _stream()),
-                   "plc_head_bwd")
+        _call(h, lib.plc_head_bwd, "plc_head_bwd", _ptr(h), npix, C, _ptr(w), _ptr(dyc), _ptr(dh), _ptr(dw), _ptr(db))
         return dh, dw.reshape(weight.shape).to(weight.dtype), db, None
 
 
@@ -344,14 +352,13 @@ class ConvParams:
         fwd = torch.empty(lib.plc_conv_packed_weight_bytes(ctypes.byref(d), PLC_PACK_FWD), dtype=torch.uint8,
                           device=w.device)
         bias_packed = torch.zeros(self.cout_p, device=w.device, dtype=torch.float32)
-        _lib.check(lib.plc_conv_pack_weight(ctypes.byref(d), PLC_PACK_FWD, _ptr(wp), _ptr(bp), _ptr(fwd),
-                                            _ptr(bias_packed), _stream()), "plc_conv_pack_weight")
+        _call(wp, lib.plc_conv_pack_weight, "plc_conv_pack_weight", ctypes.byref(d), PLC_PACK_FWD, _ptr(wp), _ptr(bp), _ptr(fwd),
+                                            _ptr(bias_packed))
         dg = None
         if need_dgrad:
             dg = torch.empty(lib.plc_conv_packed_weight_bytes(ctypes.byref(d), PLC_PACK_DGRAD), dtype=torch.uint8,
                              device=w.device)
-            _lib.check(lib.plc_conv_pack_weight(ctypes.byref(d), PLC_PACK_DGRAD, _ptr(wp), None, _ptr(dg), None,
-                                                _stream()), "plc_conv_pack_weight")
+            _call(wp, lib.plc_conv_pack_weight, "plc_conv_pack_weight", ctypes.byref(d), PLC_PACK_DGRAD, _ptr(wp), None, _ptr(dg), None)
         self._cache = (key, fwd, bias_packed, dg)
         return fwd, bias_packed, dg
 
@@ -365,15 +372,16 @@ class _ConvFn(torch.autograd.Function):
         B, H, W, C = x.shape
         if C != cp.cin_p or x.dtype != torch.bfloat16 or not x.is_contiguous():
             raise RuntimeError(f"conv input must be contiguous bf16 [B,H,W,{cp.cin_p}], got {x.dtype} {tuple(x.shape)}")
-        fwd, bias_packed, _ = cp.packed(need_dgrad=torch.is_grad_enabled())
+        # (torch.is_grad_enabled() is always False inside forward; ctx.needs_input_grad says what the graph wants.)
+        # The images packed here are a snapshot of the weights at forward time; backward reuses exactly these.
+        fwd, bias_packed, dg = cp.packed(need_dgrad=ctx.needs_input_grad[0])
         if cp.shuffle:
             out = torch.empty(B, 2 * H, 2 * W, cp.cout_p // 4, dtype=torch.bfloat16, device=x.device)
         else:
             out = torch.empty(B, H, W, cp.cout_p, dtype=torch.bfloat16, device=x.device)
         d = cp.desc(B, H, W)
-        _lib.check(lib.plc_conv_fwd(ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out), _stream()),
-                   "plc_conv_fwd")
-        ctx.cp = cp
+        _call(x, lib.plc_conv_fwd, "plc_conv_fwd", ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out))
+        ctx.cp, ctx.dg = cp, dg
         ctx.save_for_backward(x, out)
         ctx.x_needs_grad = x.requires_grad
         return out
@@ -384,22 +392,20 @@ class _ConvFn(torch.autograd.Function):
         x, out = ctx.saved_tensors
         cp = ctx.cp
         B, H, W, _ = x.shape
-        _, _, dg = cp.packed(need_dgrad=True)
+        dg = ctx.dg
         d = cp.desc(B, H, W)
         dy = dy.contiguous()
         if cp.relu or cp.shuffle:
             dz = torch.empty(B, H, W, cp.cout_p, dtype=torch.bfloat16, device=x.device)
-            _lib.check(lib.plc_conv_grad_mask(ctypes.byref(d), _ptr(out), _ptr(dy), _ptr(dz), _stream()),
-                       "plc_conv_grad_mask")
+            _call(dy, lib.plc_conv_grad_mask, "plc_conv_grad_mask", ctypes.byref(d), _ptr(out), _ptr(dy), _ptr(dz))
         else:
             dz = dy
         dx = torch.empty_like(x) if ctx.x_needs_grad else None
         dW = torch.zeros(cp.cout_p, cp.cin_p, cp.k, cp.k, dtype=torch.float32, device=x.device)
         img = torch.zeros(lib.plc_conv_wgrad_acc_bytes(ctypes.byref(d)) // 4, dtype=torch.float32, device=x.device)
         db = torch.zeros(cp.cout_p, dtype=torch.float32, device=x.device) if cp.conv.bias is not None else None
-        _lib.check(lib.plc_conv_bwd(ctypes.byref(d), _ptr(x), _ptr(dz), _ptr(dg), _ptr(dx), _ptr(img), _ptr(db),
-                                    _stream()), "plc_conv_bwd")
-        _lib.check(lib.plc_conv_wgrad_unpack(ctypes.byref(d), _ptr(img), _ptr(dW), _stream()), "plc_conv_wgrad_unpack")
+        _call(x, lib.plc_conv_bwd, "plc_conv_bwd", ctypes.byref(d), _ptr(x), _ptr(dz), _ptr(dg), _ptr(dx), _ptr(img), _ptr(db))
+        _call(img, lib.plc_conv_wgrad_unpack, "plc_conv_wgrad_unpack", ctypes.byref(d), _ptr(img), _ptr(dW))
         gw = dW[:cp.Cout, :cp.Cin].to(cp.conv.weight.dtype)
         gb = None if db is None else db[:cp.Cout].to(cp.conv.bias.dtype)
         return dx, gw, gb, None
@@ -420,7 +426,7 @@ def frames_to_nhwc(frames: Tensor, c_pad: int, out: Optional[Tensor] = None) -> 
         raise RuntimeError("frames must be float32")
     if out is None:
         out = torch.empty(T * B, H, W, c_pad, dtype=torch.bfloat16, device=frames.device)
-    _lib.check(lib.plc_frames_to_nhwc(_ptr(frames), B, T, Cf, H, W, c_pad, _ptr(out), _stream()), "plc_frames_to_nhwc")
+    _call(frames, lib.plc_frames_to_nhwc, "plc_frames_to_nhwc", _ptr(frames), B, T, Cf, H, W, c_pad, _ptr(out))
     return out
 
 
@@ -439,8 +445,7 @@ def frontend_tc(frames: Tensor, weight: Tensor, bias: Optional[Tensor], out: Ten
         raise RuntimeError("frontend_tc: frames must be fp32 [B,T,Cf,H,W], out bf16 [T*B,H,W,64]")
     w = weight.detach().to(torch.float32).contiguous()
     b = None if bias is None else bias.detach().to(torch.float32).contiguous()
-    _lib.check(lib.plc_frontend_tc_fwd(_ptr(frames), B, T, Cf, H, W, _ptr(w), _ptr(b), 64, _ptr(out), _stream()),
-               "plc_frontend_tc_fwd")
+    _call(frames, lib.plc_frontend_tc_fwd, "plc_frontend_tc_fwd", _ptr(frames), B, T, Cf, H, W, _ptr(w), _ptr(b), 64, _ptr(out))
     return out
 
 
@@ -450,6 +455,5 @@ def conv2d_same_into(x: Tensor, cp: ConvParams, out: Tensor) -> Tensor:
     B, H, W, _ = x.shape
     fwd, bias_packed, _ = cp.packed(need_dgrad=False)
     d = cp.desc(B, H, W)
-    _lib.check(lib.plc_conv_fwd(ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out), _stream()),
-               "plc_conv_fwd")
+    _call(x, lib.plc_conv_fwd, "plc_conv_fwd", ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out))
     return out

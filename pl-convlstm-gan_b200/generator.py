@@ -183,8 +183,11 @@ class Generator(nn.Module):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self.forward(*static)
-            ent = cache[key] = (graph, static, out)
-        graph, static, out = ent
+            # the graph holds raw pointers into the packed-weight images: keep them alive with it (a later backward /
+            # re-pack replaces the modules' cache entries, which must not free what the graph replays against)
+            keep = [cp._cache for cp in self._native.values()] + [self.cell1._pack_cache, self.cell2._pack_cache]
+            ent = cache[key] = (graph, static, out, keep)
+        graph, static, out, _ = ent
         for dst, src in zip(static, (rain_lr, dem, lu)):
             dst.copy_(src, non_blocking=True)
         graph.replay()

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import _ptr, _stream
+from .functional import _call, _ptr
 
 _WEIGHT_MODES = {"log": 1, "sqrt": 2, "stratified": 3}
 
@@ -55,9 +55,8 @@ class _Problem:
         ws = torch.empty(lib.plc_loss_workspace_bytes(ctypes.byref(self.desc)), dtype=torch.uint8, device=dev)
         terms = torch.empty(5, dtype=torch.float32, device=dev)
         dpred = torch.empty_like(self.pred) if want_grad else None
-        _lib.check(lib.plc_combined_loss(ctypes.byref(self.desc), _ptr(self.pred), _ptr(self.lr), _ptr(self.coords),
-                                         _ptr(self.svals), _ptr(ws), _ptr(terms), _ptr(dpred), _ptr(grad_scale),
-                                         _stream()), "plc_combined_loss")
+        _call(self.pred, lib.plc_combined_loss, "plc_combined_loss", ctypes.byref(self.desc), _ptr(self.pred),
+              _ptr(self.lr), _ptr(self.coords), _ptr(self.svals), _ptr(ws), _ptr(terms), _ptr(dpred), _ptr(grad_scale))
         return terms, dpred
 
 

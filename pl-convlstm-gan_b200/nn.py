@@ -37,7 +37,10 @@ class _CellStepFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, h, c, weight, bias, cell):
-        pw = cell._packed(need_dgrad=torch.is_grad_enabled())
+        # torch.is_grad_enabled() is always False in here; what the graph needs is in ctx.needs_input_grad.  The packed
+        # images are a SNAPSHOT of the weights at forward time and backward recomputes the gates from that snapshot, so
+        # an optimizer step between forward and backward (GAN loops) cannot desynchronise the gradient.
+        pw = cell._packed(need_dgrad=any(ctx.needs_input_grad))
         h2, c2 = F.cell_forward(x, h, c, pw)
         ctx.cell = cell
         ctx.pw = pw
@@ -50,8 +53,6 @@ class _CellStepFn(torch.autograd.Function):
     def backward(ctx, dh, dc):
         x, h, c = ctx.saved_tensors
         cell, pw = ctx.cell, ctx.pw
-        if pw.dgrad is None:
-            pw = cell._packed(need_dgrad=True)
         B, H, W, Ch = h.shape
         if dh is None:
             dh = torch.zeros_like(h)
@@ -132,20 +133,25 @@ class ConvLSTMCell(nn.Module):
 
     def forward(self, x: Tensor, h_cur, c_cur: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         """convlstm.py:16-28.  Logical [B,C,H,W] in, ``(h_next, c_next)`` logical [B,C,H,W] out (dtype of
-        ``h_cur``, channels_last strides)."""
+        ``h_cur`` / ``c_cur`` respectively, channels_last strides).
+
+        Cost of this literal drop-in form: logical NCHW-contiguous fp32 inputs are converted on the way in (3 permute /
+        cast copies) and out (2 casts).  Callers that keep the recurrent state in the working layout pay nothing: pass
+        ``x`` / ``h_cur`` as bf16 and ``c_cur`` as fp32 tensors with ``torch.channels_last`` strides (what this method
+        returns) and every conversion above is a view -- or use :class:`ConvLSTMStack`, which never leaves NHWC."""
         if c_cur is None:
             h_cur, c_cur = h_cur                         # forward(x, (h, c)) spelling
         if not h_cur.is_cuda:
             raise RuntimeError("ConvLSTMCell (plconv) has no CPU path: move the module and inputs to a CUDA device")
         if self.kernel_size % 2 == 0:
             raise RuntimeError("kernel_size must be odd (the reference's padding k//2 breaks even k)")
-        out_dtype = h_cur.dtype
+        out_dtype, c_dtype = h_cur.dtype, c_cur.dtype
         xw = self._to_working(x, self.working_cin, self.act_dtype) if self.input_dim > 0 else None
         hw = self._to_working(h_cur, self.hidden_dim, self.act_dtype)
         cw = self._to_working(c_cur, self.hidden_dim, torch.float32)
         h2, c2 = self.step_nhwc(xw, hw, cw)
         # back to the logical NCHW shape (a channels_last-strided view; no copy beyond the dtype cast)
-        return h2.to(out_dtype).permute(0, 3, 1, 2), c2.to(out_dtype).permute(0, 3, 1, 2)
+        return h2.to(out_dtype).permute(0, 3, 1, 2), c2.to(c_dtype).permute(0, 3, 1, 2)
 
 
 class _StackRolloutFn(torch.autograd.Function):
@@ -164,8 +170,8 @@ class _StackRolloutFn(torch.autograd.Function):
     def forward(ctx, cells, T, xs, *tensors):
         L = len(cells)
         states, params = tensors[:2 * L], tensors[2 * L:]
-        need_grad = torch.is_grad_enabled()
-        pws = [c._packed(need_dgrad=need_grad) for c in cells]
+        need_grad = any(ctx.needs_input_grad)          # (torch.is_grad_enabled() is always False inside forward)
+        pws = [c._packed(need_dgrad=need_grad) for c in cells]   # snapshot of the weights this rollout ran with
         B, H, W, _ = states[0].shape
         dev = states[0].device
         hs, cs = [], []
@@ -194,7 +200,7 @@ class _StackRolloutFn(torch.autograd.Function):
     def backward(ctx, d_out, *d_final):
         cells, T, xs, hs, cs = ctx.cells, ctx.T, ctx.xs, ctx.hs, ctx.cs
         L = len(cells)
-        pws = [pw if pw.dgrad is not None else c._packed(need_dgrad=True) for pw, c in zip(ctx.pws, cells)]
+        pws = ctx.pws
         B, H, W, _ = hs[0][0].shape
         dev = hs[0].device
         dW_img = [F.wgrad_accumulator(B, H, W, pw, dev) for pw in pws]     # accumulated over all T steps
@@ -217,6 +223,25 @@ class _StackRolloutFn(torch.autograd.Function):
         dxs = torch.empty_like(xs) if ctx.x_needs_grad else None
         zero_top = None
         flip = [0] * L
+        wgrads = [None] * L
+
+        def finish_layer(l):
+            """Layer l's last BPTT step (t = 0) has been queued: convert its accumulator to the reference layout and, if
+            a gradient sink is attached (GradReducer under data parallelism), hand dW / db over NOW so that the bucket's
+            all-reduce overlaps the remaining BPTT steps of the layers below instead of waiting for the whole node."""
+            cell = cells[l]
+            g = torch.zeros(4 * cell.hidden_dim, pws[l].Cin + cell.hidden_dim, pws[l].k, pws[l].k, device=dev)
+            F.wgrad_unpack(dW_img[l], pws[l], g)             # one layout conversion per backward pass
+            if pws[l].Cin != cell.input_dim:                 # drop zero-padded x channels
+                g = torch.cat([g[:, :cell.input_dim], g[:, pws[l].Cin:]], dim=1)
+            gw = g.to(cell.conv.weight.dtype)
+            gb = None if cell.conv.bias is None else db[l].to(cell.conv.bias.dtype)
+            sink = getattr(cell, "_grad_sink", None)
+            if sink is not None and sink(cell, gw, gb):
+                wgrads[l] = (None, None)
+            else:
+                wgrads[l] = (gw, gb)
+
         for t in reversed(range(T)):
             d_above = None if d_out is None else d_out[t]
             for l in reversed(range(L)):
@@ -240,17 +265,16 @@ class _StackRolloutFn(torch.autograd.Function):
                 dh_carry[l], dc_carry[l] = dst, dc_buf[l]
                 flip[l] ^= 1
                 d_above = out_dx if l > 0 else None
+                if t == 0:
+                    finish_layer(l)
         grads = [None, None, dxs]
         for l in range(L):
             grads.append(dh_carry[l] if ctx.state_needs_grad[2 * l] else None)
             grads.append(dc_carry[l] if ctx.state_needs_grad[2 * l + 1] else None)
-        for l, cell in enumerate(cells):
-            g = torch.zeros(4 * cell.hidden_dim, pws[l].Cin + cell.hidden_dim, pws[l].k, pws[l].k, device=dev)
-            F.wgrad_unpack(dW_img[l], pws[l], g)             # one layout conversion per backward pass
-            if pws[l].Cin != cell.input_dim:                 # drop zero-padded x channels
-                g = torch.cat([g[:, :cell.input_dim], g[:, pws[l].Cin:]], dim=1)
-            grads.append(g.to(cell.conv.weight.dtype))
-            grads.append(None if cell.conv.bias is None else db[l].to(cell.conv.bias.dtype))
+        for l in range(L):
+            if wgrads[l] is None:                            # T == 0: nothing ran
+                finish_layer(l)
+            grads += list(wgrads[l])
         return tuple(grads)
 
 

@@ -56,6 +56,7 @@ class GradReducer:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.buckets: List[dict] = []
         self._hooks = []
+        self._sunk: List[torch.nn.Module] = []
         for grp in groups:
             params = [p for p in grp if p.requires_grad]
             if not params:
@@ -72,6 +73,42 @@ class GradReducer:
             self.buckets.append(b)
             for p in params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
+
+    def attach_cell_sinks(self, module: torch.nn.Module) -> int:
+        """Per-LAYER hand-over inside a fused rollout: `_StackRolloutFn` is one autograd node per stack, so the
+        post-accumulate hooks above would only fire when the whole stack's BPTT has been queued.  With a sink attached,
+        the rollout's backward gives a cell's dW / db to its bucket the moment that layer's t = 0 step is queued, and
+        the bucket's all-reduce overlaps the BPTT steps still to run.  Returns the number of cells attached."""
+        by_param = {id(p): b for b in self.buckets for p in b["params"]}
+        n = 0
+        for cell in module.modules():
+            conv = getattr(cell, "conv", None)
+            if not hasattr(cell, "_packed") or conv is None:
+                continue
+            ps = [p for p in (conv.weight, conv.bias) if p is not None]
+            bs = {id(by_param.get(id(p))) for p in ps}
+            if len(bs) != 1 or by_param.get(id(ps[0])) is None:
+                continue                                     # not (entirely) in one of this reducer's buckets
+            cell._grad_sink = self._make_sink(by_param[id(ps[0])])
+            self._sunk.append(cell)
+            n += 1
+        return n
+
+    def _make_sink(self, bucket):
+        def sink(cell, gw, gb) -> bool:
+            conv = cell.conv
+            if conv.weight.grad is None or (gb is not None and conv.bias.grad is None):
+                return False                                 # .grad detached from the bucket: let autograd accumulate
+            conv.weight.grad.add_(gw)
+            k = 1
+            if gb is not None:
+                conv.bias.grad.add_(gb)
+                k = 2
+            bucket["pending"] -= k
+            if bucket["pending"] == 0:
+                self._launch(bucket)
+            return True
+        return sink
 
     def _make_hook(self, bucket):
         def hook(_param):
@@ -109,6 +146,19 @@ class GradReducer:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        for cell in self._sunk:
+            cell._grad_sink = None
+        self._sunk = []
+
+
+def nonfinite_flag(value: torch.Tensor, process_group=None) -> torch.Tensor:
+    """Device-side form of the NaN-skip (trainer.py:306-308): a float32 scalar tensor, 1 where ANY rank's `value` is
+    not finite, else 0 -- max-reduced over the ranks, never read by the host.  Hand it to a fused optimizer as
+    ``found_inf`` (the update is skipped on the device, as torch.amp.GradScaler does) so a step has no host sync."""
+    bad = (~torch.isfinite(value.detach())).any().to(torch.float32).reshape(1)
+    if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=process_group)
+    return bad
 
 
 def all_ranks_finite(value: torch.Tensor, process_group=None) -> bool:

@@ -69,8 +69,10 @@ class NowcastGenerator(nn.Module):
 class NowcastRunner:
     """Inference engine for :class:`NowcastGenerator` with every buffer preallocated.
 
-    The kernel-layout weight images (cells, front-end, head) are taken from the model when the runner is built:
-    build a new runner after the model's parameters change (training step, ``load_state_dict``)."""
+    The kernel-layout weight images (cells, front-end, head) are snapshots of the model's parameters; every ``run``
+    compares the parameters' version counters and the packed-weight generation (advanced by optimizer steps) with the
+    snapshot's and re-packs when they differ, so a runner survives training steps and ``load_state_dict``.  A captured
+    CUDA graph (:meth:`capture`) replays against the snapshot it was captured with: re-capture after weight updates."""
 
     def __init__(self, model: NowcastGenerator, B: int, H: int, W: int, device):
         self.m, self.B, self.H, self.W, self.dev = model, B, H, W, device
@@ -95,12 +97,31 @@ class NowcastRunner:
         self.c = [torch.zeros(B, H, W, hd[l], dtype=torch.float32, device=device) for l in range(L)]
         self.h_top = torch.zeros(model.t_out, B, H, W, hd[-1], dtype=adt, device=device)
         self.out = torch.zeros(model.t_out, B, H, W, dtype=torch.float32, device=device)
-        self.enc_pw = [c._packed(False) for c in model.encoder.cells]
+        self._weights_key = None
+        self.refresh_weights()
         self.zero_state = [F.zero_state_supported(pw) for pw in self.enc_pw]
-        self.fc_pw = [c._packed(False) for c in model.forecaster.cells]
         self.cell_launches_per_run = L * (model.t_in + model.t_out)
         self.launches_per_run = (2 if (self.tc_frontend and not self.fused_frontend) else 1) + \
             self.cell_launches_per_run + 1
+
+    def _key(self):
+        from . import _lib
+        return (_lib.weight_generation(), tuple(p._version for p in self.m.parameters()),
+                tuple(p.data_ptr() for p in self.m.parameters()))
+
+    def refresh_weights(self) -> bool:
+        """Re-snapshot the packed weight images if the model's parameters changed since the last snapshot."""
+        key = self._key()
+        if key == self._weights_key:
+            return False
+        m = self.m
+        if getattr(self, "fused_frontend", False):
+            self._fe_w = m.init_conv.weight.detach().to(torch.float32).contiguous()
+            self._fe_b = None if m.init_conv.bias is None else m.init_conv.bias.detach().float().contiguous()
+        self.enc_pw = [c._packed(False) for c in m.encoder.cells]
+        self.fc_pw = [c._packed(False) for c in m.forecaster.cells]
+        self._weights_key = key
+        return True
 
     # ------------------------------------------------------------------ CUDA graph (launch-bound shapes)
     def capture(self, frames_like: Tensor):
@@ -144,6 +165,8 @@ class NowcastRunner:
         per cell launch."""
         m, B, L = self.m, self.B, len(self.c)
         T_in, T_out = m.t_in, m.t_out
+        if not torch.cuda.is_current_stream_capturing():
+            self.refresh_weights()
         # front-end for all T_in steps at once (T-major batch [T*B, ...])
         if self.fused_frontend:
             F.frontend_tc(frames, self._fe_w, self._fe_b, self.feat)

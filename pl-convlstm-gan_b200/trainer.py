@@ -335,19 +335,46 @@ class Trainer:
     def load_checkpoint(self, path: str, resume: bool = True) -> dict:
         """``resume=False``: weights only (what the reference's evaluation scripts do).  ``resume=True``: also the
         optimizer moments, scheduler, history, early-stopping counters and the epoch to continue from -- the resume
-        path the reference lacks.  Checkpoints written by the reference load too (missing extras are skipped)."""
+        path the reference lacks.
+
+        Checkpoints written by the reference load too.  Its Adam was built BEFORE the first forward created
+        ``upsample_blocks`` (generator.py:129-130, trainer.py:153-158), so its ``param_groups`` hold only the leading
+        parameters of ``model.parameters()`` (the lazy blocks register last): those moments are restored and the
+        remaining parameters (trained here when ``optimizer_sees_upsample=True``) start with fresh moments."""
         ck = torch.load(path, map_location=self.device, weights_only=False)
         self.model.load_state_dict(ck["model_state_dict"])       # bumps parameter versions -> packed weights rebuilt
         if resume:
-            self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+            self._load_optimizer_state(ck["optimizer_state_dict"])
             self.scheduler.load_state_dict(ck["scheduler_state_dict"])
             self.history = ck.get("history", self.history)
             self.start_epoch = int(ck["epoch"]) + 1
             self.best_rmse = float(ck.get("best_rmse", ck.get("rmse", float("inf"))))
             self.best_epoch = int(ck.get("best_epoch", ck["epoch"]))
-            if self.early_stopping is not None and ck.get("early_stopping"):
-                self.early_stopping.load_state_dict(ck["early_stopping"])
+            if self.early_stopping is not None:
+                if ck.get("early_stopping"):
+                    self.early_stopping.load_state_dict(ck["early_stopping"])
+                elif "rmse" in ck:
+                    # reference-written file: it is only ever saved at a new best (trainer.py:386-418), so its rmse IS
+                    # the best score so far -- without this the first resumed epoch would overwrite best_model.pth
+                    self.early_stopping.best_score = float(ck["rmse"])
+                    self.early_stopping.best_epoch = int(ck["epoch"])
         return ck
+
+    def _load_optimizer_state(self, sd: dict) -> None:
+        n_saved = sum(len(g["params"]) for g in sd["param_groups"])
+        n_have = sum(len(g["params"]) for g in self.optimizer.param_groups)
+        if n_saved > n_have:
+            raise RuntimeError(
+                f"checkpoint optimizer state covers {n_saved} parameters but this trainer optimises {n_have}: it was "
+                "written with optimizer_sees_upsample=True; resume it with the same setting")
+        if n_saved < n_have:
+            if len(sd["param_groups"]) != 1 or len(self.optimizer.param_groups) != 1:
+                raise RuntimeError("cannot align a partial optimizer state with several parameter groups")
+            sd = {"state": sd["state"], "param_groups": [dict(sd["param_groups"][0])]}
+            saved_ids = list(sd["param_groups"][0]["params"])
+            fresh = [i for i in range(n_have + len(saved_ids)) if i not in set(saved_ids)][:n_have - n_saved]
+            sd["param_groups"][0]["params"] = saved_ids + fresh   # saved ids first: the order matches model.parameters()
+        self.optimizer.load_state_dict(sd)
 
 
 class SyntheticRainBatches:

@@ -129,3 +129,50 @@ def test_shard_batch():
     assert [shard_batch(64, r, 8) for r in (0, 7)] == [slice(0, 8), slice(56, 64)]
     with pytest.raises(ValueError):
         shard_batch(10, 0, 4)
+
+
+class _FakeCell(torch.nn.Module):
+    """Stands in for plconv.nn.ConvLSTMCell on CPU: a `conv` parameter holder plus the `_packed` marker attribute; the
+    fused rollout's backward hands (dW, db) to `_grad_sink` when the layer's t = 0 step has been queued."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(3, 8, 3, padding=1)
+
+    def _packed(self, need_dgrad):
+        raise AssertionError("never called on CPU")
+
+
+def w_grad_sink(rank, world, plconv):
+    from plconv.parallel import GradReducer, nonfinite_flag
+    torch.manual_seed(0)
+    top, bottom, other = _FakeCell(), _FakeCell(), torch.nn.Linear(2, 2)
+    red = GradReducer([top.parameters(), list(bottom.parameters()) + list(other.parameters())])
+    assert red.attach_cell_sinks(torch.nn.ModuleList([top, bottom, other])) == 2
+    red.zero_grad()
+    g = torch.Generator().manual_seed(10 + rank)
+    gw = [torch.randn(8, 3, 3, 3, generator=g) for _ in range(2)]
+    gb = [torch.randn(8, generator=g) for _ in range(2)]
+    # what _StackRolloutFn.backward does at t = 0, top layer first
+    assert top._grad_sink(top, gw[0], gb[0]) is True
+    launched_top = red.buckets[0]["pending"] == 0 and (world == 1 or red.buckets[0]["handle"] is not None)
+    assert bottom._grad_sink(bottom, gw[1], gb[1]) is True
+    launched_bottom_early = red.buckets[1]["pending"] == 0       # `other` has not reported yet: must still be pending
+    other(torch.ones(1, 2)).sum().backward()                      # ordinary autograd hook completes the mixed bucket
+    red.finish()
+    flag = nonfinite_flag(torch.tensor(float("inf") if rank == 1 else 0.0))
+    red.remove()
+    return (top.conv.weight.grad.clone(), bottom.conv.bias.grad.clone(), launched_top, launched_bottom_early,
+            float(flag), top._grad_sink is None)
+
+
+def test_per_layer_gradient_sink_and_device_flag():
+    out = _run("w_grad_sink")
+    gens = [torch.Generator().manual_seed(10 + r) for r in (0, 1)]
+    gw = [[torch.randn(8, 3, 3, 3, generator=g) for _ in range(2)] for g in gens]
+    gb = [[torch.randn(8, generator=g) for _ in range(2)] for g in gens]
+    for r in (0, 1):
+        w_top, b_bottom, launched_top, early, flag, removed = out[r]
+        assert torch.allclose(w_top, (gw[0][0] + gw[1][0]) / 2, atol=1e-6)
+        assert torch.allclose(b_bottom, (gb[0][1] + gb[1][1]) / 2, atol=1e-6)
+        assert launched_top and not early and flag == 1.0 and removed

@@ -275,3 +275,52 @@ def test_reference_quirk_mode_single_process_accumulates_and_clips_frozen_grads(
         assert torch.allclose(a, b_, atol=1e-7), n
     for a, b_ in zip(tr.model.up.parameters(), ref.up.parameters()):
         assert torch.allclose(a.grad, b_.grad, rtol=1e-5, atol=1e-8)      # accumulated and rescaled by every clip
+
+
+def test_reference_written_checkpoint_resumes_with_real_generator(tmp_path):
+    """A checkpoint as the REFERENCE writes it (trainer.py:402-418): Adam built before ``upsample_blocks`` exist, so
+    its param_groups hold only the leading parameters.  Resuming with the default optimizer_sees_upsample=True must
+    restore those moments, give the lazy blocks fresh ones, and seed early stopping from the saved rmse."""
+    torch.manual_seed(3)
+    kw = dict(in_channels=1, dem_channels=1, lu_channels=2, hidden_dims=[16, 32], scale_factor=4)
+    ref_like = plconv.Generator(mode="fp32", **kw)
+    opt = torch.optim.Adam(ref_like.parameters(), lr=5e-4)          # trainer.py:153-158: BEFORE the first forward
+    n_before = len(opt.param_groups[0]["params"])
+    ref_like.materialize(4)                                          # what the first forward does (generator.py:129)
+    for p in opt.param_groups[0]["params"]:
+        p.grad = torch.randn_like(p)
+    opt.step()
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.7, patience=10)
+    path = tmp_path / "best_model.pth"
+    torch.save({"epoch": 6, "model_state_dict": ref_like.state_dict(), "optimizer_state_dict": opt.state_dict(),
+                "scheduler_state_dict": sched.state_dict(), "rmse": 1.25, "history": {"epoch": list(range(7))}}, path)
+
+    cfg = TrainerConfig(hidden_dims=(16, 32), lu_channels=2, scale_factor=4, mode="fp32", early_stopping_patience=5)
+    tr = Trainer(cfg, device="cpu", model=plconv.Generator(mode="fp32", **kw), loss_module=_StubLoss())
+    n_all = len(tr.optimizer.param_groups[0]["params"])
+    assert n_all == n_before + 4                                     # two x2 blocks: weight + bias each
+    tr.load_checkpoint(str(path))
+    state = tr.optimizer.state_dict()["state"]
+    assert sorted(state) == list(range(n_before))                    # restored moments for the leading parameters only
+    want = opt.state_dict()["state"]
+    for i in range(n_before):
+        assert torch.equal(state[i]["exp_avg"], want[i]["exp_avg"])
+    for a, b in zip(tr.optimizer.param_groups[0]["params"], tr.model.parameters()):
+        assert a is b
+    assert tr.start_epoch == 7 and tr.best_rmse == pytest.approx(1.25)
+    assert tr.early_stopping.best_score == pytest.approx(1.25)       # the first resumed epoch must beat it to save
+    assert tr.early_stopping(1.3, 7) is False
+    # and the step after the resume runs (fresh moments are created lazily for the upsample parameters)
+    for p in tr.optimizer.param_groups[0]["params"]:
+        p.grad = torch.zeros_like(p)
+    tr.optimizer.step()
+    assert len(tr.optimizer.state_dict()["state"]) == n_all
+
+    quirk = Trainer(TrainerConfig(hidden_dims=(16, 32), lu_channels=2, scale_factor=4, mode="fp32",
+                                  optimizer_sees_upsample=False), device="cpu",
+                    model=plconv.Generator(mode="fp32", **kw), loss_module=_StubLoss())
+    quirk.load_checkpoint(str(path))                                 # same parameter count as the reference: direct load
+    full = tmp_path / "full.pth"
+    tr.save_checkpoint(str(full), 7, 1.0)
+    with pytest.raises(RuntimeError, match="optimizer_sees_upsample"):
+        quirk.load_checkpoint(str(full))
