@@ -146,11 +146,47 @@ int plc_conv_wgrad_unpack(const PlcConvDesc* d, const float* dW_acc, float* dW_o
 int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void* w_packed_dgrad, void* dx,
                  float* dW_acc, float* db_acc, void* stream);
 
+/* ---- strided 2-D / 3-D convolution on the same core (bf16; the discriminator of the GAN training step) ----------
+ * No reference counterpart (the reference has no discriminator: SURVEY.md section 0); the eager spec is
+ * oracle/gan_oracle.py (torch F.conv2d / F.conv3d).  North-star: "the discriminator's strided 2D/3D convolutions reuse
+ * the same implicit-GEMM core" -- these entry points run conv_igemm_tc_kernel with strided (elementStrides) and, for a
+ * time kernel, 5-D [C, W, H, T, B] tensor maps; TMA zero fill is the zero padding in all three dimensions.
+ *   x   [B, T, H, W, Cin]  bf16 (T = 1, kt = 1, stride_t = 1: a 2-D conv over B images)
+ *   w   [Cout, Cin, kt, k, k] fp32 (torch Conv3d layout; Conv2d layout when kt = 1), bias [Cout]
+ *   out [B, To, Ho, Wo, Cout] bf16, To = (T-1)/stride_t + 1, Ho = (H-1)/stride + 1 (padding kt/2, k/2, k/2)
+ *   act: 0 none, 1 ReLU, 2 LeakyReLU(slope), applied after the bias.
+ * Backward: plc_convnd_grad_prep forms dZ = dY * act'(Y) and, for a strided conv, its zero-inserted copy on the INPUT
+ * grid [B, T, H, W, Cout] (dz_dilated; NULL when all strides are 1 or when no dx will be asked for).  plc_convnd_bwd: dx [B,T,H,W,Cin]
+ * (nullable) = stride-1 conv of the zero-inserted dZ with the flipped image; dW_acc = accumulator image
+ * (plc_convnd_wgrad_acc_bytes; plc_convnd_wgrad_unpack ADDS it into [Cout,Cin,kt,k,k]); db_acc [Cout] += (nullable). */
+typedef struct PlcConvNdDesc {
+  int32_t B, T, H, W;          /* input grid                                   */
+  int32_t Cin, Cout;           /* multiples of 8 (callers zero-pad)            */
+  int32_t kt, k;               /* odd kernel sizes (time, space), <= 7         */
+  int32_t stride_t, stride;    /* 1 or 2                                       */
+  int32_t act;                 /* 0 none, 1 ReLU, 2 LeakyReLU                  */
+  float slope;                 /* LeakyReLU negative slope                     */
+  int32_t has_bias;
+} PlcConvNdDesc;
+int plc_convnd_out_shape(const PlcConvNdDesc* d, int* T_out, int* H_out, int* W_out);
+size_t plc_convnd_packed_weight_bytes(const PlcConvNdDesc* d, int pack_kind);
+int plc_convnd_pack_weight(const PlcConvNdDesc* d, int pack_kind, const float* w, const float* bias, void* w_packed,
+                           float* bias_packed, void* stream);
+int plc_convnd_fwd(const PlcConvNdDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, void* out,
+                   void* stream);
+int plc_convnd_grad_prep(const PlcConvNdDesc* d, const void* y, const void* dy, void* dz, void* dz_dilated, void* stream);
+size_t plc_convnd_wgrad_acc_bytes(const PlcConvNdDesc* d);
+int plc_convnd_wgrad_unpack(const PlcConvNdDesc* d, const float* dW_acc, float* dW, void* stream);
+int plc_convnd_bwd(const PlcConvNdDesc* d, const void* x, const void* dz, const void* dz_dilated,
+                   const void* w_packed_dgrad, void* dx, float* dW_acc, float* db_acc, void* stream);
+
 /* ---- per-launch timing (bench.py's roofline / step breakdown) -------------------------------------
  * plc_timing_enable(1) clears the record and makes every kernel launch of the library record a CUDA event pair on
  * its launching stream, tagged with a PlcKernelKind; plc_timing_enable(0) stops recording (and clears).
- * plc_timing_collect synchronises the recorded events, writes up to `capacity` (kind, milliseconds) pairs in launch
- * order, clears the record and returns the number of launches recorded (which may exceed `capacity`).  A kind groups
+ * plc_timing_collect synchronises the recorded events, writes up to `capacity` (kind, milliseconds, algorithmic FLOPs)
+ * triples in launch order, clears the record and returns the number of launches recorded (which may exceed
+ * `capacity`).  FLOPs = 2*M*N*K over the TRUE (unpadded) channel counts for the contractions, 0 for other kernels
+ * (`flops` may be NULL).  A kind groups
  * the launches one ABI call makes for that purpose (normally exactly one kernel).  Never enable it inside a region
  * whose time is reported: the events cost host time and serialise nothing but are not free.                    */
 typedef enum PlcKernelKind {
@@ -169,7 +205,7 @@ typedef enum PlcKernelKind {
   PLC_K_ELEMENTWISE = 12    /* layout conversions, gradient masks, accumulator unpack                          */
 } PlcKernelKind;
 int plc_timing_enable(int on);
-int plc_timing_collect(int* kinds, float* ms, int capacity);
+int plc_timing_collect(int* kinds, float* ms, double* flops, int capacity);
 
 /* ---- debug ---------------------------------------------------------------------------------
  * Developer aid (tools/kprof.py): when set to a zeroed device buffer of at least 148*16 uint64, the tensor-core conv

@@ -33,7 +33,14 @@ class PlcLossDesc(ctypes.Structure):
                                                "lambda_temporal")])
 
 
+class PlcConvNdDesc(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "Cin", "Cout", "kt", "k", "stride_t", "stride", "act")] +
+                [("slope", ctypes.c_float), ("has_bias", ctypes.c_int32)])
+
+
 _vp, _sz, _int = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+_np = ctypes.POINTER(PlcConvNdDesc)
+_ip = ctypes.POINTER(ctypes.c_int)
 _dp = ctypes.POINTER(PlcCellDesc)
 _cp = ctypes.POINTER(PlcConvDesc)
 _lp = ctypes.POINTER(PlcLossDesc)
@@ -58,8 +65,17 @@ SIGNATURES = {
     "plc_conv_fwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "plc_conv_grad_mask": (_int, [_cp, _vp, _vp, _vp, _vp]),
     "plc_conv_bwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "plc_convnd_out_shape": (_int, [_np, _ip, _ip, _ip]),
+    "plc_convnd_packed_weight_bytes": (_sz, [_np, _int]),
+    "plc_convnd_pack_weight": (_int, [_np, _int, _vp, _vp, _vp, _vp, _vp]),
+    "plc_convnd_fwd": (_int, [_np, _vp, _vp, _vp, _vp, _vp]),
+    "plc_convnd_grad_prep": (_int, [_np, _vp, _vp, _vp, _vp, _vp]),
+    "plc_convnd_wgrad_acc_bytes": (_sz, [_np]),
+    "plc_convnd_wgrad_unpack": (_int, [_np, _vp, _vp, _vp]),
+    "plc_convnd_bwd": (_int, [_np, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plc_timing_enable": (_int, [_int]),
-    "plc_timing_collect": (_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float), _int]),
+    "plc_timing_collect": (_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float),
+                                  ctypes.POINTER(ctypes.c_double), _int]),
     "plc_debug_set_prof": (_int, [_vp]),
     "plc_debug_set_cta_group": (_int, [_int]),
     "plc_debug_set_patch": (_int, [_int]),
@@ -107,6 +123,25 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().plc_last_error()
         raise RuntimeError(f"{what} failed (status {status}): {msg.decode() if msg else '?'}")
+
+
+# ---- per-launch timing (include/plc.h: PlcKernelKind) ---------------------------------------------------------
+KERNEL_KINDS = ("cell_fwd", "cell_fwd_zero", "bwd_gates", "bwd_dgrad", "bwd_wgrad", "conv_fwd", "conv_dgrad",
+                "conv_wgrad", "frontend", "head", "loss", "pack", "elementwise")
+
+
+def timing_enable(on: bool) -> None:
+    """Start (clearing the record) / stop the library's per-launch CUDA-event timing.  Not for reported regions."""
+    check(load().plc_timing_enable(1 if on else 0), "plc_timing_enable")
+
+
+def timing_collect(capacity: int = 1 << 16):
+    """-> list of (kind name, milliseconds, algorithmic FLOPs) in launch order; synchronises and clears the record."""
+    kinds = (ctypes.c_int * capacity)()
+    ms = (ctypes.c_float * capacity)()
+    fl = (ctypes.c_double * capacity)()
+    n = load().plc_timing_collect(kinds, ms, fl, capacity)
+    return [(KERNEL_KINDS[kinds[i]], float(ms[i]), float(fl[i])) for i in range(min(n, capacity))]
 
 
 # ---- packed-weight cache generation --------------------------------------------------------------------------

@@ -37,6 +37,13 @@ struct ConvTcParams {
   int num_m_tiles, num_n_tiles, num_tiles;
   // exact n / d for n < 2^20 via one 64-bit multiply: q = (n * mul) >> 40, mul = ceil(2^40 / d)  (0 = use '/')
   unsigned long long div_n_tiles, div_tiles_x, div_tiles_y;
+  // strided / 3-D convolutions (discriminator; default pipeline only).  H, W above are the OUTPUT grid; the input
+  // grid lives in the tensor map, whose elementStrides make a tap box pick every `stride`-th input pixel.  With
+  // nd5 the A maps are 5-D [C, W, H, T, B], "images" b = sample * T_out + t_out, and the taps gain a time loop.
+  int stride;                // spatial stride (1 or 2); tap box origin = out * stride + tap - pad
+  int nd5;                   // 1 = 5-D A tensor maps with a time dimension
+  int kt, pad_t, stride_t;   // time taps (1 = none), their padding and stride
+  int T_out;                 // output frames per sample (nd5)
   int kc;                    // channels per TMA box: 64, 32 or 16 (narrow sources pack G = 64/kc taps into one K stage)
   int chunks0, chunks1;      // kc-channel chunks of source 0 / source 1
   int num_boxes;             // ksize^2 * (chunks0 + chunks1) boxes of [kc ch x 128 px]
@@ -66,7 +73,8 @@ struct ConvTcParams {
   __nv_bfloat16* out1;       // [M, Ntot-Cin] bf16 or nullptr      (PLAIN)
   int n_total;               // PLAIN: total valid output columns
   const float* plain_bias;   // PLAIN: [n_total] fp32 in packed column order, or nullptr
-  int plain_relu;            // PLAIN: apply max(x, 0)
+  int plain_relu;            // PLAIN: apply max(x, plain_slope * x): slope 0 = ReLU, 0.2 = LeakyReLU(0.2)
+  float plain_slope;
   int plain_shuffle;         // PLAIN: PixelShuffle(2) store: column n' = sub*(n_total/4) + c -> out0[b, 2y+sub/2, 2x+sub%2, c]
   int plain_tma;             // PLAIN: outputs leave through smem staging + TMA tensor stores (tmap_o0 / tmap_o1 valid;
                              // needs no shuffle and 64-channel-aligned out0 / out1); 0 = per-thread 16-byte stores
@@ -241,20 +249,27 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         int n_tile, b, y0, x0;
         decode_tile<kCta>(p, tile, rank, n_tile, b, y0, x0);
         const int n_row = n_tile * N_TILE + rank * (N_TILE / kCta);
-        // box iterator over (source, tap = (ky, kx), kc-chunk); the K tail re-loads the last box (zero weights)
-        int src = p.chunks0 > 0 ? 0 : 1, ky = 0, kx = 0, ck = 0, bx = 0;
+        // box iterator over (source, tap = (kz, ky, kx), kc-chunk); the K tail re-loads the last box (zero weights)
+        int src = p.chunks0 > 0 ? 0 : 1, kz = 0, ky = 0, kx = 0, ck = 0, bx = 0;
+        // strided / 3-D convs: tap origin in INPUT coordinates; image b = sample * T_out + output frame
+        const int xs = x0 * p.stride - p.pad, ys = y0 * p.stride - p.pad;
+        int smp = b, ts = 0;
+        if (p.nd5) { smp = b / p.T_out; ts = (b - smp * p.T_out) * p.stride_t - p.pad_t; }
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          int cch[G], cdx[G], cdy[G], csrc[G];
+          int cch[G], cdx[G], cdy[G], cdt[G], csrc[G];
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            cch[g] = ck * KC; cdx[g] = x0 + kx - p.pad; cdy[g] = y0 + ky - p.pad; csrc[g] = src;
+            cch[g] = ck * KC; cdx[g] = xs + kx; cdy[g] = ys + ky; cdt[g] = ts + kz; csrc[g] = src;
             if (bx + 1 < p.num_boxes) {
               ++bx;
               if (++ck == (src ? p.chunks1 : p.chunks0)) {
                 ck = 0;
                 if (++kx == p.ksize) {
                   kx = 0;
-                  if (++ky == p.ksize) { ky = 0; src = 1; }
+                  if (++ky == p.ksize) {
+                    ky = 0;
+                    if (++kz == p.kt) { kz = 0; src = 1; }
+                  }
                 }
               }
             }
@@ -266,16 +281,26 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
               const uint32_t bar = full_base + stage * 8;
               mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
-              for (int g = 0; g < G; ++g)
-                tma_load_4d_s(a_dst + g * sub_bytes, csrc[g] ? &tmap_a1 : &tmap_a0, bar, cch[g], cdx[g], cdy[g], b);
+              for (int g = 0; g < G; ++g) {
+                if (p.nd5)
+                  tma_load_5d_s(a_dst + g * sub_bytes, csrc[g] ? &tmap_a1 : &tmap_a0, bar, cch[g], cdx[g], cdy[g], cdt[g],
+                                smp);
+                else
+                  tma_load_4d_s(a_dst + g * sub_bytes, csrc[g] ? &tmap_a1 : &tmap_a0, bar, cch[g], cdx[g], cdy[g], b);
+              }
               tma_load_2d_s(b_dst, &tmap_b, bar, kb * kBlockK, n_row);
             } else {
               // both CTAs' bytes are counted on the LEADER's full barrier (the MMA issuer waits there)
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
               const uint32_t bar = mapa_u32(full_base + stage * 8, 0);
 #pragma unroll
-              for (int g = 0; g < G; ++g)
-                tma_load_4d_cg2(a_dst + g * sub_bytes, csrc[g] ? &tmap_a1 : &tmap_a0, bar, cch[g], cdx[g], cdy[g], b);
+              for (int g = 0; g < G; ++g) {
+                if (p.nd5)
+                  tma_load_5d_cg2(a_dst + g * sub_bytes, csrc[g] ? &tmap_a1 : &tmap_a0, bar, cch[g], cdx[g], cdy[g],
+                                  cdt[g], smp);
+                else
+                  tma_load_4d_cg2(a_dst + g * sub_bytes, csrc[g] ? &tmap_a1 : &tmap_a0, bar, cch[g], cdx[g], cdy[g], b);
+              }
               tma_load_2d_cg2(b_dst, &tmap_b, bar, kb * kBlockK, n_row);
             }
           }
@@ -992,7 +1017,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
             }
             if (p.plain_relu) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], p.plain_slope * f[e]);
             }
             // box nl/64 = [128 px][64 ch] bf16, 128-byte rows, SWIZZLE_128B: chunk ^= row & 7
             const uint32_t dst = so + (nl >> 6) * 16384 + row * 128 + ((((nl >> 3) & 7) ^ (row & 7)) << 4);
@@ -1039,7 +1064,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                 }
                 if (p.plain_relu) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                  for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], p.plain_slope * f[e]);
                 }
                 uint4 o;
                 o.x = pack_bf16x2(f[0], f[1]);

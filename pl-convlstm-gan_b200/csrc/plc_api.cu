@@ -100,14 +100,15 @@ cudaError_t set_smem_once(Fn fn, int bytes) {
 // roofline of the dominant one from live per-launch durations.  Off by default: zero cost beyond one relaxed load.
 std::atomic<int> g_timing_on{0};
 std::mutex g_timing_mu;
-struct TimedLaunch { cudaEvent_t e0, e1; int kind; };
+struct TimedLaunch { cudaEvent_t e0, e1; int kind; double flops; };
 std::vector<TimedLaunch> g_timed;
 
 struct LaunchTimer {
   cudaStream_t st;
   int kind;
+  double flops;            // algorithmic FLOPs of the launch (2*M*N*K over the TRUE channel counts; 0 = not a contraction)
   cudaEvent_t e0 = nullptr;
-  LaunchTimer(int kind_, cudaStream_t st_) : st(st_), kind(kind_) {
+  LaunchTimer(int kind_, cudaStream_t st_, double flops_ = 0.0) : st(st_), kind(kind_), flops(flops_) {
     if (g_timing_on.load(std::memory_order_relaxed)) {
       if (cudaEventCreate(&e0) != cudaSuccess || cudaEventRecord(e0, st) != cudaSuccess) { cudaGetLastError(); e0 = nullptr; }
     }
@@ -121,7 +122,7 @@ struct LaunchTimer {
       return;
     }
     std::lock_guard<std::mutex> lk(g_timing_mu);
-    g_timed.push_back({e0, e1, kind});
+    g_timed.push_back({e0, e1, kind, flops});
   }
 };
 
@@ -213,6 +214,11 @@ int make_tmap_mat(CUtensorMap* tm, const void* ptr, long rows, long cols, int bo
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// algorithmic FLOPs of a conv-shaped contraction over B*H*W output pixels: 2 * M * Cout * (Cin * k^2)
+inline double conv_flops(int B, int H, int W, int cin, int cout, int k) {
+  return 2.0 * B * H * W * static_cast<double>(cin) * cout * k * k;
+}
+
 int check_desc(const PlcCellDesc* d) {
   if (!d) return fail(PLC_ERR_BAD_DESC, "null descriptor");
   if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Ch <= 0 || d->Cin < 0)
@@ -278,7 +284,9 @@ int pick_plain_n_tile(int n_total) {
 // K-side geometry: sources with C0 and C1 channels are read as TMA boxes of kc channels (64, 32 or 16); G = 64/kc
 // boxes (consecutive (source, tap, chunk) triples) fill one 64-element K stage.  Pick the kc with the fewest stages.
 struct KGeom { int kc, chunks0, chunks1, num_boxes, num_kb; };
-KGeom kgeom(int C0, int C1, int k) {
+KGeom kgeom_taps(int C0, int C1, int taps);
+KGeom kgeom(int C0, int C1, int k) { return kgeom_taps(C0, C1, k * k); }
+KGeom kgeom_taps(int C0, int C1, int taps) {
   KGeom best{};
   const int cands[3] = {64, 32, 16};
   for (int kc : cands) {
@@ -286,7 +294,7 @@ KGeom kgeom(int C0, int C1, int k) {
     g.kc = kc;
     g.chunks0 = cdiv(C0, kc);
     g.chunks1 = cdiv(C1, kc);
-    g.num_boxes = k * k * (g.chunks0 + g.chunks1);
+    g.num_boxes = taps * (g.chunks0 + g.chunks1);
     g.num_kb = cdiv(g.num_boxes, 64 / kc);
     if (best.kc == 0 || g.num_kb < best.num_kb) best = g;
   }
@@ -336,8 +344,8 @@ __global__ void pack_w_tc_fwd_kernel(const float* __restrict__ w, __nv_bfloat16*
 // PixelShuffle(2) store (natural channel n = c*4 + sub), else n' = n.  bias_p[n'] = bias[n].
 __global__ void pack_w_conv_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                        __nv_bfloat16* __restrict__ out, float* __restrict__ bias_p, int Cin, int Cout,
-                                       int ksize, KGeom kg, int shuffle) {
-  const int kk = ksize * ksize, ktot = kg.num_kb * 64, cps = Cout >> 2;
+                                       int kk /* taps */, KGeom kg, int shuffle) {
+  const int ktot = kg.num_kb * 64, cps = Cout >> 2;
   const size_t total = static_cast<size_t>(Cout) * ktot;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -353,8 +361,7 @@ __global__ void pack_w_conv_fwd_kernel(const float* __restrict__ w, const float*
 }
 // generic dgrad image Wd[c][k'] : rows c in [0, ctot) ; k' = (tap', chunk of dZ channel n)*64 + jj, flipped taps
 __global__ void pack_w_conv_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int ctot,
-                                         int nout, int ksize, KGeom kg) {
-  const int kk = ksize * ksize;
+                                         int nout, int kk /* taps: k*k or kt*k*k */, KGeom kg) {
   const int ktot = kg.num_kb * 64;
   const size_t total = static_cast<size_t>(ctot) * ktot;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -364,8 +371,8 @@ __global__ void pack_w_conv_dgrad_kernel(const float* __restrict__ w, __nv_bfloa
     const int n = decode_packed_k(kp, kg.kc, kk, kg.chunks0, 0, nout, 0, tap);
     float v = 0.f;
     if (n >= 0) {
-      const int fy = ksize - 1 - tap / ksize, fx = ksize - 1 - tap % ksize;
-      v = w[(static_cast<size_t>(n) * ctot + c) * kk + fy * ksize + fx];
+      // every tap coordinate flipped == the row-major tap index reversed
+      v = w[(static_cast<size_t>(n) * ctot + c) * kk + (kk - 1 - tap)];
     }
     out[idx] = __float2bfloat16(v);
   }
@@ -447,7 +454,7 @@ int pick_cta_group(int num_m_tiles) {
 
 template <int NT, int EPI, int CTA>
 int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                        const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st, int kind) {
+                        const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st, int kind, double flops) {
   using Cfg = plc::ConvTcCfg<NT, CTA, EPI>;
   plc::ConvTcParams p = p_in;
   p.prof = g_prof_buf;
@@ -484,7 +491,7 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LaunchTimer timer(kind, st);
+  LaunchTimer timer(kind, st, flops);
   PLC_CUDA(cudaLaunchKernelEx(&cfg, kfn, p, a0, a1, b, o0, o1));
   return PLC_OK;
 }
@@ -492,11 +499,12 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
 // o0 / o1: output tensor maps of the TMA-store epilogue (forward, N_TILE = 256); ignored by the other instantiations
 template <int EPI>
 int launch_conv_tc(int n_tile, int cta, const plc::ConvTcParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
-                   const CUtensorMap& b, const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st, int kind) {
+                   const CUtensorMap& b, const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st, int kind,
+                   double flops) {
 #define PLC_LAUNCH_TC(NT)                                                                     \
   case NT:                                                                                    \
-    return cta == 2 ? launch_conv_tc_inst<NT, EPI, 2>(p, a0, a1, b, o0, o1, st, kind)         \
-                    : launch_conv_tc_inst<NT, EPI, 1>(p, a0, a1, b, o0, o1, st, kind);
+    return cta == 2 ? launch_conv_tc_inst<NT, EPI, 2>(p, a0, a1, b, o0, o1, st, kind, flops)  \
+                    : launch_conv_tc_inst<NT, EPI, 1>(p, a0, a1, b, o0, o1, st, kind, flops);
   switch (n_tile) {
     PLC_LAUNCH_TC(64)
     PLC_LAUNCH_TC(128)
@@ -512,6 +520,7 @@ void fill_geom(const PlcCellDesc* d, const TcGeom& g, plc::ConvTcParams* p) {
   memset(p, 0, sizeof(*p));
   p->B = d->B; p->H = d->H; p->W = d->W;
   p->ksize = d->k; p->pad = d->k / 2;
+  p->stride = 1; p->kt = 1; p->stride_t = 1; p->T_out = 1;      // plain 2-D stride-1 conv unless the caller says otherwise
   p->tw = g.tw; p->th = g.th; p->tw_log2 = g.tw_log2;
   p->tiles_x = g.tiles_x; p->tiles_y = g.tiles_y;
   p->num_m_tiles = d->B * g.tiles_x * g.tiles_y;
@@ -612,14 +621,21 @@ int lstm_tc_setup(const PlcCellDesc* d, TcGeom* g, plc::ConvTcParams* p, int epi
 }
 
 // wgrad on the tensor cores + bias-gradient column sum (bf16 mode)
-struct WgradShape { int B, H, W, k, Cin, Ch, N; };   // sources x [.,Cin] and h [.,Ch]; N = dZ channels
+// sources x [.,Cin] and h [.,Ch]; N = dZ channels.  B, H, W = the OUTPUT grid (dZ).  Strided / 3-D convs: the source
+// lives on its own grid [Bs, Ts, Hs, Ws] and is read through strided (and, with kt > 1 or stride_t > 1, 5-D) maps.
+struct WgradShape {
+  int B, H, W, k, Cin, Ch, N;
+  int stride = 1, kt = 1, stride_t = 1, T_out = 1;
+  int Bs = 0, Ts = 0, Hs = 0, Ws = 0;      // source grid (0 = same as the output grid)
+};
 
 int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev, const void* dz, float* dW, float* db,
                           cudaStream_t st, int kind);
 
 int launch_wgrad_tc(const PlcCellDesc* d, const void* x, const void* h_prev, const void* dz, float* dW, float* db,
                     cudaStream_t st) {
-  WgradShape w{d->B, d->H, d->W, d->k, d->Cin, d->Ch, 4 * d->Ch};
+  WgradShape w;
+  w.B = d->B; w.H = d->H; w.W = d->W; w.k = d->k; w.Cin = d->Cin; w.Ch = d->Ch; w.N = 4 * d->Ch;
   return launch_wgrad_tc_shape(&w, x, h_prev, dz, dW, db, st, PLC_K_BWD_WGRAD);
 }
 
@@ -635,9 +651,12 @@ int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev
   p.tw = g.tw; p.th = g.th; p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y;
   p.PB = d->B * g.tiles_x * g.tiles_y;
   p.chunks0 = cdiv(d->Cin, 64); p.chunks1 = cdiv(d->Ch, 64);
-  p.CB = d->k * d->k * (p.chunks0 + p.chunks1);
+  p.CB = d->kt * d->k * d->k * (p.chunks0 + p.chunks1);
+  const bool nd5 = d->kt > 1 || d->stride_t > 1;
+  const bool general = nd5 || d->stride > 1;                 // strided / 3-D: single-CTA kernel only
+  p.stride = d->stride; p.nd5 = nd5; p.kt = d->kt; p.pad_t = d->kt / 2; p.stride_t = d->stride_t; p.T_out = d->T_out;
   // CTA pairs (cta_group::2, 256-row output tiles) once dZ has >= 256 channels and there is enough work
-  const bool pair = d->N >= 256 && pick_cta_group(p.PB / 2) == 2;
+  const bool pair = !general && d->N >= 256 && pick_cta_group(p.PB / 2) == 2;
   p.num_groups = cdiv(p.CB, plc::kWgMaxGB);
   p.GB = cdiv(p.CB, p.num_groups);
   if (pair) p.GB = 2 * cdiv(p.GB, 2);                      // even: the pair splits the columns in halves
@@ -657,13 +676,17 @@ int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev
   if (d->Ch > 0) {
     if ((rc = make_tmap_act(&t1, h_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th))) return rc;
   }
-  if (d->Cin > 0) {
+  if (d->Cin > 0 && general) {
+    if ((rc = make_tmap_act(&t0, x, d->Bs, d->Hs, d->Ws, d->Cin, g.tw, g.th, 2, 64, CU_TENSOR_MAP_SWIZZLE_128B, d->stride,
+                            nd5 ? d->Ts : 0)))
+      return rc;
+  } else if (d->Cin > 0) {
     if ((rc = make_tmap_act(&t0, x, d->B, d->H, d->W, d->Cin, g.tw, g.th))) return rc;
   } else {
     t0 = t1;
   }
   if (d->Ch == 0) t1 = t0;
-  LaunchTimer timer(kind, st);
+  LaunchTimer timer(kind, st, conv_flops(d->B, d->H, d->W, d->Cin + d->Ch, d->N, d->k) * d->kt);
   if (pair) {
     PLC_CUDA(set_smem_once<TagW2>(plc::wgrad_tc_kernel2, plc::kW2SmemBytes));
     cudaLaunchConfig_t cfg;
@@ -741,7 +764,8 @@ int plc_pack_weight(const PlcCellDesc* d, int pack_kind, const float* w_oihw, vo
                                                        d->k, pick_ch_tile(d->Ch), kgeom(d->Cin, d->Ch, d->k));
     else
       pack_w_conv_dgrad_kernel<<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed),
-                                                           d->Cin + d->Ch, 4 * d->Ch, d->k, kgeom(4 * d->Ch, 0, d->k));
+                                                           d->Cin + d->Ch, 4 * d->Ch, d->k * d->k,
+                                                           kgeom(4 * d->Ch, 0, d->k));
   }
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;
@@ -825,7 +849,8 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     if ((rc = make_tmap_act(&to1, h_out, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, 64))) return rc;
   }
   return launch_conv_tc<plc::EPI_LSTM_FWD>(g.n_tile, cta, p, ta0, ta1, tb, to0, to1, st,
-                                           zero_state ? PLC_K_CELL_FWD_ZERO : PLC_K_CELL_FWD);
+                                           zero_state ? PLC_K_CELL_FWD_ZERO : PLC_K_CELL_FWD,
+                                           conv_flops(d->B, d->H, d->W, (zero_state ? 0 : d->Ch) + d->Cin, 4 * d->Ch, d->k));
 }
 
 size_t plc_bwd_workspace_bytes(const PlcCellDesc* d) {
@@ -936,7 +961,8 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
       return rc;
     if ((rc = make_tmap_act(&tdc, dc_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
   }
-  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, tzo, tdc, st, PLC_K_BWD_GATES)))
+  if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, tzo, tdc, st, PLC_K_BWD_GATES,
+                                                    conv_flops(d->B, d->H, d->W, d->Cin + d->Ch, 4 * d->Ch, d->k))))
     return rc;
 
   // 2) dgrad: conv of dZ (4Ch channels) with the flipped/transposed image -> dx, dh_prev
@@ -960,7 +986,10 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     if ((rc = make_tmap_mat(&tbd, w_packed_dgrad, n_total, (long)q.num_kb * 64, 64, nt / ctaq))) return rc;
     CUtensorMap tq0 = tz, tq1 = tz;
     if ((rc = setup_plain_stores(&q, d->B, d->H, d->W, &tq0, &tq1))) return rc;
-    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, ctaq, q, tz, tz, tbd, tq0, tq1, st, PLC_K_BWD_DGRAD))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, ctaq, q, tz, tz, tbd, tq0, tq1, st, PLC_K_BWD_DGRAD,
+                                             conv_flops(d->B, d->H, d->W, 4 * d->Ch, (dx ? d->Cin : 0) + (dh_prev ? d->Ch : 0),
+                                                        d->k))))
+      return rc;
   }
 
   // 3) wgrad + bias grad
@@ -971,30 +1000,30 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
 }
 
 // ---------------------------------------------------------------------------------- weight-gradient accumulator
-static size_t wgrad_acc_elems(int mode, int Cin, int Ch, int N, int k) {
-  const size_t kk = static_cast<size_t>(k) * k;
+static size_t wgrad_acc_elems(int mode, int Cin, int Ch, int N, int taps) {
+  const size_t kk = static_cast<size_t>(taps);
   if (mode == PLC_MODE_FP32) return static_cast<size_t>(N) * (Cin + Ch) * kk;              // OIHW itself
   return static_cast<size_t>(N) * kk * (cdiv(Cin, 64) + cdiv(Ch, 64)) * 64;                 // packed [N][CB*64]
 }
-static int wgrad_unpack(int mode, int Cin, int Ch, int N, int k, const float* acc, float* dW, cudaStream_t st) {
+static int wgrad_unpack(int mode, int Cin, int Ch, int N, int taps, const float* acc, float* dW, cudaStream_t st) {
   if (!acc || !dW) return fail(PLC_ERR_NULL_ARG, "wgrad unpack: null pointer");
   LaunchTimer timer(PLC_K_ELEMENTWISE, st);
   if (mode == PLC_MODE_FP32)
-    plc::add_inplace_kernel<<<148 * 4, 256, 0, st>>>(acc, dW, wgrad_acc_elems(mode, Cin, Ch, N, k));
+    plc::add_inplace_kernel<<<148 * 4, 256, 0, st>>>(acc, dW, wgrad_acc_elems(mode, Cin, Ch, N, taps));
   else
-    plc::wgrad_unpack_kernel<<<148 * 4, 256, 0, st>>>(acc, dW, N, Cin, Ch, k);
+    plc::wgrad_unpack_kernel<<<148 * 4, 256, 0, st>>>(acc, dW, N, Cin, Ch, taps);
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;
 }
 
 size_t plc_wgrad_acc_bytes(const PlcCellDesc* d) {
   if (check_desc(d) != PLC_OK) return 0;
-  return wgrad_acc_elems(d->mode, d->Cin, d->Ch, 4 * d->Ch, d->k) * sizeof(float);
+  return wgrad_acc_elems(d->mode, d->Cin, d->Ch, 4 * d->Ch, d->k * d->k) * sizeof(float);
 }
 int plc_wgrad_unpack(const PlcCellDesc* d, const float* acc, float* dW_oihw, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
-  return wgrad_unpack(d->mode, d->Cin, d->Ch, 4 * d->Ch, d->k, acc, dW_oihw, static_cast<cudaStream_t>(stream));
+  return wgrad_unpack(d->mode, d->Cin, d->Ch, 4 * d->Ch, d->k * d->k, acc, dW_oihw, static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------------------------- generic "same" conv (bf16)
@@ -1030,10 +1059,11 @@ int plc_conv_pack_weight(const PlcConvDesc* d, int pack_kind, const float* w_oih
   LaunchTimer timer(PLC_K_PACK, st);
   if (pack_kind == PLC_PACK_FWD)
     pack_w_conv_fwd_kernel<<<148 * 4, 256, 0, st>>>(w_oihw, bias, static_cast<__nv_bfloat16*>(w_packed), bias_packed,
-                                                    d->Cin, d->Cout, d->k, kgeom(d->Cin, 0, d->k), d->pixel_shuffle);
+                                                    d->Cin, d->Cout, d->k * d->k, kgeom(d->Cin, 0, d->k),
+                                                    d->pixel_shuffle);
   else if (pack_kind == PLC_PACK_DGRAD)
     pack_w_conv_dgrad_kernel<<<148 * 4, 256, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), d->Cin, d->Cout,
-                                                      d->k, kgeom(d->Cout, 0, d->k));
+                                                      d->k * d->k, kgeom(d->Cout, 0, d->k));
   else
     return fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
   PLC_CUDA(cudaGetLastError());
@@ -1070,17 +1100,18 @@ int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, 
   CUtensorMap to0 = ta, to1 = ta;
   if ((rc = setup_plain_stores(&q, d->B, d->H, d->W, &to0, &to1))) return rc;
   return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, to0, to1, static_cast<cudaStream_t>(stream),
-                                        PLC_K_CONV_FWD);
+                                        PLC_K_CONV_FWD, conv_flops(d->B, d->H, d->W, d->Cin, d->Cout, d->k));
 }
 
 size_t plc_conv_wgrad_acc_bytes(const PlcConvDesc* d) {
   if (check_conv(d) != PLC_OK) return 0;
-  return wgrad_acc_elems(PLC_MODE_BF16_TC, d->Cin, 0, d->Cout, d->k) * sizeof(float);
+  return wgrad_acc_elems(PLC_MODE_BF16_TC, d->Cin, 0, d->Cout, d->k * d->k) * sizeof(float);
 }
 int plc_conv_wgrad_unpack(const PlcConvDesc* d, const float* acc, float* dW_oihw, void* stream) {
   int rc = check_conv(d);
   if (rc) return rc;
-  return wgrad_unpack(PLC_MODE_BF16_TC, d->Cin, 0, d->Cout, d->k, acc, dW_oihw, static_cast<cudaStream_t>(stream));
+  return wgrad_unpack(PLC_MODE_BF16_TC, d->Cin, 0, d->Cout, d->k * d->k, acc, dW_oihw,
+                      static_cast<cudaStream_t>(stream));
 }
 
 int plc_conv_grad_mask(const PlcConvDesc* d, const void* y, const void* dy, void* dz, void* stream) {
@@ -1125,10 +1156,237 @@ int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void
     if ((rc = make_tmap_mat(&tb, w_packed_dgrad, d->Cin, (long)q.num_kb * 64, 64, nt / cta))) return rc;
     CUtensorMap to0 = tz, to1 = tz;
     if ((rc = setup_plain_stores(&q, d->B, d->H, d->W, &to0, &to1))) return rc;
-    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tb, to0, to1, st, PLC_K_CONV_DGRAD))) return rc;
+    if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, tz, tz, tb, to0, to1, st, PLC_K_CONV_DGRAD,
+                                             conv_flops(d->B, d->H, d->W, d->Cout, d->Cin, d->k))))
+      return rc;
   }
   if (dW_acc) {
-    WgradShape w{d->B, d->H, d->W, d->k, d->Cin, 0, d->Cout};
+    WgradShape w;
+    w.B = d->B; w.H = d->H; w.W = d->W; w.k = d->k; w.Cin = d->Cin; w.Ch = 0; w.N = d->Cout;
+    if ((rc = launch_wgrad_tc_shape(&w, x, nullptr, dz, dW_acc, d->has_bias ? db_acc : nullptr, st, PLC_K_CONV_WGRAD)))
+      return rc;
+  }
+  return PLC_OK;
+}
+
+
+// ---------------------------------------------------------------------------------- strided 2-D / 3-D conv (bf16)
+// The discriminator's convolutions (north_star: "strided 2D/3D convolutions reuse the same implicit-GEMM core"): the
+// default pipeline of conv_igemm_tc_kernel with strided (elementStrides) and, for a time kernel, 5-D tensor maps.
+struct NdGeom { int To, Ho, Wo, taps, nd5; };
+
+static int check_convnd(const PlcConvNdDesc* d, NdGeom* g) {
+  if (!d) return fail(PLC_ERR_BAD_DESC, "null conv descriptor");
+  if (d->B <= 0 || d->T <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0)
+    return fail(PLC_ERR_BAD_DESC, "bad conv sizes B=%d T=%d H=%d W=%d Cin=%d Cout=%d", d->B, d->T, d->H, d->W, d->Cin,
+                d->Cout);
+  if (d->k <= 0 || (d->k % 2) == 0 || d->k > 7 || d->kt <= 0 || (d->kt % 2) == 0 || d->kt > 7)
+    return fail(PLC_ERR_BAD_DESC, "conv kernel sizes (kt=%d, k=%d) must be odd and <= 7 (zero padding k/2)", d->kt, d->k);
+  if ((d->stride != 1 && d->stride != 2) || (d->stride_t != 1 && d->stride_t != 2))
+    return fail(PLC_ERR_UNSUPPORTED, "conv strides (%d, %d) must be 1 or 2", d->stride_t, d->stride);
+  if (d->Cin % 8 || d->Cout % 8)
+    return fail(PLC_ERR_ALIGNMENT, "conv needs Cin %% 8 == 0 and Cout %% 8 == 0 (got %d, %d): pad channels", d->Cin, d->Cout);
+  if (d->act < 0 || d->act > 2) return fail(PLC_ERR_BAD_DESC, "act must be 0 (none), 1 (ReLU) or 2 (LeakyReLU)");
+  g->To = (d->T - 1) / d->stride_t + 1;
+  g->Ho = (d->H - 1) / d->stride + 1;
+  g->Wo = (d->W - 1) / d->stride + 1;
+  g->taps = d->kt * d->k * d->k;
+  g->nd5 = (d->kt > 1 || d->stride_t > 1) ? 1 : 0;
+  if ((long long)d->B * d->T * d->H * d->W >= (1ll << 31)) return fail(PLC_ERR_UNSUPPORTED, "B*T*H*W must be < 2^31");
+  return PLC_OK;
+}
+
+// one EPI_PLAIN launch: input grid [B, T, H, W, cin] -> output grid [B*To, Ho, Wo, cout]
+static int convnd_run(const void* x, int B, int T, int H, int W, int cin, int To, int Ho, int Wo, int cout, int kt, int k,
+                      int st_t, int st_s, const void* w_packed, const float* bias_packed, int relu, float slope, void* out,
+                      int kind, cudaStream_t st) {
+  int rc;
+  const int nd5 = (kt > 1 || st_t > 1) ? 1 : 0;
+  const int imgs = nd5 ? B * To : B * T;
+  PlcCellDesc cd{imgs, Ho, Wo, cin, cout, k, PLC_MODE_BF16_TC, 0};
+  TcGeom g;
+  pick_spatial_tile(Ho, Wo, &g);
+  plc::ConvTcParams q;
+  fill_geom(&cd, g, &q);
+  const int nt = pick_plain_n_tile(cout);
+  q.num_n_tiles = cdiv(cout, nt);
+  q.num_tiles = q.num_m_tiles * q.num_n_tiles;
+  set_kgeom(&q, kgeom_taps(cin, 0, kt * k * k));
+  q.stride = st_s; q.nd5 = nd5; q.kt = kt; q.pad_t = kt / 2; q.stride_t = st_t; q.T_out = To;
+  if (!nd5 && st_s == 1) maybe_patch(&g, &q, plc::EPI_PLAIN, nt);
+  q.n_total = cout;
+  q.Cin = cout;                        // no column split: everything goes to out0
+  q.out0 = static_cast<__nv_bfloat16*>(out);
+  q.plain_bias = bias_packed;
+  q.plain_relu = relu;
+  q.plain_slope = slope;
+  const int cta = pick_cta_group(q.num_m_tiles);
+  CUtensorMap ta, tb;
+  if (q.patch) {
+    if ((rc = make_tmap_src(&ta, x, imgs, H, W, cin, q))) return rc;
+  } else if ((rc = make_tmap_act(&ta, x, nd5 ? B : imgs, H, W, cin, q.tw, q.th, 2, q.kc, swizzle_for_kc(q.kc), st_s,
+                                 nd5 ? T : 0))) {
+    return rc;
+  }
+  if ((rc = make_tmap_mat(&tb, w_packed, cout, (long)q.num_kb * 64, 64, nt / cta))) return rc;
+  CUtensorMap to0 = ta, to1 = ta;
+  if ((rc = setup_plain_stores(&q, imgs, Ho, Wo, &to0, &to1))) return rc;
+  return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, to0, to1, st, kind,
+                                        conv_flops(imgs, Ho, Wo, cin, cout, k) * kt);
+}
+
+int plc_convnd_out_shape(const PlcConvNdDesc* d, int* T_out, int* H_out, int* W_out) {
+  NdGeom g;
+  int rc = check_convnd(d, &g);
+  if (rc) return rc;
+  if (T_out) *T_out = g.To;
+  if (H_out) *H_out = g.Ho;
+  if (W_out) *W_out = g.Wo;
+  return PLC_OK;
+}
+
+size_t plc_convnd_packed_weight_bytes(const PlcConvNdDesc* d, int pack_kind) {
+  NdGeom g;
+  if (check_convnd(d, &g) != PLC_OK) return 0;
+  if (pack_kind == PLC_PACK_FWD) return static_cast<size_t>(d->Cout) * kgeom_taps(d->Cin, 0, g.taps).num_kb * 64 * 2;
+  if (pack_kind == PLC_PACK_DGRAD) return static_cast<size_t>(d->Cin) * kgeom_taps(d->Cout, 0, g.taps).num_kb * 64 * 2;
+  fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
+  return 0;
+}
+
+int plc_convnd_pack_weight(const PlcConvNdDesc* d, int pack_kind, const float* w, const float* bias, void* w_packed,
+                           float* bias_packed, void* stream) {
+  NdGeom g;
+  int rc = check_convnd(d, &g);
+  if (rc) return rc;
+  if (!w || !w_packed) return fail(PLC_ERR_NULL_ARG, "plc_convnd_pack_weight: null pointer");
+  if (!aligned16(w_packed) || !aligned16(bias_packed)) return fail(PLC_ERR_ALIGNMENT, "packed buffers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchTimer timer(PLC_K_PACK, st);
+  if (pack_kind == PLC_PACK_FWD)
+    pack_w_conv_fwd_kernel<<<148 * 4, 256, 0, st>>>(w, bias, static_cast<__nv_bfloat16*>(w_packed), bias_packed, d->Cin,
+                                                    d->Cout, g.taps, kgeom_taps(d->Cin, 0, g.taps), 0);
+  else if (pack_kind == PLC_PACK_DGRAD)
+    pack_w_conv_dgrad_kernel<<<148 * 4, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_packed), d->Cin, d->Cout, g.taps,
+                                                      kgeom_taps(d->Cout, 0, g.taps));
+  else
+    return fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+int plc_convnd_fwd(const PlcConvNdDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, void* out,
+                   void* stream) {
+  NdGeom g;
+  int rc = check_convnd(d, &g);
+  if (rc) return rc;
+  if (!x || !w_packed_fwd || !out) return fail(PLC_ERR_NULL_ARG, "plc_convnd_fwd: null pointer");
+  if (!aligned16(x) || !aligned16(w_packed_fwd) || !aligned16(out) || !aligned16(bias_packed))
+    return fail(PLC_ERR_ALIGNMENT, "plc_convnd_fwd: all device pointers must be 16-byte aligned");
+  return convnd_run(x, d->B, d->T, d->H, d->W, d->Cin, g.To, g.Ho, g.Wo, d->Cout, d->kt, d->k, d->stride_t, d->stride,
+                    w_packed_fwd, d->has_bias ? bias_packed : nullptr, d->act != 0, d->act == 2 ? d->slope : 0.f, out,
+                    PLC_K_CONV_FWD, static_cast<cudaStream_t>(stream));
+}
+
+// dz [B,To,Ho,Wo,C] = dy * act'(y);  dzd [B,T,H,W,C] = dz placed on the stride lattice, zeros elsewhere (8 channels / thread)
+__global__ void convnd_grad_prep_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dy, uint4* __restrict__ dz,
+                                        uint4* __restrict__ dzd, int B, int T, int H, int W, int To, int Ho, int Wo, int C8,
+                                        int st_t, int st_s, int act, float slope) {
+  const bool dil = dzd != nullptr;
+  const size_t total = dil ? static_cast<size_t>(B) * T * H * W * C8 : static_cast<size_t>(B) * To * Ho * Wo * C8;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t src = idx;
+    bool on = true;
+    if (dil) {
+      const int c = idx % C8;
+      size_t r = idx / C8;
+      const int x = r % W; r /= W;
+      const int yy = r % H; r /= H;
+      const int t = r % T;
+      const int b = r / T;
+      on = (x % st_s == 0) && (yy % st_s == 0) && (t % st_t == 0) && (x / st_s < Wo) && (yy / st_s < Ho) && (t / st_t < To);
+      src = (((static_cast<size_t>(b) * To + t / st_t) * Ho + yy / st_s) * Wo + x / st_s) * C8 + c;
+    }
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (on) {
+      const uint4 g = dy[src];
+      if (act == 0) {
+        o = g;
+      } else {
+        const uint4 yv = y[src];
+        const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[i]);
+          const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yw[i]);
+          const float a = __low2float(g2) * (__low2float(y2) > 0.f ? 1.f : slope);
+          const float b2 = __high2float(g2) * (__high2float(y2) > 0.f ? 1.f : slope);
+          ow[i] = plc::pack_bf16x2(a, b2);
+        }
+        o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+      if (dil) dz[src] = o;
+    }
+    if (dil) dzd[idx] = o; else dz[idx] = o;
+  }
+}
+
+int plc_convnd_grad_prep(const PlcConvNdDesc* d, const void* y, const void* dy, void* dz, void* dz_dilated, void* stream) {
+  NdGeom g;
+  int rc = check_convnd(d, &g);
+  if (rc) return rc;
+  if (!dy || !dz || (d->act != 0 && !y)) return fail(PLC_ERR_NULL_ARG, "plc_convnd_grad_prep: null pointer");
+  const bool strided = (d->stride > 1 || d->stride_t > 1) && dz_dilated;   // NULL: only dZ is wanted (no dx downstream)
+  if (!aligned16(y) || !aligned16(dy) || !aligned16(dz) || !aligned16(dz_dilated))
+    return fail(PLC_ERR_ALIGNMENT, "plc_convnd_grad_prep: all device pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchTimer timer(PLC_K_ELEMENTWISE, st);
+  convnd_grad_prep_kernel<<<sm_count() * 8, 256, 0, st>>>(
+      static_cast<const uint4*>(y), static_cast<const uint4*>(dy), static_cast<uint4*>(dz),
+      strided ? static_cast<uint4*>(dz_dilated) : nullptr, d->B, d->T, d->H, d->W, g.To, g.Ho, g.Wo, d->Cout / 8,
+      d->stride_t, d->stride, d->act, d->act == 2 ? d->slope : 0.f);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+size_t plc_convnd_wgrad_acc_bytes(const PlcConvNdDesc* d) {
+  NdGeom g;
+  if (check_convnd(d, &g) != PLC_OK) return 0;
+  return wgrad_acc_elems(PLC_MODE_BF16_TC, d->Cin, 0, d->Cout, g.taps) * sizeof(float);
+}
+int plc_convnd_wgrad_unpack(const PlcConvNdDesc* d, const float* acc, float* dW, void* stream) {
+  NdGeom g;
+  int rc = check_convnd(d, &g);
+  if (rc) return rc;
+  return wgrad_unpack(PLC_MODE_BF16_TC, d->Cin, 0, d->Cout, g.taps, acc, dW, static_cast<cudaStream_t>(stream));
+}
+
+int plc_convnd_bwd(const PlcConvNdDesc* d, const void* x, const void* dz, const void* dz_dilated,
+                   const void* w_packed_dgrad, void* dx, float* dW_acc, float* db_acc, void* stream) {
+  NdGeom g;
+  int rc = check_convnd(d, &g);
+  if (rc) return rc;
+  if (!x || !dz) return fail(PLC_ERR_NULL_ARG, "plc_convnd_bwd: null pointer");
+  const bool strided = d->stride > 1 || d->stride_t > 1;
+  if (dx && (!w_packed_dgrad || (strided && !dz_dilated)))
+    return fail(PLC_ERR_NULL_ARG, "plc_convnd_bwd: dx needs the dgrad image (and dz_dilated for a strided conv)");
+  if (!aligned16(x) || !aligned16(dz) || !aligned16(dz_dilated) || !aligned16(dx) || !aligned16(w_packed_dgrad))
+    return fail(PLC_ERR_ALIGNMENT, "plc_convnd_bwd: all device pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dx) {
+    // dX = stride-1 "same" conv of the zero-inserted dZ (on the INPUT grid) with the flipped / transposed image:
+    // dX[i] = sum_tap dZd[i + tap' - pad] * W[k-1-tap'], dZd[u] = dZ[u / s] on the stride lattice, 0 elsewhere
+    if ((rc = convnd_run(strided ? dz_dilated : dz, d->B, d->T, d->H, d->W, d->Cout, d->T, d->H, d->W, d->Cin, d->kt, d->k,
+                         1, 1, w_packed_dgrad, nullptr, 0, 0.f, dx, PLC_K_CONV_DGRAD, st)))
+      return rc;
+  }
+  if (dW_acc) {
+    WgradShape w;
+    w.B = d->B * g.To; w.H = g.Ho; w.W = g.Wo; w.k = d->k; w.Cin = d->Cin; w.Ch = 0; w.N = d->Cout;
+    w.stride = d->stride; w.kt = d->kt; w.stride_t = d->stride_t; w.T_out = g.To;
+    w.Bs = g.nd5 ? d->B : d->B * d->T; w.Ts = d->T; w.Hs = d->H; w.Ws = d->W;
     if ((rc = launch_wgrad_tc_shape(&w, x, nullptr, dz, dW_acc, d->has_bias ? db_acc : nullptr, st, PLC_K_CONV_WGRAD)))
       return rc;
   }
@@ -1155,7 +1413,7 @@ int plc_timing_enable(int on) {
   return PLC_OK;
 }
 
-int plc_timing_collect(int* kinds, float* ms, int capacity) {
+int plc_timing_collect(int* kinds, float* ms, double* flops, int capacity) {
   std::lock_guard<std::mutex> lk(g_timing_mu);
   int n = 0;
   for (auto& t : g_timed) {
@@ -1164,7 +1422,10 @@ int plc_timing_collect(int* kinds, float* ms, int capacity) {
       cudaGetLastError();
       v = -1.f;
     }
-    if (n < capacity && kinds && ms) { kinds[n] = t.kind; ms[n] = v; }
+    if (n < capacity && kinds && ms) {
+      kinds[n] = t.kind; ms[n] = v;
+      if (flops) flops[n] = t.flops;
+    }
     ++n;
     cudaEventDestroy(t.e0);
     cudaEventDestroy(t.e1);

@@ -128,6 +128,25 @@ __device__ __forceinline__ void tma_load_4d_cg2(uint32_t smem_dst, const void* t
       : "memory");
 }
 
+// 5-D forms (3-D convolutions: [C, W, H, T, B] tensor maps; out-of-range T is zero-filled like out-of-range H / W)
+__device__ __forceinline__ void tma_load_5d_s(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                              int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_cg2(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr,
+                                                int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5, %6, %7}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // TMA tensor store smem -> global (bulk async group); out-of-bounds parts of the box are clipped
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"

@@ -24,6 +24,10 @@ struct WgradTcParams {
   int CB, GB, num_groups;     // column blocks (src,tap,chunk); blocks per CTA; groups
   int n_tiles, S;             // 128-row tiles of n = 4Ch; pixel splits
   int C0, C1, N4, Ctot;       // true channel counts
+  // strided / 3-D convolutions (single-CTA kernel only): pixel blocks tile the OUTPUT grid [B*T_out, H, W] (the dZ map);
+  // the source maps are strided (elementStrides) and, with nd5, 5-D [C, W, H, T, B]; column blocks = (src, tap, chunk)
+  // with tap = (kz, ky, kx)
+  int stride, nd5, kt, pad_t, stride_t, T_out;
   float* dW;                  // packed fp32 accumulator [N4][CB*64]: column = column-block*64 + channel-in-chunk
   float* db;                  // [N4] or nullptr: bias gradient = dZ^T x ones, one extra N=16 MMA per K-step
   unsigned long long* prof;   // debug cycle counters (plc_debug_set_prof) or nullptr
@@ -45,8 +49,8 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 
 // packed accumulator -> reference OIHW gradient:  dW[n][ic][tap] += acc[n][(column block of (src, tap, ic/64))*64 + ic%64]
 __global__ void wgrad_unpack_kernel(const float* __restrict__ acc, float* __restrict__ dW, int N4, int C0, int C1,
-                                    int ksize) {
-  const int kk = ksize * ksize, ctot = C0 + C1;
+                                    int kk /* taps: k*k, or kt*k*k for 3-D */) {
+  const int ctot = C0 + C1;
   const int chunks0 = (C0 + 63) / 64, chunks1 = (C1 + 63) / 64;
   const int Kp = kk * (chunks0 + chunks1) * 64;
   const size_t total = static_cast<size_t>(N4) * ctot * kk;
@@ -93,7 +97,7 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
   const int n_tile = job / p.num_groups;
   const int cb0 = group * p.GB;
   const int nblk = min(p.GB, p.CB - cb0);     // column blocks of this CTA
-  const int kk = p.ksize * p.ksize;
+  const int kk = p.kt * p.ksize * p.ksize;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_dz);
@@ -124,7 +128,7 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
     // ===================================================================== TMA producer (warp-uniform loop)
     // All per-column-block index math is hoisted: a single thread issues 2 + nblk TMA loads per stage and must
     // stay well under the stage's MMA time.
-    int dxs[kWgMaxGB], dys[kWgMaxGB], cks[kWgMaxGB];
+    int dxs[kWgMaxGB], dys[kWgMaxGB], dts[kWgMaxGB], cks[kWgMaxGB];
     bool s1[kWgMaxGB];
 #pragma unroll
     for (int j = 0; j < kWgMaxGB; ++j) {
@@ -134,7 +138,8 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
         if (cb < kk * p.chunks0) { tap = cb / p.chunks0; ck = cb % p.chunks0; }
         else { cb -= kk * p.chunks0; is1 = true; tap = cb / p.chunks1; ck = cb % p.chunks1; }
       }
-      dys[j] = tap / p.ksize - p.pad; dxs[j] = tap % p.ksize - p.pad; cks[j] = ck * 64; s1[j] = is1;
+      const int k2 = p.ksize * p.ksize, tz = tap / k2, t2 = tap - tz * k2;
+      dts[j] = tz - p.pad_t; dys[j] = t2 / p.ksize - p.pad; dxs[j] = t2 % p.ksize - p.pad; cks[j] = ck * 64; s1[j] = is1;
     }
     uint32_t stage = 0, phase = 0;
     const uint32_t bytes = (2 + nblk) * kWgBoxBytes;
@@ -152,11 +157,21 @@ wgrad_tc_kernel(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap_
         const uint32_t bar = smem_u32(&full_bar[stage]);
         tma_load_4d_s(st, &tmap_dz, bar, n_tile * 128, x0, y0, b);
         tma_load_4d_s(st + kWgBoxBytes, &tmap_dz, bar, n_tile * 128 + 64, x0, y0, b);
+        if (p.nd5) {   // image b = sample * T_out + output frame; source frame = out * stride_t + kz - pad_t
+          const int smp = b / p.T_out, t0 = (b - smp * p.T_out) * p.stride_t;
 #pragma unroll
-        for (int j = 0; j < kWgMaxGB; ++j) {
-          if (j < nblk)
-            tma_load_4d_s(st + (2 + j) * kWgBoxBytes, s1[j] ? &tmap_a1 : &tmap_a0, bar, cks[j], x0 + dxs[j],
-                          y0 + dys[j], b);
+          for (int j = 0; j < kWgMaxGB; ++j) {
+            if (j < nblk)
+              tma_load_5d_s(st + (2 + j) * kWgBoxBytes, s1[j] ? &tmap_a1 : &tmap_a0, bar, cks[j],
+                            x0 * p.stride + dxs[j], y0 * p.stride + dys[j], t0 + dts[j], smp);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kWgMaxGB; ++j) {
+            if (j < nblk)
+              tma_load_4d_s(st + (2 + j) * kWgBoxBytes, s1[j] ? &tmap_a1 : &tmap_a0, bar, cks[j],
+                            x0 * p.stride + dxs[j], y0 * p.stride + dys[j], b);
+          }
         }
       }
       __syncwarp();

@@ -457,3 +457,123 @@ def conv2d_same_into(x: Tensor, cp: ConvParams, out: Tensor) -> Tensor:
     d = cp.desc(B, H, W)
     _call(x, lib.plc_conv_fwd, "plc_conv_fwd", ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out))
     return out
+
+
+# --------------------------------------------------------------------------------- strided 2-D / 3-D conv (bf16)
+from ._lib import PlcConvNdDesc  # noqa: E402
+
+
+class ConvNdParams:
+    """Kernel-ready images of one (possibly strided, possibly 3-D) conv layer, cached per parameter version.
+
+    Wraps an ``nn.Conv2d`` (weight [Cout,Cin,k,k]) or ``nn.Conv3d`` (weight [Cout,Cin,kt,k,k]) PARAMETER HOLDER with
+    odd kernel sizes, padding k//2 and strides 1 or 2.  Channel counts are zero-padded to multiples of 8.
+    act: 0 none, 1 ReLU, 2 LeakyReLU(slope)."""
+
+    def __init__(self, conv: torch.nn.Module, act: int = 0, slope: float = 0.2):
+        self.conv, self.act, self.slope = conv, act, float(slope)
+        w = conv.weight
+        self.is3d = w.dim() == 5
+        self.Cout, self.Cin = w.shape[0], w.shape[1]
+        self.kt = w.shape[2] if self.is3d else 1
+        self.k = w.shape[-1]
+        st = conv.stride
+        self.stride_t = st[0] if self.is3d else 1
+        self.stride = st[-1]
+        if w.shape[-1] != w.shape[-2] or st[-1] != st[-2] or any(p != kk // 2 for p, kk in zip(conv.padding, w.shape[2:])):
+            raise ValueError("ConvNdParams: square spatial kernels / strides with padding k//2 only")
+        self.cin_p, self.cout_p = _rup(self.Cin, 8), _rup(self.Cout, 8)
+        self._cache = None
+
+    def desc(self, B, T, H, W) -> PlcConvNdDesc:
+        return PlcConvNdDesc(B, T, H, W, self.cin_p, self.cout_p, self.kt, self.k, self.stride_t, self.stride, self.act,
+                             self.slope, int(self.conv.bias is not None))
+
+    def packed(self, need_dgrad: bool):
+        w, b = self.conv.weight, self.conv.bias
+        key = (_lib.weight_generation(), w.data_ptr(), w._version,
+               None if b is None else (b.data_ptr(), b._version), str(w.device))
+        pc = self._cache
+        if pc is not None and pc[0] == key and (pc[3] is not None or not need_dgrad):
+            return pc[1], pc[2], pc[3]
+        lib = _lib.load()
+        wp = torch.zeros(self.cout_p, self.cin_p, self.kt, self.k, self.k, device=w.device, dtype=torch.float32)
+        wp[:self.Cout, :self.Cin] = w.detach().to(torch.float32).reshape(self.Cout, self.Cin, self.kt, self.k, self.k)
+        bp = None
+        if b is not None:
+            bp = torch.zeros(self.cout_p, device=w.device, dtype=torch.float32)
+            bp[:self.Cout] = b.detach().to(torch.float32)
+        d = self.desc(1, 1, 1, 1)
+        fwd = torch.empty(lib.plc_convnd_packed_weight_bytes(ctypes.byref(d), PLC_PACK_FWD), dtype=torch.uint8,
+                          device=w.device)
+        bias_packed = torch.zeros(self.cout_p, device=w.device, dtype=torch.float32)
+        _call(wp, lib.plc_convnd_pack_weight, "plc_convnd_pack_weight", ctypes.byref(d), PLC_PACK_FWD, _ptr(wp), _ptr(bp),
+              _ptr(fwd), _ptr(bias_packed))
+        dg = None
+        if need_dgrad:
+            dg = torch.empty(lib.plc_convnd_packed_weight_bytes(ctypes.byref(d), PLC_PACK_DGRAD), dtype=torch.uint8,
+                             device=w.device)
+            _call(wp, lib.plc_convnd_pack_weight, "plc_convnd_pack_weight", ctypes.byref(d), PLC_PACK_DGRAD, _ptr(wp),
+                  None, _ptr(dg), None)
+        self._cache = (key, fwd, bias_packed, dg)
+        return fwd, bias_packed, dg
+
+
+class _ConvNdFn(torch.autograd.Function):
+    """(strided / 3-D) conv + bias + activation on NHWC bf16 tensors [B,T,H,W,C] through plc_convnd_fwd / plc_convnd_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cp: ConvNdParams):
+        lib = _lib.load()
+        B, T, H, W, C = x.shape
+        if C != cp.cin_p or x.dtype != torch.bfloat16 or not x.is_contiguous():
+            raise RuntimeError(f"convnd input must be contiguous bf16 [B,T,H,W,{cp.cin_p}], got {x.dtype} {tuple(x.shape)}")
+        if not cp.is3d and (cp.kt != 1 or cp.stride_t != 1):
+            raise RuntimeError("2-D layer with a time kernel")
+        need_dx = ctx.needs_input_grad[0]
+        fwd, bias_packed, dg = cp.packed(need_dgrad=need_dx)       # snapshot of the weights this forward ran with
+        d = cp.desc(B, T, H, W)
+        to, ho, wo = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(lib.plc_convnd_out_shape(ctypes.byref(d), ctypes.byref(to), ctypes.byref(ho), ctypes.byref(wo)),
+                   "plc_convnd_out_shape")
+        out = torch.empty(B, to.value, ho.value, wo.value, cp.cout_p, dtype=torch.bfloat16, device=x.device)
+        _call(x, lib.plc_convnd_fwd, "plc_convnd_fwd", ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out))
+        ctx.cp, ctx.dg, ctx.d = cp, dg, d
+        ctx.save_for_backward(x, out)
+        ctx.need_dx, ctx.need_dw = need_dx, ctx.needs_input_grad[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, out = ctx.saved_tensors
+        cp, d = ctx.cp, ctx.d
+        dy = dy.contiguous()
+        strided = cp.stride > 1 or cp.stride_t > 1
+        dz = torch.empty_like(out)
+        dzd = torch.empty(*x.shape[:4], cp.cout_p, dtype=torch.bfloat16, device=x.device) if (strided and ctx.need_dx) \
+            else None
+        if cp.act != 0 or dzd is not None:
+            _call(dy, lib.plc_convnd_grad_prep, "plc_convnd_grad_prep", ctypes.byref(d), _ptr(out), _ptr(dy), _ptr(dz),
+                  _ptr(dzd))
+        else:
+            dz = dy
+        dx = torch.empty_like(x) if ctx.need_dx else None
+        gw = gb = None
+        img = db = None
+        if ctx.need_dw:
+            img = torch.zeros(lib.plc_convnd_wgrad_acc_bytes(ctypes.byref(d)) // 4, dtype=torch.float32, device=x.device)
+            db = torch.zeros(cp.cout_p, dtype=torch.float32, device=x.device) if cp.conv.bias is not None else None
+        _call(x, lib.plc_convnd_bwd, "plc_convnd_bwd", ctypes.byref(d), _ptr(x), _ptr(dz), _ptr(dzd), _ptr(ctx.dg), _ptr(dx),
+              _ptr(img), _ptr(db))
+        if ctx.need_dw:
+            dW = torch.zeros(cp.cout_p, cp.cin_p, cp.kt, cp.k, cp.k, dtype=torch.float32, device=x.device)
+            _call(img, lib.plc_convnd_wgrad_unpack, "plc_convnd_wgrad_unpack", ctypes.byref(d), _ptr(img), _ptr(dW))
+            gw = dW[:cp.Cout, :cp.Cin].reshape(cp.conv.weight.shape).to(cp.conv.weight.dtype)
+            gb = None if db is None else db[:cp.Cout].to(cp.conv.bias.dtype)
+        return dx, gw, gb, None
+
+
+def convnd(x: Tensor, cp: ConvNdParams) -> Tensor:
+    """x [B,T,H,W,cin_p] bf16 (T = 1 for images) -> [B,To,Ho,Wo,cout_p] bf16; padded channels are zero."""
+    return _ConvNdFn.apply(x, cp.conv.weight, cp.conv.bias, cp)

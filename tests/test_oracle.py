@@ -220,3 +220,37 @@ def test_loss_oracle_matches_live_reference_random_configs():
         ref_total.backward()
         got_total.backward()
         assert torch.allclose(pred2.grad, pred.grad, rtol=1e-6, atol=1e-9), case
+
+
+def test_gan_spec_known_answers_and_shapes():
+    """The repo-defined discriminator / GAN-loss spec (no reference counterpart): closed-form checks and the layer
+    geometry the C ABI must agree with (plc_convnd_out_shape is host-only arithmetic, so this runs without a GPU)."""
+    import ctypes
+    import math
+    import plconv
+    from oracle import gan_oracle as G
+    p = {k: torch.zeros_like(v) for k, v in G.make_discriminator_params(0).items()}
+    p["score.bias"] += 0.75
+    clips = torch.rand(2, 8, 1, 32, 40)
+    logits = G.discriminator_forward(clips, p)
+    assert torch.allclose(logits, torch.full((2,), 0.75))                       # zero weights: logit == score bias
+    z = torch.zeros(4)
+    assert abs(float(G.d_loss(z, 2)) - 2 * math.log(2)) < 1e-6                   # BCE at logit 0 is ln 2 per term
+    assert abs(float(G.g_adv_loss(z)) - math.log(2)) < 1e-6
+    big = torch.tensor([30.0, -30.0])                                            # confident and right -> loss ~ 0
+    assert float(G.d_loss(big, 1)) < 1e-9
+    a1, a2, a3, s = G.discriminator_features(clips, G.make_discriminator_params(1))
+    assert a1.shape == (16, 32, 16, 20) and a2.shape == (2, 64, 8, 8, 10) and a3.shape == (2, 128, 4, 4, 5)
+    assert s.shape == (8, 1, 4, 5)
+    lib = plconv._lib.load()
+    for (T, H, W, kt, st, sp, want) in [(1, 32, 40, 1, 1, 2, (1, 16, 20)), (8, 16, 20, 3, 1, 2, (8, 8, 10)),
+                                        (8, 8, 10, 3, 2, 2, (4, 4, 5)), (5, 11, 9, 3, 2, 2, (3, 6, 5))]:
+        d = plconv._lib.PlcConvNdDesc(2, T, H, W, 8, 8, kt, 3, st, sp, 2, 0.2, 1)
+        to, ho, wo = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert lib.plc_convnd_out_shape(ctypes.byref(d), ctypes.byref(to), ctypes.byref(ho), ctypes.byref(wo)) == 0
+        assert (to.value, ho.value, wo.value) == want
+        ref = torch.nn.functional.conv3d(torch.zeros(1, 1, T, H, W), torch.zeros(1, 1, kt, 3, 3), stride=(st, sp, sp),
+                                         padding=(kt // 2, 1, 1))
+        assert tuple(ref.shape[2:]) == want
+    bad = plconv._lib.PlcConvNdDesc(2, 4, 8, 8, 8, 8, 3, 3, 3, 2, 0, 0.0, 0)      # time stride 3: loud error
+    assert lib.plc_convnd_out_shape(ctypes.byref(bad), None, None, None) < 0
