@@ -155,9 +155,11 @@ int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void
  *   w   [Cout, Cin, kt, k, k] fp32 (torch Conv3d layout; Conv2d layout when kt = 1), bias [Cout]
  *   out [B, To, Ho, Wo, Cout] bf16, To = (T-1)/stride_t + 1, Ho = (H-1)/stride + 1 (padding kt/2, k/2, k/2)
  *   act: 0 none, 1 ReLU, 2 LeakyReLU(slope), applied after the bias.
- * Backward: plc_convnd_grad_prep forms dZ = dY * act'(Y) and, for a strided conv, its zero-inserted copy on the INPUT
- * grid [B, T, H, W, Cout] (dz_dilated; NULL when all strides are 1 or when no dx will be asked for).  plc_convnd_bwd: dx [B,T,H,W,Cin]
- * (nullable) = stride-1 conv of the zero-inserted dZ with the flipped image; dW_acc = accumulator image
+ * Backward: plc_convnd_grad_mask forms dZ = dY * act'(Y) (layers with an activation; otherwise dZ == dY).
+ * plc_convnd_bwd: dx [B,T,H,W,Cin] (nullable).  For a strided layer the transposed conv is decomposed by output phase
+ * (parity class of the dX position in every strided dimension): each phase is a stride-1 conv of dZ over its own tap
+ * subset that writes its sub-lattice of dX -- no zero-inserted copy of dZ, exactly the layer's MMAs in total; the
+ * PLC_PACK_DGRAD image holds one packed weight image per phase.  dW_acc = accumulator image
  * (plc_convnd_wgrad_acc_bytes; plc_convnd_wgrad_unpack ADDS it into [Cout,Cin,kt,k,k]); db_acc [Cout] += (nullable). */
 typedef struct PlcConvNdDesc {
   int32_t B, T, H, W;          /* input grid                                   */
@@ -174,11 +176,11 @@ int plc_convnd_pack_weight(const PlcConvNdDesc* d, int pack_kind, const float* w
                            float* bias_packed, void* stream);
 int plc_convnd_fwd(const PlcConvNdDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, void* out,
                    void* stream);
-int plc_convnd_grad_prep(const PlcConvNdDesc* d, const void* y, const void* dy, void* dz, void* dz_dilated, void* stream);
+int plc_convnd_grad_mask(const PlcConvNdDesc* d, const void* y, const void* dy, void* dz, void* stream);
 size_t plc_convnd_wgrad_acc_bytes(const PlcConvNdDesc* d);
 int plc_convnd_wgrad_unpack(const PlcConvNdDesc* d, const float* dW_acc, float* dW, void* stream);
-int plc_convnd_bwd(const PlcConvNdDesc* d, const void* x, const void* dz, const void* dz_dilated,
-                   const void* w_packed_dgrad, void* dx, float* dW_acc, float* db_acc, void* stream);
+int plc_convnd_bwd(const PlcConvNdDesc* d, const void* x, const void* dz, const void* w_packed_dgrad, void* dx,
+                   float* dW_acc, float* db_acc, void* stream);
 
 /* ---- per-launch timing (bench.py's roofline / step breakdown) -------------------------------------
  * plc_timing_enable(1) clears the record and makes every kernel launch of the library record a CUDA event pair on

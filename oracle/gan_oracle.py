@@ -49,14 +49,24 @@ def make_discriminator_params(seed: int = 0, in_channels: int = 1, widths=WIDTHS
     return p
 
 
-def discriminator_features(clips: Tensor, p: Dict[str, Tensor]):
-    """Every layer's activation, in torch layout: conv1 [N*T,32,h,w]; conv2 / conv3 [N,C,T,h,w]; score [N*T',1,h,w]."""
+def _lrelu(x: Tensor, mask):
+    """LeakyReLU; with ``mask`` (bool, same shape) the positive set is prescribed instead of taken from sign(x) -- used by
+    gradient checks to condition the spec on the activation pattern of the implementation under test (at an activation
+    within rounding error of 0 the kink makes the gradient ill-defined, and bf16 vs fp64 may land on opposite sides)."""
+    if mask is None:
+        return F.leaky_relu(x, SLOPE)
+    return torch.where(mask, x, SLOPE * x)
+
+
+def discriminator_features(clips: Tensor, p: Dict[str, Tensor], masks=None):
+    """Every layer's activation, in torch layout: conv1 [N*T,32,h,w]; conv2 / conv3 [N,C,T,h,w]; score [N*T',1,h,w].
+    masks: optional (m1, m2, m3) bool tensors in the same layouts prescribing the LeakyReLU positive sets."""
     n, t, c, hh, ww = clips.shape
-    a1 = F.leaky_relu(F.conv2d(clips.reshape(n * t, c, hh, ww), p["conv1.weight"], p["conv1.bias"], stride=2, padding=1),
-                      SLOPE)
+    m1, m2, m3 = masks if masks is not None else (None, None, None)
+    a1 = _lrelu(F.conv2d(clips.reshape(n * t, c, hh, ww), p["conv1.weight"], p["conv1.bias"], stride=2, padding=1), m1)
     x = a1.view(n, t, *a1.shape[1:]).permute(0, 2, 1, 3, 4)                       # [N, C, T, h, w]
-    a2 = F.leaky_relu(F.conv3d(x, p["conv2.weight"], p["conv2.bias"], stride=(1, 2, 2), padding=1), SLOPE)
-    a3 = F.leaky_relu(F.conv3d(a2, p["conv3.weight"], p["conv3.bias"], stride=(2, 2, 2), padding=1), SLOPE)
+    a2 = _lrelu(F.conv3d(x, p["conv2.weight"], p["conv2.bias"], stride=(1, 2, 2), padding=1), m2)
+    a3 = _lrelu(F.conv3d(a2, p["conv3.weight"], p["conv3.bias"], stride=(2, 2, 2), padding=1), m3)
     t2 = a3.shape[2]
     y = a3.permute(0, 2, 1, 3, 4).reshape(n * t2, a3.shape[1], *a3.shape[3:])
     s = F.conv2d(y, p["score.weight"], p["score.bias"], padding=1)

@@ -69,10 +69,10 @@ SIGNATURES = {
     "plc_convnd_packed_weight_bytes": (_sz, [_np, _int]),
     "plc_convnd_pack_weight": (_int, [_np, _int, _vp, _vp, _vp, _vp, _vp]),
     "plc_convnd_fwd": (_int, [_np, _vp, _vp, _vp, _vp, _vp]),
-    "plc_convnd_grad_prep": (_int, [_np, _vp, _vp, _vp, _vp, _vp]),
+    "plc_convnd_grad_mask": (_int, [_np, _vp, _vp, _vp, _vp]),
     "plc_convnd_wgrad_acc_bytes": (_sz, [_np]),
     "plc_convnd_wgrad_unpack": (_int, [_np, _vp, _vp, _vp]),
-    "plc_convnd_bwd": (_int, [_np, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "plc_convnd_bwd": (_int, [_np, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plc_timing_enable": (_int, [_int]),
     "plc_timing_collect": (_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float),
                                   ctypes.POINTER(ctypes.c_double), _int]),

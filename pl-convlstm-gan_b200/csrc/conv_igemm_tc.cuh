@@ -44,6 +44,16 @@ struct ConvTcParams {
   int nd5;                   // 1 = 5-D A tensor maps with a time dimension
   int kt, pad_t, stride_t;   // time taps (1 = none), their padding and stride
   int T_out;                 // output frames per sample (nd5)
+  // Tap geometry of the default pipeline: tap (kz, ky, kx), kz < kt, ky < ky_n, kx < kx_n, reads the source at
+  //   out * stride + tap0 + k * tap_dir       (plain conv: ky_n = kx_n = ksize, tap0 = -pad, tap_dir = +1).
+  // The transposed conv of a STRIDED layer is decomposed by output phase (parity class of the dX pixel): every phase
+  // is a stride-1 conv of dZ over the subset of taps k = k0 + j*s whose offsets (phase + pad - k) / s = o0 - j run
+  // backwards (tap_dir = -1), and its outputs land on the phase's sub-lattice of dX (o_* below).
+  int ky_n, kx_n;
+  int tap_x0, tap_y0, tap_t0, tap_dir;
+  // EPI_PLAIN output sub-lattice (o_map = 1): tile pixel (b, y, x) -> frame f = sample * o_T + t' * o_st + o_pt (nd5:
+  // b = sample * T_out + t'; else f = b), row y * o_s + o_py, column x * o_s + o_px of an [*, o_H, o_W, C] tensor
+  int o_map, o_s, o_py, o_px, o_H, o_W, o_st, o_pt, o_T;
   int kc;                    // channels per TMA box: 64, 32 or 16 (narrow sources pack G = 64/kc taps into one K stage)
   int chunks0, chunks1;      // kc-channel chunks of source 0 / source 1
   int num_boxes;             // ksize^2 * (chunks0 + chunks1) boxes of [kc ch x 128 px]
@@ -252,21 +262,22 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         // box iterator over (source, tap = (kz, ky, kx), kc-chunk); the K tail re-loads the last box (zero weights)
         int src = p.chunks0 > 0 ? 0 : 1, kz = 0, ky = 0, kx = 0, ck = 0, bx = 0;
         // strided / 3-D convs: tap origin in INPUT coordinates; image b = sample * T_out + output frame
-        const int xs = x0 * p.stride - p.pad, ys = y0 * p.stride - p.pad;
+        const int xs = x0 * p.stride + p.tap_x0, ys = y0 * p.stride + p.tap_y0;
         int smp = b, ts = 0;
-        if (p.nd5) { smp = b / p.T_out; ts = (b - smp * p.T_out) * p.stride_t - p.pad_t; }
+        if (p.nd5) { smp = b / p.T_out; ts = (b - smp * p.T_out) * p.stride_t + p.tap_t0; }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           int cch[G], cdx[G], cdy[G], cdt[G], csrc[G];
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            cch[g] = ck * KC; cdx[g] = xs + kx; cdy[g] = ys + ky; cdt[g] = ts + kz; csrc[g] = src;
+            cch[g] = ck * KC; cdx[g] = xs + kx * p.tap_dir; cdy[g] = ys + ky * p.tap_dir; cdt[g] = ts + kz * p.tap_dir;
+            csrc[g] = src;
             if (bx + 1 < p.num_boxes) {
               ++bx;
               if (++ck == (src ? p.chunks1 : p.chunks0)) {
                 ck = 0;
-                if (++kx == p.ksize) {
+                if (++kx == p.kx_n) {
                   kx = 0;
-                  if (++ky == p.ksize) {
+                  if (++ky == p.ky_n) {
                     ky = 0;
                     if (++kz == p.kt) { kz = 0; src = 1; }
                   }
@@ -1079,6 +1090,15 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                   const size_t opix = (static_cast<size_t>(b) * (2 * p.H) + (2 * y + (sub >> 1))) * (2 * p.W) +
                                       (2 * x + (sub & 1));
                   *reinterpret_cast<uint4*>(p.out0 + opix * cps + c) = o;
+                } else if (p.o_map) {
+                  // phase of a strided transposed conv: this tile's pixels are one parity class of dX
+                  int f = b;
+                  if (p.nd5) {
+                    const int smp = b / p.T_out;
+                    f = smp * p.o_T + (b - smp * p.T_out) * p.o_st + p.o_pt;
+                  }
+                  const size_t opix = (static_cast<size_t>(f) * p.o_H + (y * p.o_s + p.o_py)) * p.o_W + (x * p.o_s + p.o_px);
+                  *reinterpret_cast<uint4*>(p.out0 + opix * p.Cin + n0) = o;
                 } else if (n0 < p.Cin) {
                   if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pix * p.Cin + n0) = o;
                 } else {

@@ -521,6 +521,7 @@ void fill_geom(const PlcCellDesc* d, const TcGeom& g, plc::ConvTcParams* p) {
   p->B = d->B; p->H = d->H; p->W = d->W;
   p->ksize = d->k; p->pad = d->k / 2;
   p->stride = 1; p->kt = 1; p->stride_t = 1; p->T_out = 1;      // plain 2-D stride-1 conv unless the caller says otherwise
+  p->ky_n = p->kx_n = d->k; p->tap_x0 = p->tap_y0 = -(d->k / 2); p->tap_t0 = 0; p->tap_dir = 1;
   p->tw = g.tw; p->th = g.th; p->tw_log2 = g.tw_log2;
   p->tiles_x = g.tiles_x; p->tiles_y = g.tiles_y;
   p->num_m_tiles = d->B * g.tiles_x * g.tiles_y;
@@ -1213,6 +1214,7 @@ static int convnd_run(const void* x, int B, int T, int H, int W, int cin, int To
   q.num_tiles = q.num_m_tiles * q.num_n_tiles;
   set_kgeom(&q, kgeom_taps(cin, 0, kt * k * k));
   q.stride = st_s; q.nd5 = nd5; q.kt = kt; q.pad_t = kt / 2; q.stride_t = st_t; q.T_out = To;
+  q.tap_t0 = -(kt / 2);
   if (!nd5 && st_s == 1) maybe_patch(&g, &q, plc::EPI_PLAIN, nt);
   q.n_total = cout;
   q.Cin = cout;                        // no column split: everything goes to out0
@@ -1245,11 +1247,58 @@ int plc_convnd_out_shape(const PlcConvNdDesc* d, int* T_out, int* H_out, int* W_
   return PLC_OK;
 }
 
+// Transposed conv of a STRIDED layer, decomposed by output phase.  Along one dimension (kernel k, stride s, padding p) the
+// dX positions of parity class ph = i mod s receive exactly the taps k0, k0+s, ... with k0 = (ph + p) mod s, read from dZ
+// at offsets o0, o0-1, ... (o0 = (ph + p - k0) / s) relative to i / s:   dX[s*i' + ph] = sum_j dZ[i' + o0 - j] * W[k0 + j*s].
+// Each phase is therefore a STRIDE-1 conv of dZ with its own small tap set: no zero-inserted copy of dZ, and exactly the
+// layer's MMAs in total (a zero-insertion formulation executes s^d times as many and streams an s^d times larger tensor).
+struct PhaseDim { int k0, n, o0; };
+static PhaseDim phase_dim(int k, int s, int pad, int ph) {
+  PhaseDim r;
+  r.k0 = (ph + pad) % s;
+  r.n = r.k0 < k ? (k - r.k0 + s - 1) / s : 0;
+  r.o0 = (ph + pad - r.k0) / s;
+  return r;
+}
+// phase image Wd_ph[c][(tap j = (jz, jy, jx), dZ-channel chunk)*64 + jj] = w[n][c][k0z + jz*st][k0y + jy*s][k0x + jx*s]
+__global__ void pack_w_phase_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin, int cout,
+                                          int kt, int k, int st, int s, PhaseDim pz, PhaseDim py, PhaseDim px, KGeom kg) {
+  const int taps = pz.n * py.n * px.n, ktot = kg.num_kb * 64;
+  const size_t total = static_cast<size_t>(cin) * ktot;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int kp = idx % ktot, c = idx / ktot;
+    int tap;
+    const int n = decode_packed_k(kp, kg.kc, taps, kg.chunks0, 0, cout, 0, tap);
+    float v = 0.f;
+    if (n >= 0) {
+      const int jx = tap % px.n, jy = (tap / px.n) % py.n, jz = tap / (px.n * py.n);
+      const int kz = pz.k0 + jz * st, ky = py.k0 + jy * s, kx = px.k0 + jx * s;
+      v = w[(((static_cast<size_t>(n) * cin + c) * kt + kz) * k + ky) * k + kx];
+    }
+    out[idx] = __float2bfloat16(v);
+  }
+}
+static bool convnd_strided(const PlcConvNdDesc* d) { return d->stride > 1 || d->stride_t > 1; }
+static size_t phase_image_bytes(const PlcConvNdDesc* d, int pt, int py, int px, int* taps_out) {
+  const int taps = phase_dim(d->kt, d->stride_t, d->kt / 2, pt).n * phase_dim(d->k, d->stride, d->k / 2, py).n *
+                   phase_dim(d->k, d->stride, d->k / 2, px).n;
+  if (taps_out) *taps_out = taps;
+  return taps ? static_cast<size_t>(d->Cin) * kgeom_taps(d->Cout, 0, taps).num_kb * 128 : 0;
+}
+
 size_t plc_convnd_packed_weight_bytes(const PlcConvNdDesc* d, int pack_kind) {
   NdGeom g;
   if (check_convnd(d, &g) != PLC_OK) return 0;
   if (pack_kind == PLC_PACK_FWD) return static_cast<size_t>(d->Cout) * kgeom_taps(d->Cin, 0, g.taps).num_kb * 64 * 2;
-  if (pack_kind == PLC_PACK_DGRAD) return static_cast<size_t>(d->Cin) * kgeom_taps(d->Cout, 0, g.taps).num_kb * 64 * 2;
+  if (pack_kind == PLC_PACK_DGRAD) {
+    if (!convnd_strided(d)) return static_cast<size_t>(d->Cin) * kgeom_taps(d->Cout, 0, g.taps).num_kb * 64 * 2;
+    size_t tot = 0;   // one image per output phase, back to back
+    for (int pt = 0; pt < d->stride_t; ++pt)
+      for (int py = 0; py < d->stride; ++py)
+        for (int px = 0; px < d->stride; ++px) tot += phase_image_bytes(d, pt, py, px, nullptr);
+    return tot;
+  }
   fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
   return 0;
 }
@@ -1263,14 +1312,29 @@ int plc_convnd_pack_weight(const PlcConvNdDesc* d, int pack_kind, const float* w
   if (!aligned16(w_packed) || !aligned16(bias_packed)) return fail(PLC_ERR_ALIGNMENT, "packed buffers must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   LaunchTimer timer(PLC_K_PACK, st);
-  if (pack_kind == PLC_PACK_FWD)
+  if (pack_kind == PLC_PACK_FWD) {
     pack_w_conv_fwd_kernel<<<148 * 4, 256, 0, st>>>(w, bias, static_cast<__nv_bfloat16*>(w_packed), bias_packed, d->Cin,
                                                     d->Cout, g.taps, kgeom_taps(d->Cin, 0, g.taps), 0);
-  else if (pack_kind == PLC_PACK_DGRAD)
+  } else if (pack_kind == PLC_PACK_DGRAD && !convnd_strided(d)) {
     pack_w_conv_dgrad_kernel<<<148 * 4, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_packed), d->Cin, d->Cout, g.taps,
                                                       kgeom_taps(d->Cout, 0, g.taps));
-  else
+  } else if (pack_kind == PLC_PACK_DGRAD) {
+    size_t off = 0;
+    for (int pt = 0; pt < d->stride_t; ++pt)
+      for (int py = 0; py < d->stride; ++py)
+        for (int px = 0; px < d->stride; ++px) {
+          int taps;
+          const size_t bytes = phase_image_bytes(d, pt, py, px, &taps);
+          if (!taps) continue;
+          pack_w_phase_dgrad_kernel<<<148 * 2, 256, 0, st>>>(
+              w, reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(w_packed) + off), d->Cin, d->Cout, d->kt, d->k,
+              d->stride_t, d->stride, phase_dim(d->kt, d->stride_t, d->kt / 2, pt), phase_dim(d->k, d->stride, d->k / 2, py),
+              phase_dim(d->k, d->stride, d->k / 2, px), kgeom_taps(d->Cout, 0, taps));
+          off += bytes;
+        }
+  } else {
     return fail(PLC_ERR_BAD_DESC, "bad pack kind %d", pack_kind);
+  }
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;
 }
@@ -1288,65 +1352,38 @@ int plc_convnd_fwd(const PlcConvNdDesc* d, const void* x, const void* w_packed_f
                     PLC_K_CONV_FWD, static_cast<cudaStream_t>(stream));
 }
 
-// dz [B,To,Ho,Wo,C] = dy * act'(y);  dzd [B,T,H,W,C] = dz placed on the stride lattice, zeros elsewhere (8 channels / thread)
-__global__ void convnd_grad_prep_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dy, uint4* __restrict__ dz,
-                                        uint4* __restrict__ dzd, int B, int T, int H, int W, int To, int Ho, int Wo, int C8,
-                                        int st_t, int st_s, int act, float slope) {
-  const bool dil = dzd != nullptr;
-  const size_t total = dil ? static_cast<size_t>(B) * T * H * W * C8 : static_cast<size_t>(B) * To * Ho * Wo * C8;
+// dz = dy * act'(y) on [B,To,Ho,Wo,C], 8 channels per thread
+__global__ void convnd_grad_mask_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dy, uint4* __restrict__ dz,
+                                        size_t total, float slope) {
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    size_t src = idx;
-    bool on = true;
-    if (dil) {
-      const int c = idx % C8;
-      size_t r = idx / C8;
-      const int x = r % W; r /= W;
-      const int yy = r % H; r /= H;
-      const int t = r % T;
-      const int b = r / T;
-      on = (x % st_s == 0) && (yy % st_s == 0) && (t % st_t == 0) && (x / st_s < Wo) && (yy / st_s < Ho) && (t / st_t < To);
-      src = (((static_cast<size_t>(b) * To + t / st_t) * Ho + yy / st_s) * Wo + x / st_s) * C8 + c;
-    }
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (on) {
-      const uint4 g = dy[src];
-      if (act == 0) {
-        o = g;
-      } else {
-        const uint4 yv = y[src];
-        const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
-        uint32_t ow[4];
+    const uint4 g = dy[idx], yv = y[idx];
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+    uint32_t ow[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[i]);
-          const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yw[i]);
-          const float a = __low2float(g2) * (__low2float(y2) > 0.f ? 1.f : slope);
-          const float b2 = __high2float(g2) * (__high2float(y2) > 0.f ? 1.f : slope);
-          ow[i] = plc::pack_bf16x2(a, b2);
-        }
-        o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      }
-      if (dil) dz[src] = o;
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[i]);
+      const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yw[i]);
+      ow[i] = plc::pack_bf16x2(__low2float(g2) * (__low2float(y2) > 0.f ? 1.f : slope),
+                               __high2float(g2) * (__high2float(y2) > 0.f ? 1.f : slope));
     }
-    if (dil) dzd[idx] = o; else dz[idx] = o;
+    dz[idx] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
 
-int plc_convnd_grad_prep(const PlcConvNdDesc* d, const void* y, const void* dy, void* dz, void* dz_dilated, void* stream) {
+int plc_convnd_grad_mask(const PlcConvNdDesc* d, const void* y, const void* dy, void* dz, void* stream) {
   NdGeom g;
   int rc = check_convnd(d, &g);
   if (rc) return rc;
-  if (!dy || !dz || (d->act != 0 && !y)) return fail(PLC_ERR_NULL_ARG, "plc_convnd_grad_prep: null pointer");
-  const bool strided = (d->stride > 1 || d->stride_t > 1) && dz_dilated;   // NULL: only dZ is wanted (no dx downstream)
-  if (!aligned16(y) || !aligned16(dy) || !aligned16(dz) || !aligned16(dz_dilated))
-    return fail(PLC_ERR_ALIGNMENT, "plc_convnd_grad_prep: all device pointers must be 16-byte aligned");
+  if (!dy || !dz || !y) return fail(PLC_ERR_NULL_ARG, "plc_convnd_grad_mask: null pointer");
+  if (d->act == 0) return fail(PLC_ERR_BAD_DESC, "plc_convnd_grad_mask: the layer has no activation (dZ == dY)");
+  if (!aligned16(y) || !aligned16(dy) || !aligned16(dz))
+    return fail(PLC_ERR_ALIGNMENT, "plc_convnd_grad_mask: all device pointers must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   LaunchTimer timer(PLC_K_ELEMENTWISE, st);
-  convnd_grad_prep_kernel<<<sm_count() * 8, 256, 0, st>>>(
-      static_cast<const uint4*>(y), static_cast<const uint4*>(dy), static_cast<uint4*>(dz),
-      strided ? static_cast<uint4*>(dz_dilated) : nullptr, d->B, d->T, d->H, d->W, g.To, g.Ho, g.Wo, d->Cout / 8,
-      d->stride_t, d->stride, d->act, d->act == 2 ? d->slope : 0.f);
+  const size_t total = static_cast<size_t>(d->B) * g.To * g.Ho * g.Wo * (d->Cout / 8);
+  convnd_grad_mask_kernel<<<sm_count() * 8, 256, 0, st>>>(static_cast<const uint4*>(y), static_cast<const uint4*>(dy),
+                                                          static_cast<uint4*>(dz), total, d->act == 2 ? d->slope : 0.f);
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;
 }
@@ -1363,23 +1400,73 @@ int plc_convnd_wgrad_unpack(const PlcConvNdDesc* d, const float* acc, float* dW,
   return wgrad_unpack(PLC_MODE_BF16_TC, d->Cin, 0, d->Cout, g.taps, acc, dW, static_cast<cudaStream_t>(stream));
 }
 
-int plc_convnd_bwd(const PlcConvNdDesc* d, const void* x, const void* dz, const void* dz_dilated,
-                   const void* w_packed_dgrad, void* dx, float* dW_acc, float* db_acc, void* stream) {
+// dX of a strided layer: one stride-1 launch per output phase, writing that phase's sub-lattice of dX
+static int convnd_dgrad_phases(const PlcConvNdDesc* d, const NdGeom& g, const void* dz, const void* w_packed, void* dx,
+                               cudaStream_t st) {
+  int rc;
+  size_t off = 0;
+  for (int pt = 0; pt < d->stride_t; ++pt)
+    for (int py = 0; py < d->stride; ++py)
+      for (int px = 0; px < d->stride; ++px) {
+        const PhaseDim dzp = phase_dim(d->kt, d->stride_t, d->kt / 2, pt);
+        const PhaseDim dyp = phase_dim(d->k, d->stride, d->k / 2, py);
+        const PhaseDim dxp = phase_dim(d->k, d->stride, d->k / 2, px);
+        int taps;
+        const size_t bytes = phase_image_bytes(d, pt, py, px, &taps);
+        if (!taps)
+          return fail(PLC_ERR_UNSUPPORTED, "transposed conv: kernel (%d,%d) smaller than stride (%d,%d) leaves dX phases "
+                                           "without a tap", d->kt, d->k, d->stride_t, d->stride);
+        const int Tp = (d->T - pt + d->stride_t - 1) / d->stride_t;
+        const int Hp = (d->H - py + d->stride - 1) / d->stride, Wp = (d->W - px + d->stride - 1) / d->stride;
+        if (Tp <= 0 || Hp <= 0 || Wp <= 0) { off += bytes; continue; }
+        const int imgs = g.nd5 ? d->B * Tp : d->B * d->T;
+        PlcCellDesc cd{imgs, Hp, Wp, d->Cout, d->Cin, d->k, PLC_MODE_BF16_TC, 0};
+        TcGeom tg;
+        pick_spatial_tile(Hp, Wp, &tg);
+        plc::ConvTcParams q;
+        fill_geom(&cd, tg, &q);
+        const int nt = pick_plain_n_tile(d->Cin);
+        q.num_n_tiles = cdiv(d->Cin, nt);
+        q.num_tiles = q.num_m_tiles * q.num_n_tiles;
+        set_kgeom(&q, kgeom_taps(d->Cout, 0, taps));
+        q.nd5 = g.nd5; q.kt = dzp.n; q.T_out = Tp;
+        q.ky_n = dyp.n; q.kx_n = dxp.n;
+        q.tap_x0 = dxp.o0; q.tap_y0 = dyp.o0; q.tap_t0 = dzp.o0; q.tap_dir = -1;
+        q.n_total = d->Cin; q.Cin = d->Cin;
+        q.out0 = static_cast<__nv_bfloat16*>(dx);
+        q.o_map = 1; q.o_s = d->stride; q.o_py = py; q.o_px = px; q.o_H = d->H; q.o_W = d->W;
+        q.o_st = d->stride_t; q.o_pt = pt; q.o_T = d->T;
+        const int cta = pick_cta_group(q.num_m_tiles);
+        CUtensorMap ta, tb;
+        if ((rc = make_tmap_act(&ta, dz, g.nd5 ? d->B : d->B * d->T, g.Ho, g.Wo, d->Cout, q.tw, q.th, 2, q.kc,
+                                swizzle_for_kc(q.kc), 1, g.nd5 ? g.To : 0)))
+          return rc;
+        if ((rc = make_tmap_mat(&tb, static_cast<const char*>(w_packed) + off, d->Cin, (long)q.num_kb * 64, 64, nt / cta)))
+          return rc;
+        if ((rc = launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, ta, ta, st, PLC_K_CONV_DGRAD,
+                                                 conv_flops(imgs, Hp, Wp, d->Cout, d->Cin, 1) * taps)))
+          return rc;
+        off += bytes;
+      }
+  return PLC_OK;
+}
+
+int plc_convnd_bwd(const PlcConvNdDesc* d, const void* x, const void* dz, const void* w_packed_dgrad, void* dx,
+                   float* dW_acc, float* db_acc, void* stream) {
   NdGeom g;
   int rc = check_convnd(d, &g);
   if (rc) return rc;
   if (!x || !dz) return fail(PLC_ERR_NULL_ARG, "plc_convnd_bwd: null pointer");
-  const bool strided = d->stride > 1 || d->stride_t > 1;
-  if (dx && (!w_packed_dgrad || (strided && !dz_dilated)))
-    return fail(PLC_ERR_NULL_ARG, "plc_convnd_bwd: dx needs the dgrad image (and dz_dilated for a strided conv)");
-  if (!aligned16(x) || !aligned16(dz) || !aligned16(dz_dilated) || !aligned16(dx) || !aligned16(w_packed_dgrad))
+  if (dx && !w_packed_dgrad) return fail(PLC_ERR_NULL_ARG, "plc_convnd_bwd: dx needs the dgrad image");
+  if (!aligned16(x) || !aligned16(dz) || !aligned16(dx) || !aligned16(w_packed_dgrad))
     return fail(PLC_ERR_ALIGNMENT, "plc_convnd_bwd: all device pointers must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dx) {
-    // dX = stride-1 "same" conv of the zero-inserted dZ (on the INPUT grid) with the flipped / transposed image:
-    // dX[i] = sum_tap dZd[i + tap' - pad] * W[k-1-tap'], dZd[u] = dZ[u / s] on the stride lattice, 0 elsewhere
-    if ((rc = convnd_run(strided ? dz_dilated : dz, d->B, d->T, d->H, d->W, d->Cout, d->T, d->H, d->W, d->Cin, d->kt, d->k,
-                         1, 1, w_packed_dgrad, nullptr, 0, 0.f, dx, PLC_K_CONV_DGRAD, st)))
+  if (dx && convnd_strided(d)) {
+    if ((rc = convnd_dgrad_phases(d, g, dz, w_packed_dgrad, dx, st))) return rc;
+  } else if (dx) {
+    // stride 1: dX = "same" conv of dZ with the flipped / transposed image
+    if ((rc = convnd_run(dz, d->B, d->T, d->H, d->W, d->Cout, d->T, d->H, d->W, d->Cin, d->kt, d->k, 1, 1,
+                         w_packed_dgrad, nullptr, 0, 0.f, dx, PLC_K_CONV_DGRAD, st)))
       return rc;
   }
   if (dW_acc) {

@@ -549,13 +549,9 @@ class _ConvNdFn(torch.autograd.Function):
         x, out = ctx.saved_tensors
         cp, d = ctx.cp, ctx.d
         dy = dy.contiguous()
-        strided = cp.stride > 1 or cp.stride_t > 1
-        dz = torch.empty_like(out)
-        dzd = torch.empty(*x.shape[:4], cp.cout_p, dtype=torch.bfloat16, device=x.device) if (strided and ctx.need_dx) \
-            else None
-        if cp.act != 0 or dzd is not None:
-            _call(dy, lib.plc_convnd_grad_prep, "plc_convnd_grad_prep", ctypes.byref(d), _ptr(out), _ptr(dy), _ptr(dz),
-                  _ptr(dzd))
+        if cp.act != 0:
+            dz = torch.empty_like(out)
+            _call(dy, lib.plc_convnd_grad_mask, "plc_convnd_grad_mask", ctypes.byref(d), _ptr(out), _ptr(dy), _ptr(dz))
         else:
             dz = dy
         dx = torch.empty_like(x) if ctx.need_dx else None
@@ -564,8 +560,8 @@ class _ConvNdFn(torch.autograd.Function):
         if ctx.need_dw:
             img = torch.zeros(lib.plc_convnd_wgrad_acc_bytes(ctypes.byref(d)) // 4, dtype=torch.float32, device=x.device)
             db = torch.zeros(cp.cout_p, dtype=torch.float32, device=x.device) if cp.conv.bias is not None else None
-        _call(x, lib.plc_convnd_bwd, "plc_convnd_bwd", ctypes.byref(d), _ptr(x), _ptr(dz), _ptr(dzd), _ptr(ctx.dg), _ptr(dx),
-              _ptr(img), _ptr(db))
+        _call(x, lib.plc_convnd_bwd, "plc_convnd_bwd", ctypes.byref(d), _ptr(x), _ptr(dz), _ptr(ctx.dg), _ptr(dx), _ptr(img),
+              _ptr(db))
         if ctx.need_dw:
             dW = torch.zeros(cp.cout_p, cp.cin_p, cp.kt, cp.k, cp.k, dtype=torch.float32, device=x.device)
             _call(img, lib.plc_convnd_wgrad_unpack, "plc_convnd_wgrad_unpack", ctypes.byref(d), _ptr(img), _ptr(dW))
