@@ -116,7 +116,12 @@ struct ConvTcCfg {
   // (double-buffered up to N_TILE = 128: short-K convs finish a tile faster than its bulk stores drain)
   static constexpr int kPlainBufs = N_TILE <= 128 ? 2 : 1;
   static constexpr int kPlainBufBytes = (N_TILE / 64) * 16384;
-  static constexpr int kStoreBytes = kTmaStore ? 3 * 16384 : (EPI == 2 /*EPI_PLAIN*/ ? kPlainBufs * kPlainBufBytes : 0);
+  // bwd gates: two operand/output buffers, one per 32-channel round of a tile.  The loader warp fills a buffer by TMA
+  // with c_prev | dc_next | dh | dh2 of the round; the epilogue overwrites it IN PLACE with dc_prev | dZ_i dZ_f | dZ_o |
+  // dZ_g (same bytes per pixel) and the loader warp sends it off as five tensor stores.
+  static constexpr int kGateBufBytes = 3 * 16384;
+  static constexpr int kStoreBytes = kTmaStore ? (EPI == 1 /*EPI_LSTM_BWD_GATES*/ ? 2 * kGateBufBytes : 3 * 16384)
+                                               : (EPI == 2 /*EPI_PLAIN*/ ? kPlainBufs * kPlainBufBytes : 0);
   // cta_group::2: the CTA pair shares one 256 x N_TILE accumulator tile; each CTA stages its own 128 pixels of A
   // and HALF of the B tile (N_TILE/2 packed-weight rows), so the per-SM operand feed drops from 48 to 32 KB / K-block.
   static constexpr int kBBytes = (N_TILE / kCta) * kBlockK * 2;
@@ -125,7 +130,9 @@ struct ConvTcCfg {
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/ - kAuxBytes - kStoreBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kAuxBytes + 1024;
+  // operand pipeline region: kStages x {A, B} stages, or -- patch mode -- all of it carved into patch slots + weight stages
+  static constexpr int kPipeBytes = (kSmemBudget / 1024) * 1024;
+  static constexpr int kSmemBytes = kPipeBytes + kStoreBytes + kAuxBytes + 1024;
   // accumulator stages in TMEM: 2 for the wide LSTM tiles (2 x 256 columns); 4 for N_TILE <= 128, where a short-K
   // tile is over in less time than the commit -> epilogue -> release round trip, so the MMA warp must be able to
   // run several tiles ahead of the epilogue
@@ -161,8 +168,9 @@ __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int
 template <int V>
 struct IntC { static constexpr int value = V; };
 
-// per-granule operands of the gate-gradient epilogue (8 channels of one pixel)
-struct GateIn { float4 c0, c1, d0, d1; uint4 dh, dh2; };
+// tensor maps of the gate-gradient epilogue's per-pixel operands (EPI_LSTM_BWD_GATES, N_TILE = 256): 32-channel boxes of
+// one 128-pixel tile -- fp32 [32 ch] = 128-byte rows (SWIZZLE_128B), bf16 [32 ch] = 64-byte rows (SWIZZLE_64B)
+struct GateMaps { CUtensorMap c_prev, dc_next, dh, dh2; };
 
 // epilogue warps: the LSTM epilogues are MUFU/latency heavy (5 transcendentals per element) and must finish a tile
 // faster than the tensor core produces the next one -> two warps per TMEM lane quadrant, alternating 16-channel chunks.
@@ -178,7 +186,8 @@ template <int N_TILE, int EPI, int kCta>
 __global__ void __launch_bounds__(conv_tc_threads<EPI>(), 1)
 conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap tmap_a0,
                      const __grid_constant__ CUtensorMap tmap_a1, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1) {
+                     const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1,
+                     const __grid_constant__ GateMaps gmaps) {
   using Cfg = ConvTcCfg<N_TILE, kCta, EPI>;
   constexpr int kStages = Cfg::kStages;
   constexpr int CH_TILE = N_TILE / 4;
@@ -189,7 +198,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint8_t* stage_out = smem + kStages * Cfg::kStageBytes;                 // TMA-store staging (1024-aligned)
+  uint8_t* stage_out = smem + Cfg::kPipeBytes;                            // TMA-store staging (1024-aligned)
   float* bias_s = reinterpret_cast<float*>(stage_out + Cfg::kStoreBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + Cfg::kStoreBytes + 4096);
   uint64_t* tmem_full = bars;                      // [2]
@@ -202,6 +211,8 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   uint64_t* patch_empty = bars + 18;               // [8]
   uint64_t* bfull_bar = bars + 26;                 // [8]
   uint64_t* bempty_bar = bars + 34;                // [8]
+  uint64_t* gin_full = bars + 44;                  // [2] bwd gates: operand buffer filled by TMA
+  uint64_t* gout_ready = bars + 46;                // [2] bwd gates: outputs written, buffer ready for the tensor stores
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -226,6 +237,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     for (int s = 0; s < Cfg::kAccStages; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiWarps * kCta);  // one arrive per epilogue warp (of both CTAs of a pair)
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&gin_full[s], 1);
+      mbar_init(&gout_ready[s], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -546,6 +561,52 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       p.prof[blockIdx.x * 16 + 13] = t_patch;         //           waiting for an activation patch (patch mode)
       p.prof[blockIdx.x * 16 + 14] = t_mma;           //           narrow patch mode: inside the MMA issue loop
     }
+  } else if (warp == 3) {
+    if constexpr (EPI == EPI_LSTM_BWD_GATES && Cfg::kTmaStore) {
+      // ===================================================================== gate-operand loader / output storer
+      // Round R = 2 * (tile index of this CTA) + (32-channel half of the slice) lives in buffer R & 1.  Loads run TWO
+      // rounds ahead of the epilogue: buffer R & 1 is refilled for round R + 2 as soon as the stores of round R have
+      // finished reading it, i.e. a whole round before the epilogue warps need it.
+      const uint32_t so = smem_u32(stage_out), inf_base = smem_u32(gin_full);
+      const int my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tile_step - 1) / tile_step : 0;
+      const int rounds = 2 * my_tiles;
+      const uint32_t tx = 16384u + 8192u + (p.dc_next ? 16384u : 0u) + (p.dh2 ? 8192u : 0u);
+      auto load_round = [&](int R) {
+        if (R >= rounds) return;
+        int n_tile, b, y0, x0;
+        decode_tile<kCta>(p, tile0 + (R >> 1) * tile_step, rank, n_tile, b, y0, x0);
+        if (lane == 0) {
+          const uint32_t buf = so + (R & 1) * Cfg::kGateBufBytes, bar = inf_base + (R & 1) * 8;
+          const int cb = n_tile * CH_TILE + (R & 1) * 32;
+          mbar_arrive_expect_tx(&gin_full[R & 1], tx);
+          tma_load_4d_s(buf, &gmaps.c_prev, bar, cb, x0, y0, b);
+          if (p.dc_next) tma_load_4d_s(buf + 16384, &gmaps.dc_next, bar, cb, x0, y0, b);
+          tma_load_4d_s(buf + 32768, &gmaps.dh, bar, cb, x0, y0, b);
+          if (p.dh2) tma_load_4d_s(buf + 40960, &gmaps.dh2, bar, cb, x0, y0, b);
+        }
+        __syncwarp();
+      };
+      load_round(0);
+      load_round(1);
+      for (int R = 0; R < rounds; ++R) {
+        mbar_wait(&gout_ready[R & 1], (R >> 1) & 1);
+        int n_tile, b, y0, x0;
+        decode_tile<kCta>(p, tile0 + (R >> 1) * tile_step, rank, n_tile, b, y0, x0);
+        if (lane == 0) {   // OOB rows / images (ragged tiles, odd tail pair) are clipped by TMA
+          const uint32_t buf = so + (R & 1) * Cfg::kGateBufBytes;
+          const int cb = n_tile * CH_TILE + (R & 1) * 32;
+          tma_store_4d(&tmap_o1, buf, cb, x0, y0, b);                                    // dc_prev
+#pragma unroll
+          for (int gate = 0; gate < 4; ++gate)                                           // dZ, reference gate order
+            tma_store_4d(&tmap_o0, buf + 16384 + gate * 8192, gate * p.Ch + cb, x0, y0, b);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        __syncwarp();
+        load_round(R + 2);
+      }
+      if (lane == 0) tma_store_wait_all();   // bulk stores complete before the CTA retires
+    }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     const int q = warp & 3;             // TMEM lane quadrant == warp_idx % 4
@@ -597,24 +658,6 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
               for (int e = 0; e < 8; ++e) cpre[m][e] = 0.f;
             }
           }
-        }
-      }
-      // bwd gates (TMA-store path): this warp's first granule operands, fetched before the accumulator wait
-      GateIn gfirst;
-      if constexpr (EPI == EPI_LSTM_BWD_GATES && Cfg::kTmaStore) {
-        if (valid) {
-          const int g0 = half * (4 / (kEpiWarps / 4));
-          const size_t off = pix * p.Ch + n_tile * CH_TILE + g0 * 8;
-          const float4* cs = reinterpret_cast<const float4*>(p.c_prev + off);
-          gfirst.c0 = __ldg(cs); gfirst.c1 = __ldg(cs + 1);
-          if (p.dc_next) {
-            const float4* ds = reinterpret_cast<const float4*>(p.dc_next + off);
-            gfirst.d0 = __ldg(ds); gfirst.d1 = __ldg(ds + 1);
-          } else {
-            gfirst.d0 = make_float4(0.f, 0.f, 0.f, 0.f); gfirst.d1 = gfirst.d0;
-          }
-          gfirst.dh = __ldg(reinterpret_cast<const uint4*>(p.dh + off));
-          gfirst.dh2 = p.dh2 ? __ldg(reinterpret_cast<const uint4*>(p.dh2 + off)) : make_uint4(0u, 0u, 0u, 0u);
         }
       }
       long long te = ((kProfEnabled && p.prof) && warp == 4) ? clock64() : 0;
@@ -743,50 +786,48 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           }
         }
       } else if constexpr (EPI == EPI_LSTM_BWD_GATES && Cfg::kTmaStore) {
-        // ---- gate recompute + dZ / dc_prev, 8-channel granules, outputs through smem + TMA stores.
-        // Two rounds per tile (channels 0-31, 32-63 of the slice); every warp does GPR granules per round and
-        // prefetches the next granule's c_prev / dh / dc_next while it works on the current one.
+        // ---- gate recompute + dZ / dc_prev, 8-channel granules.  Two rounds per tile (channels 0-31,
+        // 32-63 of the slice).  The per-pixel operands arrive by TMA in the round's buffer (loader warp) and the outputs
+        // overwrite them in place: dc_prev over c_prev, dZ_o over dh, dZ_g over dh2 (same thread, same address), dZ_i and
+        // dZ_f over dc_next -- the only aliasing across threads, hence dc_next is read first and barrier X follows.
+        // No per-thread global access is left in this epilogue; ragged tiles compute on TMA's zero fill and are clipped
+        // by the tensor stores.
         const int ch0 = n_tile * CH_TILE;
-        const bool issuer = (warp == 4) && (lane == 0);
         constexpr int WQ = kEpiWarps / 4;          // warps per TMEM lane quadrant
         constexpr int GPR = 4 / WQ;                // granules per round per warp
         static_assert(CH_TILE == 64 && (4 % WQ) == 0, "TMA-store gate epilogue assumes a 64-channel slice");
-        using GIn = GateIn;
-        GIn gin[2];
-        auto issue_loads = [&](int g, GIn& in) {
-          if (valid) {
-            const size_t off = pix * p.Ch + ch0 + g * 8;
-            const float4* cs = reinterpret_cast<const float4*>(p.c_prev + off);
-            in.c0 = __ldg(cs); in.c1 = __ldg(cs + 1);
-            if (p.dc_next) {
-              const float4* ds = reinterpret_cast<const float4*>(p.dc_next + off);
-              in.d0 = __ldg(ds); in.d1 = __ldg(ds + 1);
-            } else {
-              in.d0 = make_float4(0.f, 0.f, 0.f, 0.f); in.d1 = in.d0;
-            }
-            in.dh = __ldg(reinterpret_cast<const uint4*>(p.dh + off));
-            in.dh2 = p.dh2 ? __ldg(reinterpret_cast<const uint4*>(p.dh2 + off)) : make_uint4(0u, 0u, 0u, 0u);
-          }
-        };
-        // (the first granule's loads were issued before the accumulator wait: see `gfirst` above)
-        gin[0] = gfirst;
+        const uint32_t sw = row & 7, sw64 = (row >> 1) & 3;
+        const bool pw4 = (kProfEnabled && p.prof) && warp == 4 && lane == 0;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const bool pw4 = (kProfEnabled && p.prof) && warp == 4 && lane == 0;
+          const uint32_t buf = smem_u32(stage_out) + r * Cfg::kGateBufBytes;
+          const uint32_t crow = buf + row * 128;                 // c_prev -> dc_prev   [128 px][32 ch] fp32, SWIZZLE_128B
+          const uint32_t nrow = buf + 16384 + row * 128;         // dc_next             (same layout)
+          const uint32_t zrow = buf + 16384 + row * 64;          // dZ_i, dZ_f, dZ_o (over dh), dZ_g (over dh2): four
+                                                                 // [128 px][32 ch] bf16 boxes, 64-byte rows, SWIZZLE_64B
           long long tA = pw4 ? clock64() : 0;
-          if (issuer) tma_store_wait_read();       // staging buffer free again?
-          named_bar_sync(1, 32 * kEpiWarps);
-          if (pw4) pa_barA += clock64() - tA;
+          mbar_wait(&gin_full[r], it & 1);
+          if (pw4) pa_barA += clock64() - tA;                    // waiting for the round's operands
+          uint4 dn[GPR][2];
+#pragma unroll
+          for (int j = 0; j < GPR; ++j) {
+            const uint32_t gl = half * GPR + j;
+            if (p.dc_next) {
+              dn[j][0] = ld_shared_v4(nrow + (((gl * 2) ^ sw) << 4));
+              dn[j][1] = ld_shared_v4(nrow + (((gl * 2 + 1) ^ sw) << 4));
+            } else {
+              dn[j][0] = make_uint4(0u, 0u, 0u, 0u); dn[j][1] = dn[j][0];
+            }
+          }
+          tA = pw4 ? clock64() : 0;
+          named_bar_sync(1, 32 * kEpiWarps);                     // X: every dc_next read precedes every dZ_i / dZ_f write
+          if (pw4) pa_barB += clock64() - tA;
 #pragma unroll
           for (int j = 0; j < GPR; ++j) {
             constexpr int kLast = 2 * GPR - 1;
             const int idx = r * GPR + j;
-            const int gl = half * GPR + j;          // granule within the round: 0..3
+            const uint32_t gl = half * GPR + j;     // granule within the round: 0..3
             const int g = r * 4 + gl;               // granule within the 64-channel slice: 0..7
-            if (idx < kLast) {                      // prefetch the next granule's operands
-              const int nidx = idx + 1;
-              issue_loads((nidx / GPR) * 4 + half * GPR + (nidx % GPR), gin[nidx & 1]);
-            }
             uint32_t vi[8], vf[8], vo[8], vg[8];
             tmem_ld8(t_acc + 0 * CH_TILE + g * 8, vi);
             tmem_ld8(t_acc + 1 * CH_TILE + g * 8, vf);
@@ -808,17 +849,24 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                 bg[4 * v] = d4.x; bg[4 * v + 1] = d4.y; bg[4 * v + 2] = d4.z; bg[4 * v + 3] = d4.w;
               }
             }
+            const uint32_t ca0 = crow + (((gl * 2) ^ sw) << 4), ca1 = crow + (((gl * 2 + 1) ^ sw) << 4);
+            const uint32_t za = zrow + ((gl ^ sw64) << 4);
+            const uint4 c0 = ld_shared_v4(ca0), c1 = ld_shared_v4(ca1);
+            const uint4 h1 = ld_shared_v4(za + 2 * 8192);
+            const uint4 h2 = p.dh2 ? ld_shared_v4(za + 3 * 8192) : make_uint4(0u, 0u, 0u, 0u);
             long long tL = pw4 ? clock64() : 0;
             tmem_ld_wait();
             if (pw4) pa_ld += clock64() - tL;
             if (idx == kLast) release();
             tL = pw4 ? clock64() : 0;
-            if (valid) {
-              const GIn& in = gin[idx & 1];
-              const float cp[8] = {in.c0.x, in.c0.y, in.c0.z, in.c0.w, in.c1.x, in.c1.y, in.c1.z, in.c1.w};
-              const float dcn[8] = {in.d0.x, in.d0.y, in.d0.z, in.d0.w, in.d1.x, in.d1.y, in.d1.z, in.d1.w};
-              const uint32_t w1[4] = {in.dh.x, in.dh.y, in.dh.z, in.dh.w};
-              const uint32_t w2[4] = {in.dh2.x, in.dh2.y, in.dh2.z, in.dh2.w};
+            {
+              const float cp[8] = {__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z), __uint_as_float(c0.w),
+                                   __uint_as_float(c1.x), __uint_as_float(c1.y), __uint_as_float(c1.z), __uint_as_float(c1.w)};
+              const float dcn[8] = {__uint_as_float(dn[j][0].x), __uint_as_float(dn[j][0].y), __uint_as_float(dn[j][0].z),
+                                    __uint_as_float(dn[j][0].w), __uint_as_float(dn[j][1].x), __uint_as_float(dn[j][1].y),
+                                    __uint_as_float(dn[j][1].z), __uint_as_float(dn[j][1].w)};
+              const uint32_t w1[4] = {h1.x, h1.y, h1.z, h1.w};
+              const uint32_t w2[4] = {h2.x, h2.y, h2.z, h2.w};
               float dcp[8];
               uint32_t zi[4], zf[4], zo[4], zg[4];
 #pragma unroll
@@ -849,36 +897,20 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                 zo[e >> 1] = pack_bf16x2(do_[0], do_[1]);
                 zg[e >> 1] = pack_bf16x2(dg_[0], dg_[1]);
               }
-              // staging: dZ gate boxes are [128 px][32 ch] bf16 = 64-byte rows (SWIZZLE_64B: chunk ^= (row >> 1) & 3);
-              //          dc_prev box is [128 px][32 ch] fp32 = 128-byte rows (SWIZZLE_128B: chunk ^= row & 7)
-              const uint32_t so = smem_u32(stage_out);
-              const uint32_t zrow = so + row * 64 + ((static_cast<uint32_t>(gl) ^ ((row >> 1) & 3)) << 4);
-              st_shared_v4(zrow + 0 * 8192, zi[0], zi[1], zi[2], zi[3]);
-              st_shared_v4(zrow + 1 * 8192, zf[0], zf[1], zf[2], zf[3]);
-              st_shared_v4(zrow + 2 * 8192, zo[0], zo[1], zo[2], zo[3]);
-              st_shared_v4(zrow + 3 * 8192, zg[0], zg[1], zg[2], zg[3]);
-              const uint32_t crow = so + 32768 + row * 128;
-              const uint32_t sw = row & 7;
-              st_shared_v4(crow + (((gl * 2) ^ sw) << 4), __float_as_uint(dcp[0]), __float_as_uint(dcp[1]),
-                           __float_as_uint(dcp[2]), __float_as_uint(dcp[3]));
-              st_shared_v4(crow + (((gl * 2 + 1) ^ sw) << 4), __float_as_uint(dcp[4]), __float_as_uint(dcp[5]),
-                           __float_as_uint(dcp[6]), __float_as_uint(dcp[7]));
+              st_shared_v4(za + 0 * 8192, zi[0], zi[1], zi[2], zi[3]);
+              st_shared_v4(za + 1 * 8192, zf[0], zf[1], zf[2], zf[3]);
+              st_shared_v4(za + 2 * 8192, zo[0], zo[1], zo[2], zo[3]);
+              st_shared_v4(za + 3 * 8192, zg[0], zg[1], zg[2], zg[3]);
+              st_shared_v4(ca0, __float_as_uint(dcp[0]), __float_as_uint(dcp[1]), __float_as_uint(dcp[2]),
+                           __float_as_uint(dcp[3]));
+              st_shared_v4(ca1, __float_as_uint(dcp[4]), __float_as_uint(dcp[5]), __float_as_uint(dcp[6]),
+                           __float_as_uint(dcp[7]));
             }
             if (pw4) pa_math += clock64() - tL;
           }
-          long long tB = pw4 ? clock64() : 0;
-          fence_proxy_async_smem();
-          named_bar_sync(1, 32 * kEpiWarps);
-          if (pw4) pa_barB += clock64() - tB;
-          if (issuer) {
-            const uint32_t so = smem_u32(stage_out);
-            const int cbase = ch0 + r * 32;
-#pragma unroll
-            for (int gate = 0; gate < 4; ++gate)
-              tma_store_4d(&tmap_o0, so + gate * 8192, gate * p.Ch + cbase, x0, y0, b);   // dZ, reference gate order
-            tma_store_4d(&tmap_o1, so + 32768, cbase, x0, y0, b);                         // dc_prev
-            tma_store_commit();
-          }
+          fence_proxy_async_smem();                 // my st.shared -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&gout_ready[r]);
         }
       } else if constexpr (EPI == EPI_LSTM_BWD_GATES) {
         // ---- direct-store variant (channel slices narrower than 64): 16-channel chunks
@@ -1111,7 +1143,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       }
       if (!released) release();   // warps without a chunk for this tile shape
     }
-    if (Cfg::kTmaStore || (EPI == EPI_PLAIN && p.plain_tma)) {
+    if ((Cfg::kTmaStore && EPI != EPI_LSTM_BWD_GATES) || (EPI == EPI_PLAIN && p.plain_tma)) {
       if (warp == 4 && lane == 0) tma_store_wait_all();   // bulk stores complete before the CTA retires
     }
     if ((kProfEnabled && p.prof) && warp == 4 && lane == 0) {

@@ -454,7 +454,8 @@ int pick_cta_group(int num_m_tiles) {
 
 template <int NT, int EPI, int CTA>
 int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                        const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st, int kind, double flops) {
+                        const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st, int kind, double flops,
+                        const plc::GateMaps* gm) {
   using Cfg = plc::ConvTcCfg<NT, CTA, EPI>;
   plc::ConvTcParams p = p_in;
   p.prof = g_prof_buf;
@@ -467,7 +468,7 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
     p.div_tiles_y = small ? magic(p.tiles_y) : 0;
   }
   if (p.patch) {   // carve the pipeline region into patch slots + weight stages
-    const int region = Cfg::kStages * Cfg::kStageBytes;
+    const int region = Cfg::kPipeBytes;
     if (p.kc < 64) p.patch_slots = 4;    // narrow single-unit tiles are short: several tiles of look-ahead
     else p.patch_slots = (region - 3 * p.patch_slot_bytes) / Cfg::kBBytes >= 4 ? 3 : 2;
     int nb = (region - p.patch_slots * p.patch_slot_bytes) / Cfg::kBBytes;
@@ -492,7 +493,8 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   LaunchTimer timer(kind, st, flops);
-  PLC_CUDA(cudaLaunchKernelEx(&cfg, kfn, p, a0, a1, b, o0, o1));
+  static const plc::GateMaps no_gate_maps{};     // only the gate-gradient epilogue reads them
+  PLC_CUDA(cudaLaunchKernelEx(&cfg, kfn, p, a0, a1, b, o0, o1, gm ? *gm : no_gate_maps));
   return PLC_OK;
 }
 
@@ -500,11 +502,11 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
 template <int EPI>
 int launch_conv_tc(int n_tile, int cta, const plc::ConvTcParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
                    const CUtensorMap& b, const CUtensorMap& o0, const CUtensorMap& o1, cudaStream_t st, int kind,
-                   double flops) {
-#define PLC_LAUNCH_TC(NT)                                                                     \
-  case NT:                                                                                    \
-    return cta == 2 ? launch_conv_tc_inst<NT, EPI, 2>(p, a0, a1, b, o0, o1, st, kind, flops)  \
-                    : launch_conv_tc_inst<NT, EPI, 1>(p, a0, a1, b, o0, o1, st, kind, flops);
+                   double flops, const plc::GateMaps* gm = nullptr) {
+#define PLC_LAUNCH_TC(NT)                                                                         \
+  case NT:                                                                                        \
+    return cta == 2 ? launch_conv_tc_inst<NT, EPI, 2>(p, a0, a1, b, o0, o1, st, kind, flops, gm)  \
+                    : launch_conv_tc_inst<NT, EPI, 1>(p, a0, a1, b, o0, o1, st, kind, flops, gm);
   switch (n_tile) {
     PLC_LAUNCH_TC(64)
     PLC_LAUNCH_TC(128)
@@ -543,7 +545,7 @@ int pipeline_region_nt(int nt, int* b_bytes) {
   case NT: {                                                 \
     using Cfg = plc::ConvTcCfg<NT, CTA, EPI>;                \
     *b_bytes = Cfg::kBBytes;                                 \
-    return Cfg::kStages * Cfg::kStageBytes;                  \
+    return Cfg::kPipeBytes;                                  \
   }
   switch (nt) { PLC_REGION(64) PLC_REGION(128) PLC_REGION(192) PLC_REGION(256) }
 #undef PLC_REGION
@@ -956,14 +958,23 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   const int cta = pick_cta_group(p.num_m_tiles);
   if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile / cta))) return rc;
   CUtensorMap tzo = ta1, tdc = ta1;
+  plc::GateMaps gm{};
   if (plc::tma_store_epilogue<256, plc::EPI_LSTM_BWD_GATES>() && g.n_tile == 256) {
     // dZ half-slices: [32 ch] bf16 = 64-byte rows -> SWIZZLE_64B; dc_prev [32 ch] fp32 = 128-byte rows
     if ((rc = make_tmap_act(&tzo, workspace, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th, 2, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
       return rc;
     if ((rc = make_tmap_act(&tdc, dc_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
+    // per-pixel operands of the epilogue, same boxes: c_prev / dc_next like dc_prev, dh / dh2 like a dZ gate box
+    if ((rc = make_tmap_act(&gm.c_prev, c_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
+    gm.dc_next = gm.c_prev;
+    if (dc_next && (rc = make_tmap_act(&gm.dc_next, dc_next, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
+    if ((rc = make_tmap_act(&gm.dh, dh, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    gm.dh2 = gm.dh;
+    if (dh2 && (rc = make_tmap_act(&gm.dh2, dh2, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
   }
   if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, tzo, tdc, st, PLC_K_BWD_GATES,
-                                                    conv_flops(d->B, d->H, d->W, d->Cin + d->Ch, 4 * d->Ch, d->k))))
+                                                    conv_flops(d->B, d->H, d->W, d->Cin + d->Ch, 4 * d->Ch, d->k), &gm)))
     return rc;
 
   // 2) dgrad: conv of dZ (4Ch channels) with the flipped/transposed image -> dx, dh_prev
