@@ -116,10 +116,13 @@ struct ConvTcCfg {
   // (double-buffered up to N_TILE = 128: short-K convs finish a tile faster than its bulk stores drain)
   static constexpr int kPlainBufs = N_TILE <= 128 ? 2 : 1;
   static constexpr int kPlainBufBytes = (N_TILE / 64) * 16384;
-  // bwd gates: two operand/output buffers, one per 32-channel round of a tile.  The loader warp fills a buffer by TMA
-  // with c_prev | dc_next | dh | dh2 of the round; the epilogue overwrites it IN PLACE with dc_prev | dZ_i dZ_f | dZ_o |
-  // dZ_g (same bytes per pixel) and the loader warp sends it off as five tensor stores.
-  static constexpr int kGateBufBytes = 3 * 16384;
+  // bwd gates: two operand/output buffers holding one 16-channel round of a tile each (four rounds per 64-channel
+  // slice).  The loader warp fills a buffer by TMA with c_prev | dc_next | dh | dh2 of the round; the epilogue overwrites
+  // it IN PLACE with dc_prev | dZ_i dZ_f | dZ_o | dZ_g (same bytes per pixel) and the loader warp sends it off as five
+  // tensor stores.  Small rounds keep the buffers at 48 KB: the mainloop is weight-feed bound below ~6 weight stages
+  // (32-channel rounds = 96 KB left 2 patch slots + 4 stages and the MMA warp waited for weights half of the time).
+  static constexpr int kGateRoundCh = 16;
+  static constexpr int kGateBufBytes = 128 * kGateRoundCh * 12;     // 24 KB
   static constexpr int kStoreBytes = kTmaStore ? (EPI == 1 /*EPI_LSTM_BWD_GATES*/ ? 2 * kGateBufBytes : 3 * 16384)
                                                : (EPI == 2 /*EPI_PLAIN*/ ? kPlainBufs * kPlainBufBytes : 0);
   // cta_group::2: the CTA pair shares one 256 x N_TILE accumulator tile; each CTA stages its own 128 pixels of A
@@ -168,8 +171,8 @@ __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int
 template <int V>
 struct IntC { static constexpr int value = V; };
 
-// tensor maps of the gate-gradient epilogue's per-pixel operands (EPI_LSTM_BWD_GATES, N_TILE = 256): 32-channel boxes of
-// one 128-pixel tile -- fp32 [32 ch] = 128-byte rows (SWIZZLE_128B), bf16 [32 ch] = 64-byte rows (SWIZZLE_64B)
+// tensor maps of the gate-gradient epilogue's per-pixel operands (EPI_LSTM_BWD_GATES, N_TILE = 256): 16-channel boxes of
+// one 128-pixel tile -- fp32 [16 ch] = 64-byte rows (SWIZZLE_64B), bf16 [16 ch] = 32-byte rows (SWIZZLE_32B)
 struct GateMaps { CUtensorMap c_prev, dc_next, dh, dh2; };
 
 // epilogue warps: the LSTM epilogues are MUFU/latency heavy (5 transcendentals per element) and must finish a tile
@@ -564,25 +567,27 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   } else if (warp == 3) {
     if constexpr (EPI == EPI_LSTM_BWD_GATES && Cfg::kTmaStore) {
       // ===================================================================== gate-operand loader / output storer
-      // Round R = 2 * (tile index of this CTA) + (32-channel half of the slice) lives in buffer R & 1.  Loads run TWO
-      // rounds ahead of the epilogue: buffer R & 1 is refilled for round R + 2 as soon as the stores of round R have
+      // Round R = NR * (tile index of this CTA) + (16-channel quarter of the slice) lives in buffer R & 1.  Loads run
+      // TWO rounds ahead of the epilogue: buffer R & 1 is refilled for round R + 2 as soon as the stores of round R have
       // finished reading it, i.e. a whole round before the epilogue warps need it.
+      constexpr int RC = Cfg::kGateRoundCh, NR = CH_TILE / RC;
+      constexpr uint32_t kF = 128 * RC * 4, kH = 128 * RC * 2;     // bytes of an fp32 / bf16 box
       const uint32_t so = smem_u32(stage_out), inf_base = smem_u32(gin_full);
       const int my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tile_step - 1) / tile_step : 0;
-      const int rounds = 2 * my_tiles;
-      const uint32_t tx = 16384u + 8192u + (p.dc_next ? 16384u : 0u) + (p.dh2 ? 8192u : 0u);
+      const int rounds = NR * my_tiles;
+      const uint32_t tx = kF + kH + (p.dc_next ? kF : 0u) + (p.dh2 ? kH : 0u);
       auto load_round = [&](int R) {
         if (R >= rounds) return;
         int n_tile, b, y0, x0;
-        decode_tile<kCta>(p, tile0 + (R >> 1) * tile_step, rank, n_tile, b, y0, x0);
+        decode_tile<kCta>(p, tile0 + (R / NR) * tile_step, rank, n_tile, b, y0, x0);
         if (lane == 0) {
           const uint32_t buf = so + (R & 1) * Cfg::kGateBufBytes, bar = inf_base + (R & 1) * 8;
-          const int cb = n_tile * CH_TILE + (R & 1) * 32;
+          const int cb = n_tile * CH_TILE + (R % NR) * RC;
           mbar_arrive_expect_tx(&gin_full[R & 1], tx);
           tma_load_4d_s(buf, &gmaps.c_prev, bar, cb, x0, y0, b);
-          if (p.dc_next) tma_load_4d_s(buf + 16384, &gmaps.dc_next, bar, cb, x0, y0, b);
-          tma_load_4d_s(buf + 32768, &gmaps.dh, bar, cb, x0, y0, b);
-          if (p.dh2) tma_load_4d_s(buf + 40960, &gmaps.dh2, bar, cb, x0, y0, b);
+          if (p.dc_next) tma_load_4d_s(buf + kF, &gmaps.dc_next, bar, cb, x0, y0, b);
+          tma_load_4d_s(buf + 2 * kF, &gmaps.dh, bar, cb, x0, y0, b);
+          if (p.dh2) tma_load_4d_s(buf + 2 * kF + kH, &gmaps.dh2, bar, cb, x0, y0, b);
         }
         __syncwarp();
       };
@@ -591,14 +596,14 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       for (int R = 0; R < rounds; ++R) {
         mbar_wait(&gout_ready[R & 1], (R >> 1) & 1);
         int n_tile, b, y0, x0;
-        decode_tile<kCta>(p, tile0 + (R >> 1) * tile_step, rank, n_tile, b, y0, x0);
+        decode_tile<kCta>(p, tile0 + (R / NR) * tile_step, rank, n_tile, b, y0, x0);
         if (lane == 0) {   // OOB rows / images (ragged tiles, odd tail pair) are clipped by TMA
           const uint32_t buf = so + (R & 1) * Cfg::kGateBufBytes;
-          const int cb = n_tile * CH_TILE + (R & 1) * 32;
+          const int cb = n_tile * CH_TILE + (R % NR) * RC;
           tma_store_4d(&tmap_o1, buf, cb, x0, y0, b);                                    // dc_prev
 #pragma unroll
           for (int gate = 0; gate < 4; ++gate)                                           // dZ, reference gate order
-            tma_store_4d(&tmap_o0, buf + 16384 + gate * 8192, gate * p.Ch + cb, x0, y0, b);
+            tma_store_4d(&tmap_o0, buf + kF + gate * kH, gate * p.Ch + cb, x0, y0, b);
           tma_store_commit();
           tma_store_wait_read();
         }
@@ -786,35 +791,37 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           }
         }
       } else if constexpr (EPI == EPI_LSTM_BWD_GATES && Cfg::kTmaStore) {
-        // ---- gate recompute + dZ / dc_prev, 8-channel granules.  Two rounds per tile (channels 0-31,
-        // 32-63 of the slice).  The per-pixel operands arrive by TMA in the round's buffer (loader warp) and the outputs
+        // ---- gate recompute + dZ / dc_prev, 8-channel granules.  Four 16-channel rounds per tile.
+        // The per-pixel operands arrive by TMA in the round's buffer (loader warp) and the outputs
         // overwrite them in place: dc_prev over c_prev, dZ_o over dh, dZ_g over dh2 (same thread, same address), dZ_i and
         // dZ_f over dc_next -- the only aliasing across threads, hence dc_next is read first and barrier X follows.
         // No per-thread global access is left in this epilogue; ragged tiles compute on TMA's zero fill and are clipped
         // by the tensor stores.
         const int ch0 = n_tile * CH_TILE;
+        constexpr int RC = Cfg::kGateRoundCh, NR = CH_TILE / RC, GR = RC / 8;
         constexpr int WQ = kEpiWarps / 4;          // warps per TMEM lane quadrant
-        constexpr int GPR = 4 / WQ;                // granules per round per warp
-        static_assert(CH_TILE == 64 && (4 % WQ) == 0, "TMA-store gate epilogue assumes a 64-channel slice");
-        const uint32_t sw = row & 7, sw64 = (row >> 1) & 3;
+        constexpr int GPR = GR / WQ;               // granules per round per warp
+        constexpr uint32_t kF = 128 * RC * 4, kH = 128 * RC * 2;     // bytes of an fp32 / bf16 box
+        static_assert(CH_TILE == 64 && RC == 16 && GPR >= 1 && GPR * WQ == GR, "gate epilogue: 16-channel rounds, 8 warps");
+        const uint32_t sw64 = (row >> 1) & 3, sw32 = (row >> 2) & 1;
         const bool pw4 = (kProfEnabled && p.prof) && warp == 4 && lane == 0;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const uint32_t buf = smem_u32(stage_out) + r * Cfg::kGateBufBytes;
-          const uint32_t crow = buf + row * 128;                 // c_prev -> dc_prev   [128 px][32 ch] fp32, SWIZZLE_128B
-          const uint32_t nrow = buf + 16384 + row * 128;         // dc_next             (same layout)
-          const uint32_t zrow = buf + 16384 + row * 64;          // dZ_i, dZ_f, dZ_o (over dh), dZ_g (over dh2): four
-                                                                 // [128 px][32 ch] bf16 boxes, 64-byte rows, SWIZZLE_64B
+        for (int r = 0; r < NR; ++r) {
+          const uint32_t buf = smem_u32(stage_out) + (r & 1) * Cfg::kGateBufBytes;
+          const uint32_t crow = buf + row * 64;                  // c_prev -> dc_prev   [128 px][16 ch] fp32, SWIZZLE_64B
+          const uint32_t nrow = buf + kF + row * 64;             // dc_next             (same layout)
+          const uint32_t zrow = buf + kF + row * 32;             // dZ_i, dZ_f, dZ_o (over dh), dZ_g (over dh2): four
+                                                                 // [128 px][16 ch] bf16 boxes, 32-byte rows, SWIZZLE_32B
           long long tA = pw4 ? clock64() : 0;
-          mbar_wait(&gin_full[r], it & 1);
+          mbar_wait(&gin_full[r & 1], ((it * NR + r) >> 1) & 1);
           if (pw4) pa_barA += clock64() - tA;                    // waiting for the round's operands
           uint4 dn[GPR][2];
 #pragma unroll
           for (int j = 0; j < GPR; ++j) {
             const uint32_t gl = half * GPR + j;
             if (p.dc_next) {
-              dn[j][0] = ld_shared_v4(nrow + (((gl * 2) ^ sw) << 4));
-              dn[j][1] = ld_shared_v4(nrow + (((gl * 2 + 1) ^ sw) << 4));
+              dn[j][0] = ld_shared_v4(nrow + (((gl * 2) ^ sw64) << 4));
+              dn[j][1] = ld_shared_v4(nrow + (((gl * 2 + 1) ^ sw64) << 4));
             } else {
               dn[j][0] = make_uint4(0u, 0u, 0u, 0u); dn[j][1] = dn[j][0];
             }
@@ -824,10 +831,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           if (pw4) pa_barB += clock64() - tA;
 #pragma unroll
           for (int j = 0; j < GPR; ++j) {
-            constexpr int kLast = 2 * GPR - 1;
+            constexpr int kLast = NR * GPR - 1;
             const int idx = r * GPR + j;
-            const uint32_t gl = half * GPR + j;     // granule within the round: 0..3
-            const int g = r * 4 + gl;               // granule within the 64-channel slice: 0..7
+            const uint32_t gl = half * GPR + j;     // granule within the round
+            const int g = r * GR + gl;              // granule within the 64-channel slice: 0..7
             uint32_t vi[8], vf[8], vo[8], vg[8];
             tmem_ld8(t_acc + 0 * CH_TILE + g * 8, vi);
             tmem_ld8(t_acc + 1 * CH_TILE + g * 8, vf);
@@ -849,11 +856,11 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                 bg[4 * v] = d4.x; bg[4 * v + 1] = d4.y; bg[4 * v + 2] = d4.z; bg[4 * v + 3] = d4.w;
               }
             }
-            const uint32_t ca0 = crow + (((gl * 2) ^ sw) << 4), ca1 = crow + (((gl * 2 + 1) ^ sw) << 4);
-            const uint32_t za = zrow + ((gl ^ sw64) << 4);
+            const uint32_t ca0 = crow + (((gl * 2) ^ sw64) << 4), ca1 = crow + (((gl * 2 + 1) ^ sw64) << 4);
+            const uint32_t za = zrow + ((gl ^ sw32) << 4);
             const uint4 c0 = ld_shared_v4(ca0), c1 = ld_shared_v4(ca1);
-            const uint4 h1 = ld_shared_v4(za + 2 * 8192);
-            const uint4 h2 = p.dh2 ? ld_shared_v4(za + 3 * 8192) : make_uint4(0u, 0u, 0u, 0u);
+            const uint4 h1 = ld_shared_v4(za + 2 * kH);
+            const uint4 h2 = p.dh2 ? ld_shared_v4(za + 3 * kH) : make_uint4(0u, 0u, 0u, 0u);
             long long tL = pw4 ? clock64() : 0;
             tmem_ld_wait();
             if (pw4) pa_ld += clock64() - tL;
@@ -897,10 +904,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                 zo[e >> 1] = pack_bf16x2(do_[0], do_[1]);
                 zg[e >> 1] = pack_bf16x2(dg_[0], dg_[1]);
               }
-              st_shared_v4(za + 0 * 8192, zi[0], zi[1], zi[2], zi[3]);
-              st_shared_v4(za + 1 * 8192, zf[0], zf[1], zf[2], zf[3]);
-              st_shared_v4(za + 2 * 8192, zo[0], zo[1], zo[2], zo[3]);
-              st_shared_v4(za + 3 * 8192, zg[0], zg[1], zg[2], zg[3]);
+              st_shared_v4(za + 0 * kH, zi[0], zi[1], zi[2], zi[3]);
+              st_shared_v4(za + 1 * kH, zf[0], zf[1], zf[2], zf[3]);
+              st_shared_v4(za + 2 * kH, zo[0], zo[1], zo[2], zo[3]);
+              st_shared_v4(za + 3 * kH, zg[0], zg[1], zg[2], zg[3]);
               st_shared_v4(ca0, __float_as_uint(dcp[0]), __float_as_uint(dcp[1]), __float_as_uint(dcp[2]),
                            __float_as_uint(dcp[3]));
               st_shared_v4(ca1, __float_as_uint(dcp[4]), __float_as_uint(dcp[5]), __float_as_uint(dcp[6]),
@@ -910,7 +917,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           }
           fence_proxy_async_smem();                 // my st.shared -> visible to the TMA (async proxy)
           __syncwarp();
-          if (lane == 0) mbar_arrive(&gout_ready[r]);
+          if (lane == 0) mbar_arrive(&gout_ready[r & 1]);
         }
       } else if constexpr (EPI == EPI_LSTM_BWD_GATES) {
         // ---- direct-store variant (channel slices narrower than 64): 16-channel chunks

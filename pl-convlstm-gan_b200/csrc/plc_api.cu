@@ -960,18 +960,18 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   CUtensorMap tzo = ta1, tdc = ta1;
   plc::GateMaps gm{};
   if (plc::tma_store_epilogue<256, plc::EPI_LSTM_BWD_GATES>() && g.n_tile == 256) {
-    // dZ half-slices: [32 ch] bf16 = 64-byte rows -> SWIZZLE_64B; dc_prev [32 ch] fp32 = 128-byte rows
-    if ((rc = make_tmap_act(&tzo, workspace, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th, 2, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
-      return rc;
-    if ((rc = make_tmap_act(&tdc, dc_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
-    // per-pixel operands of the epilogue, same boxes: c_prev / dc_next like dc_prev, dh / dh2 like a dZ gate box
-    if ((rc = make_tmap_act(&gm.c_prev, c_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
+    // 16-channel round boxes (ConvTcCfg::kGateRoundCh): bf16 = 32-byte rows -> SWIZZLE_32B (dZ gate slices, dh, dh2);
+    // fp32 = 64-byte rows -> SWIZZLE_64B (dc_prev, c_prev, dc_next)
+    const int rc_ch = 16;
+    const CUtensorMapSwizzle s32 = CU_TENSOR_MAP_SWIZZLE_32B, s64 = CU_TENSOR_MAP_SWIZZLE_64B;
+    if ((rc = make_tmap_act(&tzo, workspace, d->B, d->H, d->W, 4 * d->Ch, g.tw, g.th, 2, rc_ch, s32))) return rc;
+    if ((rc = make_tmap_act(&tdc, dc_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, rc_ch, s64))) return rc;
+    if ((rc = make_tmap_act(&gm.c_prev, c_prev, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, rc_ch, s64))) return rc;
     gm.dc_next = gm.c_prev;
-    if (dc_next && (rc = make_tmap_act(&gm.dc_next, dc_next, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, 32))) return rc;
-    if ((rc = make_tmap_act(&gm.dh, dh, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (dc_next && (rc = make_tmap_act(&gm.dc_next, dc_next, d->B, d->H, d->W, d->Ch, g.tw, g.th, 4, rc_ch, s64))) return rc;
+    if ((rc = make_tmap_act(&gm.dh, dh, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, rc_ch, s32))) return rc;
     gm.dh2 = gm.dh;
-    if (dh2 && (rc = make_tmap_act(&gm.dh2, dh2, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, 32, CU_TENSOR_MAP_SWIZZLE_64B)))
-      return rc;
+    if (dh2 && (rc = make_tmap_act(&gm.dh2, dh2, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, rc_ch, s32))) return rc;
   }
   if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, tzo, tdc, st, PLC_K_BWD_GATES,
                                                     conv_flops(d->B, d->H, d->W, d->Cin + d->Ch, 4 * d->Ch, d->k), &gm)))
