@@ -182,6 +182,26 @@ int plc_convnd_wgrad_unpack(const PlcConvNdDesc* d, const float* dW_acc, float* 
 int plc_convnd_bwd(const PlcConvNdDesc* d, const void* x, const void* dz, const void* w_packed_dgrad, void* dx,
                    float* dW_acc, float* db_acc, void* stream);
 
+/* ---- frame-level first layer (discriminator conv1): 3x3 conv straight from fp32 frames --------------------------
+ * out[n, yo, xo, co] = act(bias[co] + sum_{ci, ky, kx} w[co, ci, ky, kx] * frames[n, ci, yo*s + ky - 1, xo*s + kx - 1])
+ *   frames [N, Cf, H, W] fp32 (Cf = 1..4; a clip [B, T, Cf, H, W] is N = B*T frames), zero padding 1, stride s = 1 or 2
+ *   w [Cout, Cf, 3, 3] fp32 (torch layout, unpacked), bias [Cout]; Cout in {8, 16, 32, 64, 128, 256}
+ *   out / y / dy [N, Ho, Wo, Cout] bf16, Ho = (H-1)/s + 1;  act: 0 none, 1 ReLU, 2 LeakyReLU(slope)
+ * With one rain channel the layer is 9 multiply-adds per output value and HBM-bound: SIMT kernels that read the frames
+ * where they lie replace the implicit-GEMM path for it (csrc/frame_conv.cuh has the numbers).  Eager spec:
+ * oracle/gan_oracle.py conv1.  plc_frameconv_bwd takes the forward output y and dY and applies act'(y) on the fly:
+ * dframes [N, Cf, H, W] fp32 is overwritten (nullable), dW [Cout, Cf, 3, 3] and db [Cout] are ACCUMULATED (nullable). */
+typedef struct PlcFrameConvDesc {
+  int32_t N, Cf, H, W, Cout, stride, act;
+  float slope;
+  int32_t has_bias;
+} PlcFrameConvDesc;
+int plc_frameconv_out_shape(const PlcFrameConvDesc* d, int* H_out, int* W_out);
+int plc_frameconv_fwd(const PlcFrameConvDesc* d, const float* frames, const float* w_oihw, const float* bias, void* out,
+                      void* stream);
+int plc_frameconv_bwd(const PlcFrameConvDesc* d, const float* frames, const float* w_oihw, const void* y, const void* dy,
+                      float* dframes, float* dW, float* db, void* stream);
+
 /* ---- per-launch timing (bench.py's roofline / step breakdown) -------------------------------------
  * plc_timing_enable(1) clears the record and makes every kernel launch of the library record a CUDA event pair on
  * its launching stream, tagged with a PlcKernelKind; plc_timing_enable(0) stops recording (and clears).

@@ -38,8 +38,14 @@ class PlcConvNdDesc(ctypes.Structure):
                 [("slope", ctypes.c_float), ("has_bias", ctypes.c_int32)])
 
 
+class PlcFrameConvDesc(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_int32) for n in ("N", "Cf", "H", "W", "Cout", "stride", "act")] +
+                [("slope", ctypes.c_float), ("has_bias", ctypes.c_int32)])
+
+
 _vp, _sz, _int = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
 _np = ctypes.POINTER(PlcConvNdDesc)
+_fp = ctypes.POINTER(PlcFrameConvDesc)
 _ip = ctypes.POINTER(ctypes.c_int)
 _dp = ctypes.POINTER(PlcCellDesc)
 _cp = ctypes.POINTER(PlcConvDesc)
@@ -73,6 +79,9 @@ SIGNATURES = {
     "plc_convnd_wgrad_acc_bytes": (_sz, [_np]),
     "plc_convnd_wgrad_unpack": (_int, [_np, _vp, _vp, _vp]),
     "plc_convnd_bwd": (_int, [_np, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "plc_frameconv_out_shape": (_int, [_fp, _ip, _ip]),
+    "plc_frameconv_fwd": (_int, [_fp, _vp, _vp, _vp, _vp, _vp]),
+    "plc_frameconv_bwd": (_int, [_fp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plc_timing_enable": (_int, [_int]),
     "plc_timing_collect": (_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float),
                                   ctypes.POINTER(ctypes.c_double), _int]),

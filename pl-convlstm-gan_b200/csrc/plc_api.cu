@@ -16,6 +16,7 @@
 #include "../../include/plc.h"
 #include "conv_igemm_tc.cuh"
 #include "conv_simt.cuh"
+#include "frame_conv.cuh"
 #include "frame_io.cuh"
 #include "frontend_tc.cuh"
 #include "loss.cuh"
@@ -1487,6 +1488,100 @@ int plc_convnd_bwd(const PlcConvNdDesc* d, const void* x, const void* dz, const 
     w.Bs = g.nd5 ? d->B : d->B * d->T; w.Ts = d->T; w.Hs = d->H; w.Ws = d->W;
     if ((rc = launch_wgrad_tc_shape(&w, x, nullptr, dz, dW_acc, d->has_bias ? db_acc : nullptr, st, PLC_K_CONV_WGRAD)))
       return rc;
+  }
+  return PLC_OK;
+}
+
+// ---------------------------------------------------------------------------------- frame-level first layer
+static int check_frameconv(const PlcFrameConvDesc* d, const char* fn) {
+  if (!d) return fail(PLC_ERR_NULL_ARG, "%s: null descriptor", fn);
+  if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cf < 1 || d->Cf > 4)
+    return fail(PLC_ERR_BAD_DESC, "%s: need N, H, W > 0 and 1 <= Cf <= 4 (got N=%d H=%d W=%d Cf=%d)", fn, d->N, d->H, d->W,
+                d->Cf);
+  if (static_cast<long long>(d->N) * d->H >= (1ll << 31)) return fail(PLC_ERR_UNSUPPORTED, "%s: N*H must be < 2^31", fn);
+  if (d->stride != 1 && d->stride != 2) return fail(PLC_ERR_UNSUPPORTED, "%s: stride must be 1 or 2 (got %d)", fn, d->stride);
+  if (d->act < 0 || d->act > 2) return fail(PLC_ERR_BAD_DESC, "%s: act must be 0, 1 or 2", fn);
+  const int G = d->Cout / 8;
+  if (d->Cout % 8 || G < 1 || G > 32 || (G & (G - 1)))
+    return fail(PLC_ERR_UNSUPPORTED, "%s: Cout must be 8, 16, 32, 64, 128 or 256 (got %d)", fn, d->Cout);
+  return PLC_OK;
+}
+
+static void fill_frameconv(const PlcFrameConvDesc* d, plc::FrameConvParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->N = d->N; p->Cf = d->Cf; p->H = d->H; p->W = d->W; p->Cout = d->Cout; p->stride = d->stride;
+  p->Ho = (d->H - 1) / d->stride + 1; p->Wo = (d->W - 1) / d->stride + 1;
+  p->act = d->act; p->slope = d->slope;
+}
+
+int plc_frameconv_out_shape(const PlcFrameConvDesc* d, int* H_out, int* W_out) {
+  if (int rc = check_frameconv(d, "plc_frameconv_out_shape")) return rc;
+  if (H_out) *H_out = (d->H - 1) / d->stride + 1;
+  if (W_out) *W_out = (d->W - 1) / d->stride + 1;
+  return PLC_OK;
+}
+
+int plc_frameconv_fwd(const PlcFrameConvDesc* d, const float* frames, const float* w_oihw, const float* bias, void* out,
+                      void* stream) {
+  if (int rc = check_frameconv(d, "plc_frameconv_fwd")) return rc;
+  if (!frames || !w_oihw || !out || (d->has_bias && !bias)) return fail(PLC_ERR_NULL_ARG, "plc_frameconv_fwd: null pointer");
+  if (!aligned16(out)) return fail(PLC_ERR_ALIGNMENT, "plc_frameconv_fwd: out must be 16-byte aligned");
+  plc::FrameConvParams p;
+  fill_frameconv(d, &p);
+  p.frames = frames; p.w = w_oihw; p.bias = d->has_bias ? bias : nullptr;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  const size_t rows = static_cast<size_t>(p.N) * p.Ho, cap = static_cast<size_t>(sm_count()) * 8;
+  const size_t blocks = (rows + 7) / 8;           // 8 warps per block, one output row per warp at a time
+  const size_t smem = (static_cast<size_t>(d->Cf) * 9 * d->Cout + d->Cout) * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchTimer timer(PLC_K_CONV_FWD, st, 2.0 * p.N * p.Ho * p.Wo * 9.0 * d->Cf * d->Cout);
+  plc::frameconv_fwd_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, smem, st>>>(p);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+int plc_frameconv_bwd(const PlcFrameConvDesc* d, const float* frames, const float* w_oihw, const void* y, const void* dy,
+                      float* dframes, float* dW, float* db, void* stream) {
+  if (int rc = check_frameconv(d, "plc_frameconv_bwd")) return rc;
+  if (!frames || !w_oihw || !dy || (d->act != 0 && !y)) return fail(PLC_ERR_NULL_ARG, "plc_frameconv_bwd: null pointer");
+  if (!aligned16(y) || !aligned16(dy)) return fail(PLC_ERR_ALIGNMENT, "plc_frameconv_bwd: y / dy must be 16-byte aligned");
+  plc::FrameConvParams p;
+  fill_frameconv(d, &p);
+  p.frames = frames; p.w = w_oihw;
+  p.y = static_cast<const __nv_bfloat16*>(y); p.dy = static_cast<const __nv_bfloat16*>(dy);
+  p.dframes = dframes; p.dW = dW; p.db = d->has_bias ? db : nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double flops = 2.0 * p.N * p.Ho * p.Wo * 9.0 * d->Cf * d->Cout;
+  if (dW) {
+    const size_t rows = static_cast<size_t>(p.N) * p.Ho, cap = static_cast<size_t>(sm_count()) * 4;
+    const size_t blocks = (rows + 7) / 8;
+    LaunchTimer timer(PLC_K_CONV_WGRAD, st, flops);
+    plc::frameconv_wgrad_kernel<<<dim3(static_cast<unsigned>(blocks < cap ? blocks : cap), d->Cf), 256, 0, st>>>(p);
+    PLC_CUDA(cudaGetLastError());
+  }
+  if (dframes) {
+    const int R = d->stride == 2 ? 2 : 3;
+    const size_t smem = (static_cast<size_t>(9) * d->Cf * d->Cout + static_cast<size_t>(R) * p.Wo * 9 * d->Cf) * sizeof(float);
+    if (smem > 200 * 1024) return fail(PLC_ERR_UNSUPPORTED, "plc_frameconv_bwd: output row too wide for the dgrad ring (W=%d)", d->W);
+    const int cap = sm_count() * 8;
+    const unsigned grid = static_cast<unsigned>(p.N < cap ? p.N : cap);
+    LaunchTimer timer(PLC_K_CONV_DGRAD, st, flops);
+#define PLC_FC_DGRAD(SS, CC)                                                                                        \
+  do {                                                                                                              \
+    if (smem > 48 * 1024)                                                                                           \
+      PLC_CUDA(cudaFuncSetAttribute(plc::frameconv_dgrad_kernel<SS, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    static_cast<int>(smem)));                                                       \
+    plc::frameconv_dgrad_kernel<SS, CC><<<grid, 256, smem, st>>>(p);                                                \
+  } while (0)
+    if (d->stride == 2) {
+      switch (d->Cf) { case 1: PLC_FC_DGRAD(2, 1); break; case 2: PLC_FC_DGRAD(2, 2); break;
+                       case 3: PLC_FC_DGRAD(2, 3); break; default: PLC_FC_DGRAD(2, 4); }
+    } else {
+      switch (d->Cf) { case 1: PLC_FC_DGRAD(1, 1); break; case 2: PLC_FC_DGRAD(1, 2); break;
+                       case 3: PLC_FC_DGRAD(1, 3); break; default: PLC_FC_DGRAD(1, 4); }
+    }
+#undef PLC_FC_DGRAD
+    PLC_CUDA(cudaGetLastError());
   }
   return PLC_OK;
 }

@@ -573,3 +573,56 @@ class _ConvNdFn(torch.autograd.Function):
 def convnd(x: Tensor, cp: ConvNdParams) -> Tensor:
     """x [B,T,H,W,cin_p] bf16 (T = 1 for images) -> [B,To,Ho,Wo,cout_p] bf16; padded channels are zero."""
     return _ConvNdFn.apply(x, cp.conv.weight, cp.conv.bias, cp)
+
+
+# --------------------------------------------------------------------------------- frame-level first layer (fp32 frames in)
+from ._lib import PlcFrameConvDesc  # noqa: E402
+
+
+def frameconv_supported(conv: torch.nn.Module) -> bool:
+    """True if `conv` is a layer plc_frameconv_* runs: Conv2d(Cf <= 4, Cout in {8..256, power of two}, 3, stride 1|2, padding 1)."""
+    w = conv.weight
+    g = w.shape[0] // 8
+    return (w.dim() == 4 and tuple(w.shape[2:]) == (3, 3) and w.shape[1] <= 4 and w.shape[0] % 8 == 0 and 1 <= g <= 32
+            and g & (g - 1) == 0 and tuple(conv.padding) == (1, 1) and conv.stride[0] == conv.stride[1]
+            and conv.stride[0] in (1, 2))
+
+
+class _FrameConvFn(torch.autograd.Function):
+    """act(conv3x3(frames)) from fp32 frames [N,Cf,H,W] to NHWC bf16 [N,Ho,Wo,Cout] (plc_frameconv_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, frames, weight, bias, stride: int, act: int, slope: float):
+        lib = _lib.load()
+        _require_cuda(frames, "frames")
+        if frames.dtype != torch.float32 or frames.dim() != 4 or not frames.is_contiguous():
+            raise RuntimeError(f"frameconv: frames must be contiguous fp32 [N,Cf,H,W], got {frames.dtype} {tuple(frames.shape)}")
+        N, Cf, H, W = frames.shape
+        d = PlcFrameConvDesc(N, Cf, H, W, weight.shape[0], stride, act, float(slope), int(bias is not None))
+        ho, wo = ctypes.c_int(), ctypes.c_int()
+        _lib.check(lib.plc_frameconv_out_shape(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)), "plc_frameconv_out_shape")
+        w = weight.detach().to(torch.float32).contiguous()       # snapshot of the weights this forward ran with
+        b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        out = torch.empty(N, ho.value, wo.value, weight.shape[0], dtype=torch.bfloat16, device=frames.device)
+        _call(frames, lib.plc_frameconv_fwd, "plc_frameconv_fwd", ctypes.byref(d), _ptr(frames), _ptr(w), _ptr(b), _ptr(out))
+        ctx.d, ctx.w, ctx.has_bias = d, w, bias is not None
+        ctx.save_for_backward(frames, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        frames, out = ctx.saved_tensors
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dy = dy.contiguous()
+        dx = torch.empty_like(frames) if need_dx else None
+        dW = torch.zeros_like(ctx.w) if need_dw else None
+        db = torch.zeros(ctx.w.shape[0], dtype=torch.float32, device=frames.device) if (need_dw and ctx.has_bias) else None
+        _call(frames, lib.plc_frameconv_bwd, "plc_frameconv_bwd", ctypes.byref(ctx.d), _ptr(frames), _ptr(ctx.w), _ptr(out),
+              _ptr(dy), _ptr(dx), _ptr(dW), _ptr(db))
+        return dx, dW, db, None, None, None
+
+
+def frameconv(frames: Tensor, conv: torch.nn.Module, act: int = 0, slope: float = 0.2) -> Tensor:
+    """frames [N,Cf,H,W] fp32 -> act(conv(frames)) as NHWC bf16 [N,Ho,Wo,Cout]; `conv` is the parameter holder."""
+    return _FrameConvFn.apply(frames, conv.weight, conv.bias, conv.stride[0], act, slope)

@@ -27,7 +27,9 @@ class Discriminator(nn.Module):
 
     conv1 Conv2d(C,32,3,s2) per frame -> conv2 Conv3d(32,64,3,s(1,2,2)) -> conv3 Conv3d(64,128,3,s(2,2,2)), LeakyReLU(0.2)
     after each -> score Conv2d(128,1,3) per frame -> mean.  The nn.Conv2d / nn.Conv3d modules are PARAMETER HOLDERS
-    (state_dict keys conv1/conv2/conv3/score .weight/.bias, torch default init); they are never called."""
+    (state_dict keys conv1/conv2/conv3/score .weight/.bias, torch default init); they are never called.
+    conv1 runs in plc_frameconv_* (reads the fp32 frames directly) when its shape allows, else on the implicit-GEMM
+    core like the other three."""
 
     def __init__(self, in_channels: int = 1, widths: Sequence[int] = (32, 64, 128), slope: float = 0.2):
         super().__init__()
@@ -54,9 +56,14 @@ class Discriminator(nn.Module):
             raise RuntimeError("Discriminator (plconv) has no CPU path")
         n, t, c, hh, ww = clip.shape
         cp1, cp2, cp3, cp4 = self._params()
-        x = clip.permute(0, 1, 3, 4, 2)                                   # [N,T,H,W,C] (a view when C == 1)
-        x = TF.pad(x, (0, cp1.cin_p - c)).to(torch.bfloat16).contiguous()
-        a1 = F.convnd(x.view(n * t, 1, hh, ww, cp1.cin_p), cp1)           # strided 2-D conv, every frame
+        if F.frameconv_supported(self.conv1):
+            # first layer straight from the fp32 frames (plc_frameconv_*: HBM-bound SIMT kernels, no pad / cast pass)
+            a1 = F.frameconv(clip.reshape(n * t, c, hh, ww).float().contiguous(), self.conv1, act=2, slope=self.slope)
+            a1 = a1.unsqueeze(1)
+        else:
+            x = clip.permute(0, 1, 3, 4, 2)                               # [N,T,H,W,C] (a view when C == 1)
+            x = TF.pad(x, (0, cp1.cin_p - c)).to(torch.bfloat16).contiguous()
+            a1 = F.convnd(x.view(n * t, 1, hh, ww, cp1.cin_p), cp1)       # strided 2-D conv, every frame
         a2 = F.convnd(a1.view(n, t, *a1.shape[2:]), cp2)                  # strided 3-D conv (time stride 1)
         a3 = F.convnd(a2, cp3)                                            # strided 3-D conv (time stride 2)
         s = F.convnd(a3.view(n * a3.shape[1], 1, *a3.shape[2:]), cp4)     # 3x3 score conv, every remaining frame

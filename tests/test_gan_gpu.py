@@ -100,6 +100,56 @@ def test_strided_and_3d_conv_both_cta_group_paths(case, cta, cuda_device):
         lib.plc_debug_set_cta_group(0)
 
 
+# (N, Cf, H, W, Cout, stride, act)
+FRAME_CASES = [
+    (6, 1, 32, 32, 32, 2, 2),        # the discriminator's conv1
+    (3, 1, 19, 13, 32, 2, 2),        # odd, ragged grid
+    (2, 3, 17, 24, 16, 2, 1),        # 3 frame channels, ReLU
+    (2, 2, 16, 21, 8, 1, 0),         # stride 1, no activation
+    (2, 4, 12, 12, 64, 1, 2),        # 4 channels, stride 1
+    (1, 1, 9, 7, 128, 2, 2),
+]
+
+
+@pytest.mark.parametrize("case", FRAME_CASES, ids=lambda c: "N%d_Cf%d_%dx%d_C%d_s%d_act%d" % c)
+def test_frameconv_forward_backward_vs_torch(case, cuda_device):
+    """plc_frameconv_fwd / _bwd (first discriminator layer straight from fp32 frames) vs torch conv2d in fp64: output
+    (bf16 store: 1e-2 of max), d frames, dW, db (the activation mask taken from the stored bf16 output on both sides)."""
+    from plconv import functional as PF
+    n, cf, hh, ww, cout, s, act = case
+    torch.manual_seed(11)
+    conv = torch.nn.Conv2d(cf, cout, 3, stride=s, padding=1).to(cuda_device)
+    assert PF.frameconv_supported(conv)
+    x = torch.randn(n, cf, hh, ww, device=cuda_device).requires_grad_()
+    y = PF.frameconv(x, conv, act=act, slope=0.2)                          # [n, ho, wo, cout] bf16
+    xr = x.detach().double().cpu().requires_grad_()
+    wr = conv.weight.detach().double().cpu().requires_grad_()
+    br = conv.bias.detach().double().cpu().requires_grad_()
+    zr = TF.conv2d(xr, wr, br, stride=s, padding=1)
+    pos = (y.detach() > 0).permute(0, 3, 1, 2).cpu()
+    yr = zr if act == 0 else torch.where(pos, zr, (0.2 if act == 2 else 0.0) * zr)
+    assert tuple(y.shape) == (n, yr.shape[2], yr.shape[3], cout)
+    assert rel_err(y.permute(0, 3, 1, 2).cpu(), yr) < 1e-2, report("y", y.permute(0, 3, 1, 2).cpu(), yr)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    (yr * gy.float().permute(0, 3, 1, 2).cpu().double()).sum().backward()
+    assert rel_err(x.grad.cpu(), xr.grad) < 1e-3, report("dframes", x.grad.cpu(), xr.grad)
+    assert rel_err(conv.weight.grad.cpu(), wr.grad) < 1e-3, report("dW", conv.weight.grad.cpu(), wr.grad)
+    assert rel_err(conv.bias.grad.cpu(), br.grad) < 1e-3, report("db", conv.bias.grad.cpu(), br.grad)
+
+
+def test_frameconv_loud_errors(cuda_device):
+    from plconv import functional as PF
+    conv = torch.nn.Conv2d(1, 32, 3, stride=2, padding=1).to(cuda_device)
+    with pytest.raises(RuntimeError, match="contiguous fp32"):
+        PF.frameconv(torch.zeros(2, 1, 8, 8, device=cuda_device, dtype=torch.bfloat16), conv)
+    with pytest.raises(RuntimeError):
+        PF.frameconv(torch.zeros(2, 1, 8, 8), conv)                                        # CPU tensor
+    assert not PF.frameconv_supported(torch.nn.Conv2d(8, 32, 3, stride=2, padding=1))      # too many channels
+    assert not PF.frameconv_supported(torch.nn.Conv2d(1, 24, 3, stride=2, padding=1))      # Cout / 8 not a power of two
+    assert not PF.frameconv_supported(torch.nn.Conv2d(1, 32, 5, stride=2, padding=2))      # 5x5
+
+
 def test_convnd_loud_errors(cuda_device):
     from plconv import functional as PF
     conv = torch.nn.Conv2d(8, 8, 4, stride=2, padding=2).to(cuda_device)          # even kernel
