@@ -68,6 +68,10 @@ def parse():
                          "strong scaling); infer = configs[1]; radar = configs[3] inference; radar-train = configs[3] "
                          "training (batch 16 per GPU, weak scaling)")
     ap.add_argument("--no-gan", action="store_true", help="train workloads: generator-only L1 training, no discriminator")
+    ap.add_argument("--global-batch", type=int, default=None,
+                    help="train: override the global batch (e.g. 8 on one GPU = the per-GPU shard of the 8-GPU run)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="train: issue every launch from Python instead of replaying the step as one CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=None, help="sequences per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -148,7 +152,10 @@ def committed_traffic(key: str):
 
 # ================================================================================= training workloads (cfg3 / cfg4)
 def train_cfg(args):
-    return RADAR_TRAIN if args.workload == "radar-train" else TRAIN
+    cfg = RADAR_TRAIN if args.workload == "radar-train" else TRAIN
+    if args.global_batch and cfg["scaling"] == "strong":
+        cfg = dict(cfg, global_batch=args.global_batch)
+    return cfg
 
 
 def train_batch_sizes(cfg, world):
@@ -328,6 +335,11 @@ def run_train(args):
         return float(t.item())
 
     K, Wm = args.steps, max(args.warmup, 3)
+    eager_step = step
+    if not args.no_graph:
+        # the whole step (D step + G step: forward, BPTT, NCCL all-reduce, clip, Adam) recorded once, replayed per batch
+        from plconv.training import GraphedStep
+        step = GraphedStep(eager_step, (frames_dev, target_dev), warmup=3)
     # ---------------- device-resident region (value)
     for _ in range(Wm):
         step(frames_dev, target_dev)
@@ -375,7 +387,7 @@ def run_train(args):
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     for _ in range(n_prof):
-        step(frames_dev, target_dev)
+        eager_step(frames_dev, target_dev)         # eager: same kernels as the graph, each bracketed by an event pair
     p1.record()
     torch.cuda.synchronize()
     rec = _lib.timing_collect()
@@ -454,6 +466,8 @@ def run_train(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": train_config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": e2e_ms / K, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
+            "launch_mode": "eager (one Python -> C ABI call per kernel)" if args.no_graph else
+                           "the whole step replayed as one CUDA graph (plconv.training.GraphedStep)",
             "gpu_launches": int(round(K * launches_per_step)),
             "gpu_launches_per_step": launches_per_step,
             "loss": last_loss,

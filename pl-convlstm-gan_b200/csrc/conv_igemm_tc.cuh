@@ -248,6 +248,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<kCta>(tmem_ptr_s, Cfg::kTmemCols);
+  // Everything above touched only shared memory, TMEM and kernel parameters: under programmatic dependent launch it
+  // overlaps the tail of the preceding kernel of the stream.  From here on global memory is read and written.
+  pdl_launch_dependents();
+  pdl_wait();
   if (EPI != EPI_PLAIN) {
     // forward: sigmoid(x + b) = 0.5 * tanh(0.5 * x + 0.5 * b) + 0.5 -> stage HALF the bias of the i, f, o gates so the
     // bias add folds into the FFMA that scales the pre-activation

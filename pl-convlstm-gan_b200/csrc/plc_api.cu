@@ -440,6 +440,16 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ s
 // cta_group choice: a CTA pair (cta_group::2) halves the per-SM weight-tile traffic and wins once there are
 // enough 128-pixel tiles to keep all 74 pairs busy; tiny problems keep 148 independent CTAs.
 // PLC_CTA_GROUP=1|2 overrides (used by the benchmarks to A/B the two paths).
+// Programmatic dependent launch for the persistent tensor-core kernels (PLC_PDL=0 turns it off for A/B runs): consecutive
+// cell-step kernels of a rollout form a dependent chain, so without it every launch pays grid drain + launch latency +
+// prologue back to back (~19 us fixed per launch measured at the 8-GPU shard of cfg3, where a cell kernel is ~55 us).
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PLC_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 std::atomic<int> g_cta_override{0};   // plc_debug_set_cta_group (process-wide on purpose: backward runs on autograd threads)
 int pick_cta_group(int num_m_tiles) {
   static const int forced = [] {
@@ -486,13 +496,15 @@ int launch_conv_tc_inst(const plc::ConvTcParams& p_in, const CUtensorMap& a0, co
   cfg.blockDim = dim3(plc::conv_tc_threads<EPI>());
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTA;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   LaunchTimer timer(kind, st, flops);
   static const plc::GateMaps no_gate_maps{};     // only the gate-gradient epilogue reads them
   PLC_CUDA(cudaLaunchKernelEx(&cfg, kfn, p, a0, a1, b, o0, o1, gm ? *gm : no_gate_maps));
@@ -699,11 +711,13 @@ int launch_wgrad_tc_shape(const WgradShape* d, const void* x, const void* h_prev
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = plc::kW2SmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     PLC_CUDA(cudaLaunchKernelEx(&cfg, plc::wgrad_tc_kernel2, p, tz, t0, t1));
   } else {
     PLC_CUDA(set_smem_once<TagW1>(plc::wgrad_tc_kernel, plc::kWgSmemBytes));

@@ -176,6 +176,12 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // ---------------------------------------------------------------- cluster
+// Programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization): the next kernel of
+// the stream may be scheduled onto SMs as this grid's CTAs retire and run its prologue (barrier init, TMEM allocation,
+// descriptor prefetch) there; it must execute pdl_wait() before touching any global memory, which returns once the
+// preceding grid has completed and its writes are visible.  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

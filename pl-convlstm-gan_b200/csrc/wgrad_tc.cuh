@@ -301,6 +301,8 @@ wgrad_tc_kernel2(const WgradTcParams p, const __grid_constant__ CUtensorMap tmap
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<2>(tmem_ptr_s, kWgTmemCols);
+  pdl_launch_dependents();     // prologue above overlaps the preceding kernel's tail (see plc_ptx.cuh)
+  pdl_wait();
   const bool do_db = (p.db != nullptr) && (group == 0);
   if (do_db) {
     for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_s)[i] = 0x3F803F80u;

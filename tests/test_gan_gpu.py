@@ -257,3 +257,41 @@ def test_gan_losses_and_one_step_vs_eager_spec(cuda_device):
     for q0, q in zip(before, list(gen.parameters()) + list(disc.parameters())):
         assert torch.isfinite(q).all() and not torch.equal(q0, q)
     assert float(step.g.skipped_dev) == 0.0 and float(step.d.skipped_dev) == 0.0
+
+
+def test_graphed_gan_step_matches_eager(cuda_device):
+    """plconv.training.GraphedStep: the whole GAN step recorded as ONE CUDA graph (2 eager warm-up steps + capture +
+    3 replays) vs 5 eager steps from the same seeds on the same batch: every step's generator loss within 2e-3 relative
+    and every parameter of G and D within 2e-3 absolute (Adam steps of 5e-4 / 2e-4; the only non-determinism is the
+    order of the fp32 `red.global.add` reductions in the weight-gradient kernels).  Also: an eager forward after the
+    replays must see the CURRENT weights (packed-weight caches are invalidated by the replay)."""
+    import plconv
+    from plconv.training import GraphedStep
+    b, t_in, t_out, hh, ww, hd = 2, 3, 3, 32, 32, [16, 16]
+    torch.manual_seed(9)
+    frames = torch.relu(torch.randn(b, t_in, 1, hh, ww, device=cuda_device) + 0.3)
+    target = torch.relu(torch.randn(b, t_out, 1, hh, ww, device=cuda_device) + 0.3)
+
+    def make():
+        torch.manual_seed(21)
+        gen = plconv.NowcastGenerator(1, hd, 3, t_in, t_out, "bf16").to(cuda_device)
+        disc = plconv.Discriminator().to(cuda_device)
+        return gen, disc, plconv.GanTrainStep(gen, disc, lambda_adv=0.05)
+
+    gen_e, disc_e, step_e = make()
+    eager_losses = [float(step_e(frames, target)) for _ in range(5)]
+    gen_g, disc_g, step_g = make()
+    graphed = GraphedStep(step_g, (frames, target), warmup=2)
+    assert graphed.eager_steps == 2
+    graph_losses = [float(graphed(frames, target).clone()) for _ in range(3)]
+    print("eager losses", eager_losses, "graph replays", graph_losses)
+    for a, g in zip(eager_losses[2:], graph_losses):
+        assert abs(a - g) < 2e-3 * abs(a), (eager_losses, graph_losses)
+    for (k, pe), pg in zip(list(gen_e.named_parameters()) + list(disc_e.named_parameters()),
+                           list(gen_g.parameters()) + list(disc_g.parameters())):
+        assert torch.isfinite(pg).all()
+        assert (pe - pg).abs().max() < 2e-3, (k, float((pe - pg).abs().max()))
+    with torch.no_grad():                              # stale packed weights would reproduce the pre-step prediction
+        ye, yg = gen_e(frames), gen_g(frames)
+    assert rel_err(yg.cpu(), ye.cpu()) < 2e-2, report("post-replay forward", yg.cpu(), ye.cpu())
+    assert float(step_g.g.skipped_dev) == 0.0
