@@ -24,7 +24,7 @@ def test_reference_arm_json_line():
     # both arms must print the SAME config object (the driver compares them): rebuild ours without a GPU
     sys.path.insert(0, ROOT)
     import bench
-    ns = type("A", (), {"workload": "train", "no_gan": False})()
+    ns = type("A", (), {"workload": "train", "no_gan": False, "global_batch": None})()
     assert d["config"] == bench.train_config_dict(ns, 1)
 
 
