@@ -471,9 +471,29 @@ def run_train(args):
             "gpu_launches": int(round(K * launches_per_step)),
             "gpu_launches_per_step": launches_per_step,
             "loss": last_loss,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks}))
-    if world > 1:
-        dist.destroy_process_group()
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks}), flush=True)
+    shutdown(step, world, dev)
+
+
+def shutdown(step, world, dev):
+    """Orderly exit of a multi-rank run: the JSON line is already out.  Release the CUDA graph (it holds captured NCCL
+    kernels) before the process group goes away, and never let a stuck communicator teardown keep the job alive."""
+    import torch
+    import torch.distributed as dist
+    if world <= 1:
+        return
+    watchdog = threading.Timer(45.0, lambda: os._exit(0))     # the measurement is complete; do not hang the launcher
+    watchdog.daemon = True
+    watchdog.start()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    if hasattr(step, "close"):
+        step.close()
+    torch.cuda.synchronize(dev)
+    dist.destroy_process_group()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)      # skip interpreter teardown (NCCL watchdog threads, graph pools): everything is reported and released
 
 
 # ================================================================================= inference workloads (cfg2 / cfg4)

@@ -107,3 +107,13 @@ class GraphedStep:
         # the replay repacked and then updated the weights behind the Python-side caches' backs
         _lib.invalidate_packed_weights()
         return self.static_out
+
+    def close(self) -> None:
+        """Drop the recorded graph (and with it the captured NCCL launches).  Call before
+        ``torch.distributed.destroy_process_group()``: tearing a communicator down while a live graph still holds its
+        kernels can block in NCCL's destroy path."""
+        if self.graph is not None:
+            dev = self.static_in[0].device
+            torch.cuda.synchronize(dev)
+            self.graph.reset()
+            self.graph = None
