@@ -406,7 +406,7 @@ def run_train(args):
         kernels = {}
         for kind, d in sorted(kinds.items(), key=lambda kv: -kv[1]["ms"]):
             kernels[kind] = {"launches_per_step": d["launches"] / n_prof, "avg_launch_us": d["ms"] / d["launches"] * 1e3,
-                             "share_of_step": d["ms"] / prof_ms,
+                             "share_of_step": (d["ms"] / n_prof) / (ms / K),
                              "executed_tflops": (d["flops"] / (d["ms"] * 1e-3) / 1e12) if d["flops"] else None}
         launches_per_step = len(rec) / n_prof
         # dominant call: the BPTT cell step = the three kernels of one plc_cell_bwd (gate recompute, dgrad, wgrad);
@@ -428,10 +428,11 @@ def run_train(args):
                 "achieved": ach, "peak": peak_sus, "unit": "TFLOP/s", "frac": ach / peak_sus,
                 "frac_of_burst": ach / peak_burst, "peak_burst": peak_burst, "peak_source": peak_src,
                 "flops_per_launch": algo / calls, "avg_launch_us": bwd_ms / calls * 1e3, "launches_timed": calls,
-                "share_of_step": bwd_ms / prof_ms,
+                "share_of_step": (bwd_ms / n_prof) / (ms / K),
                 "note": "algorithmic FLOPs = dgrad + wgrad of the call (2F at Cin = Ch); the gate-recompute MMAs it also "
-                        "executes are not counted.  Per-launch CUDA events from a separate pass of "
-                        f"{n_prof} steps (never inside a reported region); peak = sustained bf16 matmul (the kernels run "
+                        "executes are not counted.  Per-launch CUDA events from a separate eager pass of "
+                        f"{n_prof} steps (never inside a reported region); share_of_step = the kind's event time per "
+                        "step / the reported (graph-replayed) step time; peak = sustained bf16 matmul (the kernels run "
                         "inside a multi-second step), burst alongside",
                 "traffic": committed_traffic("cell_bwd_cfg3_dram_bytes_per_call"),
                 "cell_fwd": None if not fwd else {

@@ -38,11 +38,16 @@ print(f"wgrad leaders {len(lead)}: MMA warp total {lead[:,0].mean():.0f} cyc, bl
       f"per block {lead[:,0].mean()/lead[:,3].mean():.0f}, wait-full {100*lead[:,2].mean()/lead[:,0].mean():.1f}%")
 ep = p[p[:, 5] > 0]
 print(f"epilogue: wait-acc {ep[:,4].mean():.0f} cyc, flush {ep[:,5].mean():.0f} cyc")
-# per output-column group (pair index = blockIdx / 2; s = pair % S, group = (pair / S) % num_groups; S = 24 and
-# 3 groups at the cfg2 shape): group 0 also carries the bias-gradient MMA
+# per output-column group (pair index = blockIdx / 2; s = pair % S, group = (pair / S) % num_groups); group 0 also
+# carries the bias-gradient MMA.  PLC_WGRAD_GB=4 forces 4-block groups (N = 256 MMAs only, last group N = 128).
+CB = k * k * ((cin + 63) // 64 + (ch + 63) // 64)
+GB = int(os.environ.get("PLC_WGRAD_GB", "0")) or 2 * ((-(-CB // (-(-CB // 6))) + 1) // 2)
+groups = -(-CB // GB)
+S = max(1, 74 // groups)
+print(f"CB {CB} GB {GB} groups {groups} S {S}")
 idx = torch.arange(148)[p[:, 3] > 0] // 2
-for g in range(3):
-    sel = lead[(idx // 24) % 3 == g]
+for g in range(groups):
+    sel = lead[(idx // S) % groups == g]
     if len(sel):
         print(f"  group {g}: {len(sel)} pairs, MMA warp total {sel[:,0].mean():.0f} cyc (min {sel[:,0].min():.0f}, max "
               f"{sel[:,0].max():.0f}), per block {sel[:,0].mean()/sel[:,3].mean():.0f}, wait-full "

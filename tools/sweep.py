@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4]: ConvLSTM cell microbench sweep (hidden 32-256, kernel 3/5, H/W 64-512), forward and
-BPTT cell step, CUDA events (median of 10 after 3 warm-ups), fraction of the measured bf16 peak.
-Writes a markdown table to stdout.   python tools/sweep.py [--quick]"""
+BPTT cell step, CUDA events (median of 10 after 3 warm-ups), fraction of the measured bf16 peak -- next to the
+REFERENCE cell (convlstm.py:16-28 restated inline: cat -> conv2d -> split -> sigmoid/tanh -> update) run eagerly on the
+same GPU (fp32 parameters, torch's default flags = cuDNN with TF32 convolutions allowed, autograd backward) and on this
+box's CPU cores (one sample, scaled linearly to the batch; only where a step stays under ~2 s).  Reported baselines only.
+Writes a markdown table to stdout.   python tools/sweep.py [--quick] [--no-cpu]"""
 import json
 import os
 import sys
@@ -15,13 +18,60 @@ from plconv import functional as F  # noqa: E402
 from microbench import time_fn  # noqa: E402
 
 
+def ref_cell(x, h, c, w, b):
+    """The reference's ConvLSTMCell.forward (src/models/convlstm.py:16-28), NCHW fp32."""
+    k = w.shape[-1]
+    z = torch.nn.functional.conv2d(torch.cat([x, h], 1), w, b, padding=k // 2)
+    i, f, o, g = torch.split(z, h.shape[1], 1)
+    i, f, o, g = torch.sigmoid(i), torch.sigmoid(f), torch.sigmoid(o), torch.tanh(g)
+    c2 = f * c + i * g
+    return o * torch.tanh(c2), c2
+
+
+def ref_times(B, ch, hw, k, dev, iters=5, warm=2):
+    """(fwd us, fwd+bwd us) of the eager reference cell on `dev`."""
+    import time
+    w = (torch.randn(4 * ch, 2 * ch, k, k, device=dev) * 0.02).requires_grad_()
+    b = torch.zeros(4 * ch, device=dev, requires_grad=True)
+    x = torch.randn(B, ch, hw, hw, device=dev, requires_grad=True)
+    h = (torch.randn(B, ch, hw, hw, device=dev) * 0.5).requires_grad_()
+    c = torch.randn(B, ch, hw, hw, device=dev, requires_grad=True)
+    gh, gc = torch.randn(B, ch, hw, hw, device=dev), torch.randn(B, ch, hw, hw, device=dev)
+
+    def fwd():
+        with torch.no_grad():
+            ref_cell(x, h, c, w, b)
+
+    def both():
+        for t in (w, b, x, h, c):
+            t.grad = None
+        h2, c2 = ref_cell(x, h, c, w, b)
+        torch.autograd.backward([h2, c2], [gh, gc])
+
+    if dev.type == "cuda":
+        return time_fn(fwd, iters=iters, warm=warm)[0], time_fn(both, iters=iters, warm=warm)[0]
+    out = []
+    for fn in (fwd, both):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            fn()
+        out.append((time.perf_counter() - t0) / 2 * 1e6)
+    return tuple(out)
+
+
 def main():
     quick = "--quick" in sys.argv
     dev = torch.device("cuda:0")
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peaks))["bf16_tflops_sustained"] if os.path.exists(peaks) else 1590.0
-    print(f"| B | Cin=Ch | HxW | k | fwd us | fwd TFLOP/s | frac of {peak:.0f} | bwd us | fwd+bwd TFLOP/s (3F) | frac |")
-    print("|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    print(f"reference columns: eager convlstm.py cell, fp32; GPU = same B200 (cuDNN, TF32 convs allowed = torch default), "
+          f"CPU = {cores} cores, 1 sample x B (linear)\n")
+    print(f"| B | Cin=Ch | HxW | k | fwd us | fwd TFLOP/s | frac of {peak:.0f} | bwd us | fwd+bwd TFLOP/s (3F) | frac | "
+          f"ref GPU fwd us | ref GPU fwd+bwd us | speed-up fwd / fwd+bwd | ref CPU fwd+bwd ms |")
+    print("|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|")
     chs = [32, 64, 128, 256]
     sizes = [64, 128, 256] if quick else [64, 128, 256, 512]
     for ch in chs:
@@ -51,10 +101,20 @@ def main():
                                                          dh_prev=dhp, dc_prev=dcp), iters=10, warm=3)
                 tf_f = flops / fwd / 1e6
                 tf_t = 3 * flops / (fwd + bwd) / 1e6
-                print(f"| {B} | {ch} | {hw}x{hw} | {k} | {fwd:.1f} | {tf_f:.0f} | {tf_f / peak:.2f} | {bwd:.1f} | "
-                      f"{tf_t:.0f} | {tf_t / peak:.2f} |", flush=True)
-                del x, h, c, h2, c2, dh, dc, ws, dx, dhp, dcp
+                del x, h, c, h2, c2, dh, dc, ws, dx, dhp, dcp, img
                 torch.cuda.empty_cache()
+                try:
+                    rf, rb = ref_times(B, ch, hw, k, dev)
+                    ref_s = f"{rf:.0f} | {rb:.0f} | {rf / fwd:.1f}x / {rb / (fwd + bwd):.1f}x"
+                except torch.OutOfMemoryError:
+                    ref_s = "OOM | OOM | -"
+                torch.cuda.empty_cache()
+                cpu_s = "-"
+                if "--no-cpu" not in sys.argv and 3 * flops / B < 0.6e12:      # ~2 s per step at ~0.3 TFLOP/s
+                    _, cb = ref_times(1, ch, hw, k, torch.device("cpu"))
+                    cpu_s = f"{cb * B / 1e3:.0f}"
+                print(f"| {B} | {ch} | {hw}x{hw} | {k} | {fwd:.1f} | {tf_f:.0f} | {tf_f / peak:.2f} | {bwd:.1f} | "
+                      f"{tf_t:.0f} | {tf_t / peak:.2f} | {ref_s} | {cpu_s} |", flush=True)
 
 
 if __name__ == "__main__":
