@@ -423,8 +423,9 @@ def run_train(args):
             step_tf = 3.0 * cell_flops_step / (ms / K * 1e-3) / 1e12
             roofline = {
                 "bound": "tensor",
-                "kernel": "BPTT cell step = plc_cell_bwd: conv_igemm_tc_kernel<256,EPI_LSTM_BWD_GATES> (gate recompute "
-                          "+ dZ) + conv_igemm_tc_kernel<128,EPI_PLAIN> (dgrad) + wgrad_tc_kernel2 (dW, db)",
+                "kernel": "BPTT cell step = plc_cell_bwd[_saved]: conv_igemm_tc_kernel<256,EPI_LSTM_BWD_GATES> (gate "
+                          "gradients dZ: from saved gates when `bptt_gates` says so, else gate recompute) + "
+                          "conv_igemm_tc_kernel<128,EPI_PLAIN> (dgrad) + wgrad_tc_kernel2 (dW, db)",
                 "achieved": ach, "peak": peak_sus, "unit": "TFLOP/s", "frac": ach / peak_sus,
                 "frac_of_burst": ach / peak_burst, "peak_burst": peak_burst, "peak_source": peak_src,
                 "flops_per_launch": algo / calls, "avg_launch_us": bwd_ms / calls * 1e3, "launches_timed": calls,
@@ -460,6 +461,8 @@ def run_train(args):
                                   f"step); oracle port = the reference's ATen CPU ops, fp32 autograd"}
 
     if rank == 0:
+        from plconv import nn as _pnn
+        saved_bytes = _pnn.LAST_SAVED_GATES_BYTES
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         print(json.dumps({
             "metric": train_metric(args), "value": value, "unit": "sequences/s", "n_gpus": world, "steps": K,
@@ -467,6 +470,9 @@ def run_train(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": train_config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": "sequences/s", "ms_per_step": e2e_ms / K, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
+            "bptt_gates": (f"saved by the forward pass ({saved_bytes / 2**30:.1f} GiB per rollout): the backward gate kernel "
+                           "streams them instead of re-running the gate contraction" if saved_bytes else
+                           "recomputed in the backward gate kernel (no extra memory)"),
             "launch_mode": "eager (one Python -> C ABI call per kernel)" if args.no_graph else
                            "the whole step replayed as one CUDA graph (plconv.training.GraphedStep)",
             "gpu_launches": int(round(K * launches_per_step)),

@@ -118,6 +118,27 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
                  const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc, float* db_acc,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- saved-gates BPTT (optional; trades HBM for tensor time and power) -----------------------------------------
+ * The reference's autograd keeps the activated gates of every step (convlstm.py:21-24 outputs are saved tensors);
+ * plc_cell_bwd recomputes them instead (one extra gate contraction per step, no extra memory).  Where memory allows,
+ * the forward pass can keep them -- bf16, 8 bytes per hidden element per step -- and the backward gate-gradient kernel
+ * then runs WITHOUT its mainloop: it streams the saved gates (bulk copies) next to c_prev / dc_next / dh / dh2 and is
+ * HBM-bound.  On a power-capped B200 that removes a quarter of the cell path's tensor-core energy.
+ *   plc_saved_gates_bytes: size of the per-step buffer, or 0 when the descriptor has no saved-gates form (fp32 mode,
+ *     Ch % 64 != 0) -- then use plc_cell_fwd / plc_cell_bwd.  The layout is private to the library (tile-major,
+ *     see ConvTcParams::gates_saved) and tied to the descriptor: pass the same descriptor to both calls.
+ *   plc_cell_fwd_save: plc_cell_fwd that also fills `gates_saved` (h_prev = c_prev = NULL zero-state form allowed).
+ *   plc_cell_bwd_saved: plc_cell_bwd without w_packed_fwd / bias, reading `gates_saved` of the same step.  Gradients
+ *     differ from plc_cell_bwd only by the bf16 rounding of the stored gates (inside the 1e-2 bf16 budget).        */
+size_t plc_saved_gates_bytes(const PlcCellDesc* d);
+int plc_cell_fwd_save(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                      const void* w_packed_fwd, const float* bias, void* h_out, void* c_out, void* gates_saved,
+                      void* stream);
+int plc_cell_bwd_saved(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                       const void* gates_saved, const void* w_packed_dgrad, const void* dh, const void* dh2,
+                       const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc, float* db_acc,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- generic "same" convolution on the same tensor-core core (bf16; SURVEY.md section 8f "next-1") ----------------
  * Replaces the plain nn.Conv2d layers of the reference Generator body: UpsampleBlock conv + PixelShuffle(2) + ReLU
  * (generator.py:10-28), post_process convs (generator.py:67-71), attention convs (attention.py:6-10).
@@ -145,6 +166,14 @@ size_t plc_conv_wgrad_acc_bytes(const PlcConvDesc* d);
 int plc_conv_wgrad_unpack(const PlcConvDesc* d, const float* dW_acc, float* dW_oihw, void* stream);
 int plc_conv_bwd(const PlcConvDesc* d, const void* x, const void* dz, const void* w_packed_dgrad, void* dx,
                  float* dW_acc, float* db_acc, void* stream);
+/* Weight gradient of a NARROW-input layer (the front-end init_conv of generator.py:50-55,166-168: 1 rain + 2 coordinate
+ * channels): with cin_true * k * k <= 32 the whole receptive field of a pixel fits ONE 32-column im2col row, and the
+ * reduction over pixels becomes a plain [Cout x 32] GEMM instead of k*k column blocks that are 5/8 zero padding.
+ * plc_conv_im2col_narrow: x [B,H,W,8] bf16 (channels >= cin_true are zero) -> col [B,H,W,32] bf16,
+ * col[pixel][tap * cin_true + c] = x[pixel + tap offset][c], zero outside the image.  The caller then runs
+ * plc_conv_bwd (dx = NULL) with a k = 1, Cin = 32 descriptor on `col` and maps dW1[Cout][tap * cin_true + c] back
+ * to [Cout][c][ky][kx].  `d` describes the ORIGINAL layer (Cin = 8, k).                                          */
+int plc_conv_im2col_narrow(const PlcConvDesc* d, int cin_true, const void* x, void* col, void* stream);
 
 /* ---- strided 2-D / 3-D convolution on the same core (bf16; the discriminator of the GAN training step) ----------
  * No reference counterpart (the reference has no discriminator: SURVEY.md section 0); the eager spec is

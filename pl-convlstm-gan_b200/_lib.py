@@ -66,10 +66,14 @@ SIGNATURES = {
     "plc_conv_wgrad_acc_bytes": (_sz, [_cp]),
     "plc_conv_wgrad_unpack": (_int, [_cp, _vp, _vp, _vp]),
     "plc_cell_bwd": (_int, [_dp] + [_vp] * 15 + [_sz, _vp]),
+    "plc_saved_gates_bytes": (_sz, [_dp]),
+    "plc_cell_fwd_save": (_int, [_dp] + [_vp] * 9),
+    "plc_cell_bwd_saved": (_int, [_dp] + [_vp] * 14 + [_sz, _vp]),
     "plc_conv_packed_weight_bytes": (_sz, [_cp, _int]),
     "plc_conv_pack_weight": (_int, [_cp, _int, _vp, _vp, _vp, _vp, _vp]),
     "plc_conv_fwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "plc_conv_grad_mask": (_int, [_cp, _vp, _vp, _vp, _vp]),
+    "plc_conv_im2col_narrow": (_int, [_cp, _int, _vp, _vp, _vp]),
     "plc_conv_bwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plc_convnd_out_shape": (_int, [_np, _ip, _ip, _ip]),
     "plc_convnd_packed_weight_bytes": (_sz, [_np, _int]),

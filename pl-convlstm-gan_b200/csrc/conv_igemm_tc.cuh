@@ -74,6 +74,12 @@ struct ConvTcParams {
   float* c_out;              // [M, Ch] fp32                       (FWD)
   __nv_bfloat16* h_out;      // [M, Ch] bf16                       (FWD)
   __nv_bfloat16* gates_out;  // [M, 4Ch] bf16 or nullptr           (FWD)
+  // saved-gates mode (N_TILE = 256): the forward pass keeps the ACTIVATED gates so that BPTT can skip the gate
+  // recompute contraction.  Private tile-major layout, 16 bytes per (tile, gate, 8-channel granule, tile row):
+  //   gates_saved[(((m_tile * num_n_tiles + n_tile) * 4 + gate) * 8 + granule) * 128 + row]   (uint4 = 8 bf16)
+  // -> a forward epilogue warp (32 consecutive tile rows) stores 512 contiguous bytes per instruction, and one
+  // 16-channel round of a gate (2 granules) is ONE contiguous 4 KB run for the backward kernel's bulk copies.
+  uint4* gates_saved;        // FWD: written; BWD_GATES: read instead of running the mainloop
   const __nv_bfloat16* dh;   // [M, Ch] bf16                       (BWD_GATES)
   const __nv_bfloat16* dh2;  // [M, Ch] bf16 or nullptr, added     (BWD_GATES)
   const float* dc_next;      // [M, Ch] fp32 or nullptr            (BWD_GATES)
@@ -89,6 +95,7 @@ struct ConvTcParams {
   int plain_tma;             // PLAIN: outputs leave through smem staging + TMA tensor stores (tmap_o0 / tmap_o1 valid;
                              // needs no shuffle and 64-channel-aligned out0 / out1); 0 = per-thread 16-byte stores
   unsigned long long* prof;  // debug: per-CTA cycle counters [gridDim][16] or nullptr (plc_debug_set_prof)
+  int exp_skip_mma;          // EXPERIMENT (PLC_EXP_SKIP_GATE_MMA=1, results are garbage): no operand loads, no MMAs
 };
 
 constexpr int kTileM = 128;
@@ -217,6 +224,9 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   uint64_t* gin_full = bars + 44;                  // [2] bwd gates: operand buffer filled by TMA
   uint64_t* gout_ready = bars + 46;                // [2] bwd gates: outputs written, buffer ready for the tensor stores
 
+  // saved-gates form of the gate-gradient kernel: no operand loads, no MMAs; the epilogue takes the activated gates the
+  // forward pass stored (bulk copies into the idle operand-pipeline region) instead of the accumulator
+  const bool saved = (EPI == EPI_LSTM_BWD_GATES) && p.gates_saved != nullptr;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int rank = (kCta == 2) ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader (issues the MMAs)
@@ -419,7 +429,8 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         }
       }
     };
-    if (p.patch) produce_patch();
+    if (p.exp_skip_mma || saved) {}
+    else if (p.patch) produce_patch();
     else if (p.kc == 64) produce(IntC<1>{});
     else if (p.kc == 32) produce(IntC<2>{});
     else produce(IntC<4>{});
@@ -437,7 +448,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
     uint32_t stage = 0, phase = 0, bstage = 0, bphase = 0;
     int it = 0;
     long long t_empty = 0, t_full = 0, t_patch = 0, t_mma = 0, t0 = clock64();
-    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+    for (int tile = tile0; tile < num_tiles && !saved; tile += tile_step, ++it) {
       const int as = it % Cfg::kAccStages;
       const uint32_t aphase = (it / Cfg::kAccStages) & 1;
       long long ta = (kProfEnabled && p.prof) ? clock64() : 0;
@@ -445,6 +456,14 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       tc_fence_after();
       if ((kProfEnabled && p.prof)) t_empty += clock64() - ta;
       const uint32_t d_tmem = tmem_base + as * N_TILE;
+      if (p.exp_skip_mma) {
+        if (elect_one()) {
+          if constexpr (kCta == 1) umma_commit<1>(&tmem_full[as]);
+          else umma_commit_mc2(&tmem_full[as], 0b11);
+        }
+        __syncwarp();
+        continue;
+      }
       if (p.patch) {
         // shifted views: tap (ky, kx) of the tile = the patch read from pixel row ky, pixel kx on (start address
         // + (ky * (tw+2p) + kx) * 128 B), 8-pixel groups (tile rows) one patch row = (tw+2p) * 128 B apart
@@ -579,7 +598,8 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       const uint32_t so = smem_u32(stage_out), inf_base = smem_u32(gin_full);
       const int my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tile_step - 1) / tile_step : 0;
       const int rounds = NR * my_tiles;
-      const uint32_t tx = kF + kH + (p.dc_next ? kF : 0u) + (p.dh2 ? kH : 0u);
+      const uint32_t tx = kF + kH + (p.dc_next ? kF : 0u) + (p.dh2 ? kH : 0u) + (saved ? 4u * 4096u : 0u);
+      const uint32_t gsb = smem_u32(smem_a);               // saved gates of a round: 2 x [4 gates][2 granules][128 rows][16 B]
       auto load_round = [&](int R) {
         if (R >= rounds) return;
         int n_tile, b, y0, x0;
@@ -592,6 +612,14 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           if (p.dc_next) tma_load_4d_s(buf + kF, &gmaps.dc_next, bar, cb, x0, y0, b);
           tma_load_4d_s(buf + 2 * kF, &gmaps.dh, bar, cb, x0, y0, b);
           if (p.dh2) tma_load_4d_s(buf + 2 * kF + kH, &gmaps.dh2, bar, cb, x0, y0, b);
+          if (saved) {
+            const int m_tile = fast_div(tile0 + (R / NR) * tile_step, p.num_n_tiles, p.div_n_tiles) * kCta + rank;
+            const uint4* gsrc = p.gates_saved + (static_cast<size_t>(m_tile) * p.num_n_tiles + n_tile) * (4 * 8 * 128) +
+                                (R % NR) * (2 * 128);
+#pragma unroll
+            for (int gate = 0; gate < 4; ++gate)
+              bulk_load_1d_s(gsb + (R & 1) * 16384 + gate * 4096, gsrc + gate * (8 * 128), 4096, bar);
+          }
         }
         __syncwarp();
       };
@@ -671,8 +699,10 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       }
       long long te = ((kProfEnabled && p.prof) && warp == 4) ? clock64() : 0;
       if ((kProfEnabled && p.prof) && warp == 4 && lane == 0) pa_pre += te - tTop;     // decode + operand prefetch issue
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
+      if (!saved) {
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+      }
       if ((kProfEnabled && p.prof) && warp == 4 && lane == 0) {
         const long long now = clock64();
         pa_wait += now - te;                    // epilogue warp 4: waiting for an accumulator
@@ -763,6 +793,21 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
               cdst[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
               *reinterpret_cast<uint4*>(p.h_out + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
             }
+            if (p.gates_saved) {
+              if constexpr (N_TILE == 256) {
+                const int m_tile = fast_div(tile, p.num_n_tiles, p.div_n_tiles) * kCta + rank;
+                uint4* gs = p.gates_saved + (static_cast<size_t>(m_tile) * p.num_n_tiles + n_tile) * (4 * 8 * 128) +
+                            g * 128 + row;
+#pragma unroll
+                for (int gate = 0; gate < 4; ++gate) {
+                  const uint32_t* src = gate == 0 ? vi : gate == 1 ? vf : gate == 2 ? vo : vg;
+                  gs[gate * (8 * 128)] = make_uint4(pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1])),
+                                                    pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3])),
+                                                    pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5])),
+                                                    pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7])));
+                }
+              }
+            }
             if (p.gates_out) {
               __nv_bfloat16* gbase = p.gates_out + pix * (4 * p.Ch) + chb;
 #pragma unroll
@@ -840,13 +885,20 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
             const uint32_t gl = half * GPR + j;     // granule within the round
             const int g = r * GR + gl;              // granule within the 64-channel slice: 0..7
             uint32_t vi[8], vf[8], vo[8], vg[8];
-            tmem_ld8(t_acc + 0 * CH_TILE + g * 8, vi);
-            tmem_ld8(t_acc + 1 * CH_TILE + g * 8, vf);
-            tmem_ld8(t_acc + 2 * CH_TILE + g * 8, vo);
-            tmem_ld8(t_acc + 3 * CH_TILE + g * 8, vg);
+            uint4 sg[4];                            // saved mode: activated gates i, f, o, g of this granule (8 x bf16 each)
+            if (!saved) {
+              tmem_ld8(t_acc + 0 * CH_TILE + g * 8, vi);
+              tmem_ld8(t_acc + 1 * CH_TILE + g * 8, vf);
+              tmem_ld8(t_acc + 2 * CH_TILE + g * 8, vo);
+              tmem_ld8(t_acc + 3 * CH_TILE + g * 8, vg);
+            } else {
+              const uint32_t ga = smem_u32(smem_a) + (r & 1) * 16384 + gl * 2048 + row * 16;
+#pragma unroll
+              for (int gate = 0; gate < 4; ++gate) sg[gate] = ld_shared_v4(ga + gate * 4096);
+            }
             const int chb = ch0 + g * 8;
             float bi[8], bf[8], bo[8], bg[8];
-            {
+            if (!saved) {
               const float4* s0 = reinterpret_cast<const float4*>(bias_s + 0 * p.Ch + chb);
               const float4* s1 = reinterpret_cast<const float4*>(bias_s + 1 * p.Ch + chb);
               const float4* s2 = reinterpret_cast<const float4*>(bias_s + 2 * p.Ch + chb);
@@ -866,9 +918,9 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
             const uint4 h1 = ld_shared_v4(za + 2 * kH);
             const uint4 h2 = p.dh2 ? ld_shared_v4(za + 3 * kH) : make_uint4(0u, 0u, 0u, 0u);
             long long tL = pw4 ? clock64() : 0;
-            tmem_ld_wait();
+            if (!saved) tmem_ld_wait();
             if (pw4) pa_ld += clock64() - tL;
-            if (idx == kLast) release();
+            if (idx == kLast && !saved) release();
             tL = pw4 ? clock64() : 0;
             {
               const float cp[8] = {__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z), __uint_as_float(c0.w),
@@ -889,10 +941,20 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                   const int jj = e + u;
-                  const float ig = sigmoid_fast(__uint_as_float(vi[jj]) + bi[jj]);
-                  const float fg = sigmoid_fast(__uint_as_float(vf[jj]) + bf[jj]);
-                  const float og = sigmoid_fast(__uint_as_float(vo[jj]) + bo[jj]);
-                  const float gt = tanh_fast(__uint_as_float(vg[jj]) + bg[jj]);
+                  float ig, fg, og, gt;
+                  if (!saved) {
+                    ig = sigmoid_fast(__uint_as_float(vi[jj]) + bi[jj]);
+                    fg = sigmoid_fast(__uint_as_float(vf[jj]) + bf[jj]);
+                    og = sigmoid_fast(__uint_as_float(vo[jj]) + bo[jj]);
+                    gt = tanh_fast(__uint_as_float(vg[jj]) + bg[jj]);
+                  } else {                       // bf16 -> fp32: the stored half is the high half of the float
+                    const uint32_t wi = (&sg[0].x)[e >> 1], wf = (&sg[1].x)[e >> 1];
+                    const uint32_t wo = (&sg[2].x)[e >> 1], wg = (&sg[3].x)[e >> 1];
+                    ig = __uint_as_float(u ? (wi & 0xffff0000u) : (wi << 16));
+                    fg = __uint_as_float(u ? (wf & 0xffff0000u) : (wf << 16));
+                    og = __uint_as_float(u ? (wo & 0xffff0000u) : (wo << 16));
+                    gt = __uint_as_float(u ? (wg & 0xffff0000u) : (wg << 16));
+                  }
                   const float c2 = fmaf(fg, cp[jj], ig * gt);
                   const float tc = tanh_fast(c2);
                   const float dh_ = dhp[u];
@@ -1152,7 +1214,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           }
         }
       }
-      if (!released) release();   // warps without a chunk for this tile shape
+      if (!released && !saved) release();   // warps without a chunk for this tile shape
     }
     if ((Cfg::kTmaStore && EPI != EPI_LSTM_BWD_GATES) || (EPI == EPI_PLAIN && p.plain_tma)) {
       if (warp == 4 && lane == 0) tma_store_wait_all();   // bulk stores complete before the CTA retires

@@ -423,6 +423,42 @@ __global__ void conv_grad_mask_vec_kernel(const uint4* __restrict__ y, const uin
   }
 }
 
+// im2col of a NARROW conv input for the weight gradient: x [B,H,W,Cp] bf16 (Cp = 8: the true channels c < C, zero
+// padded) -> col [B,H,W,32] bf16 with col[pix][tap * C + c] = x[pix + tap offset][c] (zero outside the image, zero
+// beyond k*k*C).  One thread per pixel: k*k 16-byte loads (neighbouring threads share them through L1), 64 bytes out.
+__global__ void im2col_narrow_kernel(const __nv_bfloat16* __restrict__ x, uint4* __restrict__ col, int B, int H, int W,
+                                     int C, int k) {
+  // per-column source (row offset, column offset, element offset); columns >= k*k*C read nothing
+  __shared__ int s_dy[32], s_dx[32], s_off[32];
+  const int pad = k / 2, ncol = k * k * C;
+  if (threadIdx.x < 32) {
+    const int i = threadIdx.x;
+    const int tap = i < ncol ? i / C : 0, c = i < ncol ? i - tap * C : 0;
+    const int ky = tap / k, kx = tap - ky * k;
+    s_dy[i] = i < ncol ? ky - pad : (1 << 20);       // far outside any image: the bounds test rejects it
+    s_dx[i] = kx - pad;
+    s_off[i] = ((ky - pad) * W + (kx - pad)) * 8 + c;
+  }
+  __syncthreads();
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < npix;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int xx = pix % W;
+    const int yy = (pix / W) % H;
+    const unsigned short* base = xs + pix * 8;
+    uint32_t out[16];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {          // static register indices
+      const unsigned sy = static_cast<unsigned>(yy + s_dy[i]), sx = static_cast<unsigned>(xx + s_dx[i]);
+      const unsigned short v = (sy < static_cast<unsigned>(H) && sx < static_cast<unsigned>(W)) ? __ldg(base + s_off[i]) : 0;
+      if (i & 1) out[i >> 1] |= static_cast<uint32_t>(v) << 16; else out[i >> 1] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) col[pix * 4 + i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+  }
+}
+
 // ------------------------------------------------------------------ layout kernels
 // src [B, Cs, H*W] fp32  ->  dst [B, H*W, Cd] bf16 (channels >= Cs zero-filled); 32x32 smem transpose
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cs,
@@ -820,11 +856,27 @@ int plc_cell_fwd_zero_state_ok(const PlcCellDesc* d) {
   return (d->k * d->k * kg.chunks0) % (64 / kg.kc) == 0;   // the x taps fill whole K stages
 }
 
-int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
-                 const void* w_packed_fwd, const float* bias, void* h_out, void* c_out, void* gates_out,
-                 void* stream) {
+// saved-gates mode: bf16 tensor-core mode with full 64-channel slices (N_TILE = 256, the TMA epilogues)
+static bool saved_gates_supported(const PlcCellDesc* d) {
+  return d->mode == PLC_MODE_BF16_TC && pick_ch_tile(d->Ch) == 64 && plc::tma_store_epilogue<256, plc::EPI_LSTM_FWD>() &&
+         plc::tma_store_epilogue<256, plc::EPI_LSTM_BWD_GATES>();
+}
+size_t plc_saved_gates_bytes(const PlcCellDesc* d) {
+  if (check_desc(d) != PLC_OK || !saved_gates_supported(d)) return 0;
+  TcGeom g;
+  plc::ConvTcParams p;
+  lstm_tc_setup(d, &g, &p, plc::EPI_LSTM_FWD);       // the forward kernel's tile geometry defines the layout
+  return static_cast<size_t>(p.num_m_tiles) * p.num_n_tiles * (4 * 8 * 128 * 16);
+}
+
+static int cell_fwd_impl(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                         const void* w_packed_fwd, const float* bias, void* h_out, void* c_out, void* gates_out,
+                         void* gates_saved, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
+  if (gates_saved && !saved_gates_supported(d))
+    return fail(PLC_ERR_UNSUPPORTED, "plc_cell_fwd_save: saved-gates mode needs bf16 mode and Ch %% 64 == 0 "
+                                     "(plc_saved_gates_bytes returns 0 for this descriptor)");
   // zero-initial-state form (generator.py:156-160 starts every sequence from h = c = 0): h_prev == c_prev == NULL
   const bool zero_state = !h_prev && !c_prev;
   if (zero_state && !plc_cell_fwd_zero_state_ok(d))
@@ -867,6 +919,7 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
   p.c_out = static_cast<float*>(c_out);
   p.h_out = static_cast<__nv_bfloat16*>(h_out);
   p.gates_out = static_cast<__nv_bfloat16*>(gates_out);
+  p.gates_saved = static_cast<uint4*>(gates_saved);
   const long full_kb = p.num_kb;               // K extent of the packed weight image (both sources)
   if (zero_state) {
     // h_prev == 0: its taps contribute nothing.  The packed K order is source-major, so the x part is the leading
@@ -895,22 +948,37 @@ int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
                                            conv_flops(d->B, d->H, d->W, (zero_state ? 0 : d->Ch) + d->Cin, 4 * d->Ch, d->k));
 }
 
+int plc_cell_fwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                 const void* w_packed_fwd, const float* bias, void* h_out, void* c_out, void* gates_out,
+                 void* stream) {
+  return cell_fwd_impl(d, x, h_prev, c_prev, w_packed_fwd, bias, h_out, c_out, gates_out, nullptr, stream);
+}
+int plc_cell_fwd_save(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                      const void* w_packed_fwd, const float* bias, void* h_out, void* c_out, void* gates_saved,
+                      void* stream) {
+  if (!gates_saved) return fail(PLC_ERR_NULL_ARG, "plc_cell_fwd_save: gates_saved is null");
+  if (!aligned16(gates_saved)) return fail(PLC_ERR_ALIGNMENT, "plc_cell_fwd_save: gates_saved must be 16-byte aligned");
+  return cell_fwd_impl(d, x, h_prev, c_prev, w_packed_fwd, bias, h_out, c_out, nullptr, gates_saved, stream);
+}
+
 size_t plc_bwd_workspace_bytes(const PlcCellDesc* d) {
   if (check_desc(d) != PLC_OK) return 0;
   const size_t m = static_cast<size_t>(d->B) * d->H * d->W;
   return m * 4 * d->Ch * (d->mode == PLC_MODE_FP32 ? 4 : 2);
 }
 
-int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
-                 const void* w_packed_fwd, const void* w_packed_dgrad, const float* bias, const void* dh,
-                 const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc,
-                 float* db_acc, void* workspace, size_t workspace_bytes, void* stream) {
+static int cell_bwd_impl(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                         const void* w_packed_fwd, const void* w_packed_dgrad, const float* bias, const void* gates_saved,
+                         const void* dh, const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev,
+                         float* dW_acc, float* db_acc, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
-  if ((d->Cin > 0 && !x) || !h_prev || !c_prev || !w_packed_fwd || !dh || !dc_prev || !workspace)
+  if ((d->Cin > 0 && !x) || !h_prev || !c_prev || (!w_packed_fwd && !gates_saved) || !dh || !dc_prev || !workspace)
     return fail(PLC_ERR_NULL_ARG, "plc_cell_bwd: null pointer");
   if ((dx || dh_prev) && !w_packed_dgrad) return fail(PLC_ERR_NULL_ARG, "plc_cell_bwd: dgrad image missing");
-  if (d->has_bias && !bias) return fail(PLC_ERR_NULL_ARG, "plc_cell_bwd: has_bias set but bias is null");
+  if (d->has_bias && !bias && !gates_saved) return fail(PLC_ERR_NULL_ARG, "plc_cell_bwd: has_bias set but bias is null");
+  if (gates_saved && !saved_gates_supported(d))
+    return fail(PLC_ERR_UNSUPPORTED, "plc_cell_bwd_saved: saved-gates mode needs bf16 mode and Ch %% 64 == 0");
   if (workspace_bytes < plc_bwd_workspace_bytes(d))
     return fail(PLC_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, plc_bwd_workspace_bytes(d));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -978,8 +1046,18 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     return fail(PLC_ERR_ALIGNMENT, "plc_cell_bwd: all device pointers must be 16-byte aligned");
   TcGeom g;
   plc::ConvTcParams p;
-  lstm_tc_setup(d, &g, &p, plc::EPI_LSTM_BWD_GATES);
+  // saved-gates form: the tile geometry must be the FORWARD kernel's (it defines the saved layout); no mainloop runs
+  lstm_tc_setup(d, &g, &p, gates_saved ? plc::EPI_LSTM_FWD : plc::EPI_LSTM_BWD_GATES);
+  if (gates_saved) {
+    if (!aligned16(gates_saved)) return fail(PLC_ERR_ALIGNMENT, "plc_cell_bwd_saved: gates_saved must be 16-byte aligned");
+    p.patch = 0;
+    p.gates_saved = static_cast<uint4*>(const_cast<void*>(gates_saved));
+  }
   // 1) gate recompute (same mainloop as the forward) + dZ / dc_prev epilogue
+  {
+    static const int skip = [] { const char* e = getenv("PLC_EXP_SKIP_GATE_MMA"); return e ? atoi(e) : 0; }();
+    p.exp_skip_mma = skip;
+  }
   p.bias = d->has_bias ? bias : nullptr;
   p.c_prev = static_cast<const float*>(c_prev);
   p.dh = static_cast<const __nv_bfloat16*>(dh);
@@ -995,7 +1073,8 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     ta0 = ta1;
   }
   const int cta = pick_cta_group(p.num_m_tiles);
-  if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile / cta))) return rc;
+  if (gates_saved) tb = ta1;      // never dereferenced (no mainloop); must still be a valid descriptor for the prefetch
+  else if ((rc = make_tmap_mat(&tb, w_packed_fwd, 4L * d->Ch, (long)p.num_kb * 64, 64, g.n_tile / cta))) return rc;
   CUtensorMap tzo = ta1, tdc = ta1;
   plc::GateMaps gm{};
   if (plc::tma_store_epilogue<256, plc::EPI_LSTM_BWD_GATES>() && g.n_tile == 256) {
@@ -1013,7 +1092,8 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     if (dh2 && (rc = make_tmap_act(&gm.dh2, dh2, d->B, d->H, d->W, d->Ch, g.tw, g.th, 2, rc_ch, s32))) return rc;
   }
   if ((rc = launch_conv_tc<plc::EPI_LSTM_BWD_GATES>(g.n_tile, cta, p, ta0, ta1, tb, tzo, tdc, st, PLC_K_BWD_GATES,
-                                                    conv_flops(d->B, d->H, d->W, d->Cin + d->Ch, 4 * d->Ch, d->k), &gm)))
+                                                    gates_saved ? 0.0 : conv_flops(d->B, d->H, d->W, d->Cin + d->Ch,
+                                                                                   4 * d->Ch, d->k), &gm)))
     return rc;
 
   // 2) dgrad: conv of dZ (4Ch channels) with the flipped/transposed image -> dx, dh_prev
@@ -1048,6 +1128,23 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
     if ((rc = launch_wgrad_tc(d, x, h_prev, workspace, dW_acc, d->has_bias ? db_acc : nullptr, st))) return rc;
   }
   return PLC_OK;
+}
+
+int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                 const void* w_packed_fwd, const void* w_packed_dgrad, const float* bias, const void* dh,
+                 const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc,
+                 float* db_acc, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!w_packed_fwd) return fail(PLC_ERR_NULL_ARG, "plc_cell_bwd: null pointer");
+  return cell_bwd_impl(d, x, h_prev, c_prev, w_packed_fwd, w_packed_dgrad, bias, nullptr, dh, dh2, dc_next, dx, dh_prev,
+                       dc_prev, dW_acc, db_acc, workspace, workspace_bytes, stream);
+}
+int plc_cell_bwd_saved(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
+                       const void* gates_saved, const void* w_packed_dgrad, const void* dh, const void* dh2,
+                       const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc, float* db_acc,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (!gates_saved) return fail(PLC_ERR_NULL_ARG, "plc_cell_bwd_saved: gates_saved is null");
+  return cell_bwd_impl(d, x, h_prev, c_prev, nullptr, w_packed_dgrad, nullptr, gates_saved, dh, dh2, dc_next, dx, dh_prev,
+                       dc_prev, dW_acc, db_acc, workspace, workspace_bytes, stream);
 }
 
 // ---------------------------------------------------------------------------------- weight-gradient accumulator
@@ -1178,6 +1275,23 @@ int plc_conv_grad_mask(const PlcConvDesc* d, const void* y, const void* dy, void
     conv_grad_mask_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dz), npix,
         d->H, d->W, d->Cout, d->relu, d->pixel_shuffle);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
+int plc_conv_im2col_narrow(const PlcConvDesc* d, int cin_true, const void* x, void* col, void* stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  if (!x || !col) return fail(PLC_ERR_NULL_ARG, "plc_conv_im2col_narrow: null pointer");
+  if (d->Cin != 8 || cin_true < 1 || cin_true > 8 || d->k * d->k * cin_true > 32)
+    return fail(PLC_ERR_UNSUPPORTED, "plc_conv_im2col_narrow: needs an 8-channel (padded) input and k*k*cin_true <= 32 "
+                                     "(got Cin %d, k %d, cin_true %d)", d->Cin, d->k, cin_true);
+  if (!aligned16(x) || !aligned16(col))
+    return fail(PLC_ERR_ALIGNMENT, "plc_conv_im2col_narrow: all device pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchTimer timer(PLC_K_ELEMENTWISE, st);
+  im2col_narrow_kernel<<<sm_count() * 16, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint4*>(col),
+                                                        d->B, d->H, d->W, cin_true, d->k);
   PLC_CUDA(cudaGetLastError());
   return PLC_OK;
 }

@@ -108,6 +108,11 @@ __device__ __forceinline__ void tma_load_4d_s(uint32_t smem_dst, const void* tma
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// plain (1-D) bulk copy global -> this CTA's shared memory, completion bytes on a local mbarrier; 16-byte granularity
+__device__ __forceinline__ void bulk_load_1d_s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
 // 2-CTA variants: data lands in this CTA's smem, completion bytes are signalled on the
 // barrier address given (which may be the peer/leader CTA's barrier, cluster address).
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr,

@@ -96,10 +96,18 @@ def _act_dtype(mode: int):
     return torch.bfloat16 if mode == PLC_MODE_BF16_TC else torch.float32
 
 
+def saved_gates_bytes(B: int, H: int, W: int, pw: PackedWeights) -> int:
+    """Bytes of one step's saved-gates buffer (plc_saved_gates_bytes); 0 = this shape/mode has no saved-gates form."""
+    lib = _lib.load()
+    d = make_desc(B, H, W, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)
+    return int(lib.plc_saved_gates_bytes(ctypes.byref(d)))
+
+
 def cell_forward(x: Optional[Tensor], h: Tensor, c: Tensor, pw: PackedWeights,
                  h_out: Optional[Tensor] = None, c_out: Optional[Tensor] = None,
-                 gates_out: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
-    """One fused cell step (convlstm.py:16-28).  NHWC tensors; returns (h_next, c_next)."""
+                 gates_out: Optional[Tensor] = None, saved: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """One fused cell step (convlstm.py:16-28).  NHWC tensors; returns (h_next, c_next).  `saved` (uint8,
+    :func:`saved_gates_bytes`) additionally keeps the activated gates for :func:`cell_backward_acc`'s saved form."""
     lib = _lib.load()
     B, H, W, Ch = h.shape
     adt = _act_dtype(pw.mode)
@@ -117,6 +125,12 @@ def cell_forward(x: Optional[Tensor], h: Tensor, c: Tensor, pw: PackedWeights,
     if c_out is None:
         c_out = torch.empty_like(c)
     d = make_desc(B, H, W, pw.Cin, Ch, pw.k, pw.mode, pw.bias is not None)
+    if saved is not None:
+        if gates_out is not None:
+            raise RuntimeError("cell_forward: pass gates_out or saved, not both")
+        _call(h, lib.plc_cell_fwd_save, "plc_cell_fwd_save", ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h), _ptr(c),
+              _ptr(pw.fwd), _ptr(pw.bias), _ptr(h_out), _ptr(c_out), _ptr(saved))
+        return h_out, c_out
     _call(h, lib.plc_cell_fwd, "plc_cell_fwd", ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h), _ptr(c), _ptr(pw.fwd),
                                 _ptr(pw.bias), _ptr(h_out), _ptr(c_out), _ptr(gates_out))
     return h_out, c_out
@@ -174,10 +188,11 @@ def cell_backward_acc(x: Optional[Tensor], h_prev: Tensor, c_prev: Tensor, pw: P
                       dh2: Optional[Tensor], dc_next: Optional[Tensor], dW_img: Optional[Tensor],
                       db_acc: Optional[Tensor], need_dx: bool = True, workspace: Optional[Tensor] = None,
                       dx: Optional[Tensor] = None, dh_prev: Optional[Tensor] = None,
-                      dc_prev: Optional[Tensor] = None):
+                      dc_prev: Optional[Tensor] = None, saved: Optional[Tensor] = None):
     """BPTT of one cell step: returns (dx, dh_prev, dc_prev).  `dW_img` is the accumulator image from
     :func:`wgrad_accumulator` (accumulated in place across steps; convert once with :func:`wgrad_unpack`);
-    `db_acc` [4Ch] fp32 is accumulated in place."""
+    `db_acc` [4Ch] fp32 is accumulated in place.  `saved` = the buffer the forward step filled (``cell_forward(...,
+    saved=)``): the gate recompute contraction is skipped (plc_cell_bwd_saved)."""
     lib = _lib.load()
     B, H, W, Ch = h_prev.shape
     if pw.dgrad is None:
@@ -191,6 +206,11 @@ def cell_backward_acc(x: Optional[Tensor], h_prev: Tensor, c_prev: Tensor, pw: P
     if dc_prev is None:
         dc_prev = torch.empty_like(c_prev)
     d = make_desc(B, H, W, pw.Cin, Ch, pw.k, pw.mode, pw.bias is not None)
+    if saved is not None:
+        _call(h_prev, lib.plc_cell_bwd_saved, "plc_cell_bwd_saved", ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None,
+              _ptr(h_prev), _ptr(c_prev), _ptr(saved), _ptr(pw.dgrad), _ptr(dh), _ptr(dh2), _ptr(dc_next),
+              _ptr(dx), _ptr(dh_prev), _ptr(dc_prev), _ptr(dW_img), _ptr(db_acc), _ptr(workspace), workspace.numel())
+        return dx, dh_prev, dc_prev
     _call(h_prev, lib.plc_cell_bwd, "plc_cell_bwd", ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h_prev), _ptr(c_prev),
                                 _ptr(pw.fwd), _ptr(pw.dgrad), _ptr(pw.bias), _ptr(dh), _ptr(dh2), _ptr(dc_next),
                                 _ptr(dx), _ptr(dh_prev), _ptr(dc_prev), _ptr(dW_img), _ptr(db_acc),
@@ -400,6 +420,22 @@ class _ConvFn(torch.autograd.Function):
             _call(dy, lib.plc_conv_grad_mask, "plc_conv_grad_mask", ctypes.byref(d), _ptr(out), _ptr(dy), _ptr(dz))
         else:
             dz = dy
+        if (not ctx.x_needs_grad) and cp.cin_p == 8 and cp.Cin * cp.k * cp.k <= 32 and not cp.shuffle:
+            # narrow input (front-end init_conv: 3 channels): one 32-column im2col row per pixel, then the reduction
+            # over pixels is ONE [Cout x 32] column block instead of k*k blocks of mostly zero padding
+            col = torch.empty(B, H, W, 32, dtype=torch.bfloat16, device=x.device)
+            _call(x, lib.plc_conv_im2col_narrow, "plc_conv_im2col_narrow", ctypes.byref(d), cp.Cin, _ptr(x), _ptr(col))
+            d1 = PlcConvDesc(B, H, W, 32, cp.cout_p, 1, 0, 0, int(cp.conv.bias is not None))
+            dW1 = torch.zeros(cp.cout_p, 32, 1, 1, dtype=torch.float32, device=x.device)
+            img = torch.zeros(lib.plc_conv_wgrad_acc_bytes(ctypes.byref(d1)) // 4, dtype=torch.float32, device=x.device)
+            db = torch.zeros(cp.cout_p, dtype=torch.float32, device=x.device) if cp.conv.bias is not None else None
+            _call(x, lib.plc_conv_bwd, "plc_conv_bwd", ctypes.byref(d1), _ptr(col), _ptr(dz), None, None, _ptr(img), _ptr(db))
+            _call(img, lib.plc_conv_wgrad_unpack, "plc_conv_wgrad_unpack", ctypes.byref(d1), _ptr(img), _ptr(dW1))
+            kk = cp.k * cp.k
+            gw = dW1[:cp.Cout, :kk * cp.Cin, 0, 0].reshape(cp.Cout, kk, cp.Cin).permute(0, 2, 1)
+            gw = gw.reshape(cp.Cout, cp.Cin, cp.k, cp.k).to(cp.conv.weight.dtype)
+            gb = None if db is None else db[:cp.Cout].to(cp.conv.bias.dtype)
+            return None, gw, gb, None
         dx = torch.empty_like(x) if ctx.x_needs_grad else None
         dW = torch.zeros(cp.cout_p, cp.cin_p, cp.k, cp.k, dtype=torch.float32, device=x.device)
         img = torch.zeros(lib.plc_conv_wgrad_acc_bytes(ctypes.byref(d)) // 4, dtype=torch.float32, device=x.device)

@@ -14,6 +14,7 @@
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -154,6 +155,31 @@ class ConvLSTMCell(nn.Module):
         return h2.to(out_dtype).permute(0, 3, 1, 2), c2.to(c_dtype).permute(0, 3, 1, 2)
 
 
+# Saved-gates BPTT (plc_cell_fwd_save / plc_cell_bwd_saved): "auto" keeps the activated gates of a rollout when they fit
+# comfortably (<= 20 % of the device's memory and <= half of what is free right now), "on" always (where the shape has
+# a saved form), "off" never (recompute, no extra memory).  PLC_SAVE_GATES overrides the default.
+SAVE_GATES = os.environ.get("PLC_SAVE_GATES", "auto")
+LAST_SAVED_GATES_BYTES = 0      # introspection: bytes the most recent rollout kept (0 = it recomputed)
+
+
+def _saved_gates_plan(cells, pws, T, B, H, W, dev):
+    """bytes per step of every layer's saved-gates buffer (0 = recompute for that layer)."""
+    global LAST_SAVED_GATES_BYTES
+    mode = SAVE_GATES
+    LAST_SAVED_GATES_BYTES = 0
+    if mode not in ("auto", "on", "1"):
+        return [0] * len(cells)
+    per = [F.saved_gates_bytes(B, H, W, pw) for pw in pws]
+    total = T * sum(per)
+    if mode == "auto" and total > 0:
+        free, cap = torch.cuda.mem_get_info(dev)
+        free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+        if total > 0.2 * cap or total > 0.5 * free:
+            return [0] * len(cells)
+    LAST_SAVED_GATES_BYTES = total
+    return per
+
+
 class _StackRolloutFn(torch.autograd.Function):
     """The whole stacked T-step rollout (generator.py:156-171) as ONE autograd node.
 
@@ -182,12 +208,18 @@ class _StackRolloutFn(torch.autograd.Function):
             c_ring[0].copy_(states[2 * l + 1])
             hs.append(h_ring)
             cs.append(c_ring)
+        # saved-gates BPTT where memory allows: one buffer per (layer, step), filled by the forward kernel
+        sv = [None] * L
+        if need_grad:
+            per = _saved_gates_plan(cells, pws, T, B, H, W, dev)
+            sv = [torch.empty(T, n, device=dev, dtype=torch.uint8) if n else None for n in per]
         for t in range(T):                                   # generator.py:164
             inp = None if xs is None else xs[t]
             for l in range(L):                               # generator.py:170-171
-                F.cell_forward(inp, hs[l][t], cs[l][t], pws[l], h_out=hs[l][t + 1], c_out=cs[l][t + 1])
+                F.cell_forward(inp, hs[l][t], cs[l][t], pws[l], h_out=hs[l][t + 1], c_out=cs[l][t + 1],
+                               saved=None if sv[l] is None else sv[l][t])
                 inp = hs[l][t + 1]
-        ctx.cells, ctx.T, ctx.pws = cells, T, pws
+        ctx.cells, ctx.T, ctx.pws, ctx.sv = cells, T, pws, sv
         ctx.xs, ctx.hs, ctx.cs = xs, hs, cs
         ctx.x_needs_grad = xs is not None and xs.requires_grad
         ctx.state_needs_grad = [s.requires_grad for s in states]
@@ -261,7 +293,8 @@ class _StackRolloutFn(torch.autograd.Function):
                     out_dx = dxs[t] if (l == 0) else dx_buf[l]
                 dst = dh_buf[l][flip[l]]
                 F.cell_backward_acc(x_in, hs[l][t], cs[l][t], pws[l], dh, dh2, dc_carry[l], dW_img[l], db[l],
-                                    need_dx=need_dx, workspace=ws[l], dx=out_dx, dh_prev=dst, dc_prev=dc_buf[l])
+                                    need_dx=need_dx, workspace=ws[l], dx=out_dx, dh_prev=dst, dc_prev=dc_buf[l],
+                                    saved=None if ctx.sv[l] is None else ctx.sv[l][t])
                 dh_carry[l], dc_carry[l] = dst, dc_buf[l]
                 flip[l] ^= 1
                 d_above = out_dx if l > 0 else None

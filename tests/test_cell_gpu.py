@@ -410,3 +410,89 @@ def test_patch_vs_default_pipeline_random_shapes(cuda_device):
         for i, nm in list(enumerate(("h", "c", "dh_prev", "dc_prev", "dW", "db", "dx")))[2:len(a)]:
             err = float((a[i] - p_[i]).abs().max() / (a[i].abs().max() + 1e-20))
             assert err <= 1e-2, f"{tag} {nm} {err:.3e}"
+
+
+# ---- saved-gates BPTT: the forward keeps the activated gates, the backward gate kernel runs without its mainloop -----
+SAVED_SHAPES = [
+    (2, 64, 64, 16, 8, 3),       # exactly one tile per image
+    (2, 64, 64, 20, 13, 3),      # ragged in both directions (uninitialised saved rows must be clipped)
+    (3, 0, 64, 24, 24, 3),       # no input tensor (forecaster first layer)
+    (1, 64, 128, 33, 17, 3),     # two 64-channel slices (n tiles)
+    (2, 128, 64, 19, 21, 5),     # k = 5, two x chunks
+]
+
+
+@pytest.mark.parametrize("cta", [1, 2], ids=["cta1", "cta2"])
+@pytest.mark.parametrize("shape", SAVED_SHAPES, ids=lambda s: "B%d_Cin%d_Ch%d_%dx%d_k%d" % s)
+def test_saved_gates_bptt_matches_recompute_and_oracle(shape, cta, cuda_device):
+    """plc_cell_fwd_save + plc_cell_bwd_saved: the forward outputs are bit-identical to plc_cell_fwd; the gradients
+    agree with the recompute path up to the bf16 rounding of the stored gates (fp32 outputs <= 6e-3 of max, bf16 outputs
+    <= 1e-2 = two ulps at the largest value) and with the fp64 oracle
+    inside the same 2e-2 bound the recompute path is held to."""
+    plconv, F = _plconv()
+    lib = plconv._lib.load()
+    lib.plc_debug_set_cta_group(cta)
+    try:
+        B, cin, ch, H, W, k = shape
+        dev = cuda_device
+        gen = torch.Generator().manual_seed(31 + sum(shape))
+        fan_in = (cin + ch) * k * k
+        w = (torch.rand(4 * ch, cin + ch, k, k, generator=gen) * 2 - 1) * (3.0 / fan_in) ** 0.5 * 2
+        b = torch.randn(4 * ch, generator=gen) * 0.5
+        x = torch.randn(B, cin, H, W, generator=gen) if cin else None
+        h = torch.randn(B, ch, H, W, generator=gen) * 0.5
+        c = torch.randn(B, ch, H, W, generator=gen)
+        gh = torch.randn(B, ch, H, W, generator=gen)
+        gh2 = torch.randn(B, ch, H, W, generator=gen) * 0.3
+        gc = torch.randn(B, ch, H, W, generator=gen)
+        pw = F.pack_weights(w.to(dev), b.to(dev), cin, ch, k, plconv.PLC_MODE_BF16_TC, with_dgrad=True)
+        nbytes = F.saved_gates_bytes(B, H, W, pw)
+        assert nbytes > 0 and nbytes % (64 * 1024) == 0
+        xd = nhwc(x, torch.bfloat16, dev) if cin else None
+        hd, cd = nhwc(h, torch.bfloat16, dev), nhwc(c, torch.float32, dev)
+        saved = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device=dev)        # bf16 NaN pattern where nothing is stored
+        h_a, c_a = F.cell_forward(xd, hd, cd, pw)
+        h_b, c_b = F.cell_forward(xd, hd, cd, pw, saved=saved)
+        assert torch.equal(h_a, h_b) and torch.equal(c_a, c_b)
+        dh, dh2, dc = nhwc(gh, torch.bfloat16, dev), nhwc(gh2, torch.bfloat16, dev), nhwc(gc, torch.float32, dev)
+
+        def bwd(sv):
+            img = F.wgrad_accumulator(B, H, W, pw, dev)
+            db = torch.zeros(4 * ch, device=dev)
+            dx, dhp, dcp = F.cell_backward_acc(xd, hd, cd, pw, dh, dh2, dc, img, db, saved=sv)
+            dW = torch.zeros(4 * ch, cin + ch, k, k, device=dev)
+            F.wgrad_unpack(img, pw, dW)
+            return dx, dhp, dcp, dW, db
+
+        rec, sav = bwd(None), bwd(saved)
+        torch.cuda.synchronize()
+        names = ("dx", "dh_prev", "dc_prev", "dW", "db")
+        for n_, a, s_ in zip(names, rec, sav):
+            if a is None:
+                assert s_ is None
+                continue
+            assert torch.isfinite(s_.float()).all(), n_
+            # dx / dh_prev are bf16 tensors: one or two ulps at the largest value are 4e-3 .. 8e-3 of max
+            tol = 1e-2 if s_.dtype == torch.bfloat16 else 6e-3
+            assert rel_err(s_, a) < tol, report(n_ + " saved vs recompute", s_, a)
+        xr = None if x is None else bf16r(x).double()
+        ref = O.cell_backward(xr, bf16r(h).double(), c.double(), bf16r(w).double(), b.double(),
+                              (bf16r(gh) + bf16r(gh2)).double(), gc.double())
+        got = {"dx": None if sav[0] is None else nchw(sav[0]), "dh_prev": nchw(sav[1]), "dc_prev": nchw(sav[2]),
+               "dW": sav[3].cpu(), "db": sav[4].cpu()}
+        bad = [report(n_, got[n_], ref[n_]) for n_ in names if got[n_] is not None and rel_err(got[n_], ref[n_]) >= 2e-2]
+        assert not bad, " | ".join(bad)
+    finally:
+        lib.plc_debug_set_cta_group(0)
+
+
+def test_saved_gates_unsupported_shapes_are_loud(cuda_device):
+    plconv, F = _plconv()
+    dev = cuda_device
+    w = torch.randn(4 * 32, 32 + 32, 3, 3, device=dev) * 0.05
+    pw = F.pack_weights(w, None, 32, 32, 3, plconv.PLC_MODE_BF16_TC, with_dgrad=True)
+    assert F.saved_gates_bytes(2, 16, 16, pw) == 0                              # Ch % 64 != 0: recompute only
+    x = torch.zeros(2, 16, 16, 32, device=dev, dtype=torch.bfloat16)
+    c = torch.zeros(2, 16, 16, 32, device=dev)
+    with pytest.raises(RuntimeError, match="saved-gates"):
+        F.cell_forward(x, x.clone(), c, pw, saved=torch.empty(65536, dtype=torch.uint8, device=dev))
