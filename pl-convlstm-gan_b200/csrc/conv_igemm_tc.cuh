@@ -221,12 +221,17 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   uint64_t* patch_empty = bars + 18;               // [8]
   uint64_t* bfull_bar = bars + 26;                 // [8]
   uint64_t* bempty_bar = bars + 34;                // [8]
-  uint64_t* gin_full = bars + 44;                  // [2] bwd gates: operand buffer filled by TMA
-  uint64_t* gout_ready = bars + 46;                // [2] bwd gates: outputs written, buffer ready for the tensor stores
+  uint64_t* gin_full = bars + 44;                  // [4] bwd gates: operand buffer filled by TMA
+  uint64_t* gout_ready = bars + 48;                // [4] bwd gates: outputs written, buffer ready for the tensor stores
 
   // saved-gates form of the gate-gradient kernel: no operand loads, no MMAs; the epilogue takes the activated gates the
   // forward pass stored (bulk copies into the idle operand-pipeline region) instead of the accumulator
   const bool saved = (EPI == EPI_LSTM_BWD_GATES) && p.gates_saved != nullptr;
+  // gate-gradient round buffers: two 24 KB in/out buffers behind the operand pipeline (recompute); in the saved form the
+  // idle pipeline region holds FOUR 40 KB buffers (24 KB in/out + 16 KB of saved gates) so that the loads run four
+  // rounds = one whole tile ahead -- the kernel is HBM-bound and needs the bytes in flight
+  const int g_nb = saved ? 4 : 2;
+  const uint32_t g_stride = saved ? 40960u : static_cast<uint32_t>(Cfg::kGateBufBytes);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int rank = (kCta == 2) ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader (issues the MMAs)
@@ -251,7 +256,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiWarps * kCta);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&gin_full[s], 1);
       mbar_init(&gout_ready[s], kEpiWarps);
     }
@@ -590,24 +595,25 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
   } else if (warp == 3) {
     if constexpr (EPI == EPI_LSTM_BWD_GATES && Cfg::kTmaStore) {
       // ===================================================================== gate-operand loader / output storer
-      // Round R = NR * (tile index of this CTA) + (16-channel quarter of the slice) lives in buffer R & 1.  Loads run
-      // TWO rounds ahead of the epilogue: buffer R & 1 is refilled for round R + 2 as soon as the stores of round R have
-      // finished reading it, i.e. a whole round before the epilogue warps need it.
+      // Round R = NR * (tile index of this CTA) + (16-channel quarter of the slice) lives in buffer R % g_nb.  Loads run
+      // g_nb rounds ahead of the epilogue (2 with the recompute mainloop, 4 in the saved-gates form): buffer R % g_nb is
+      // refilled for round R + g_nb as soon as the stores of round R have finished reading it.
       constexpr int RC = Cfg::kGateRoundCh, NR = CH_TILE / RC;
       constexpr uint32_t kF = 128 * RC * 4, kH = 128 * RC * 2;     // bytes of an fp32 / bf16 box
-      const uint32_t so = smem_u32(stage_out), inf_base = smem_u32(gin_full);
+      const uint32_t so = saved ? smem_u32(smem_a) : smem_u32(stage_out), inf_base = smem_u32(gin_full);
       const int my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tile_step - 1) / tile_step : 0;
       const int rounds = NR * my_tiles;
       const uint32_t tx = kF + kH + (p.dc_next ? kF : 0u) + (p.dh2 ? kH : 0u) + (saved ? 4u * 4096u : 0u);
-      const uint32_t gsb = smem_u32(smem_a);               // saved gates of a round: 2 x [4 gates][2 granules][128 rows][16 B]
+      // saved gates of a round: [4 gates][2 granules][128 rows][16 B] behind the round's in/out buffer
       auto load_round = [&](int R) {
         if (R >= rounds) return;
         int n_tile, b, y0, x0;
         decode_tile<kCta>(p, tile0 + (R / NR) * tile_step, rank, n_tile, b, y0, x0);
         if (lane == 0) {
-          const uint32_t buf = so + (R & 1) * Cfg::kGateBufBytes, bar = inf_base + (R & 1) * 8;
+          const int bi = R % g_nb;
+          const uint32_t buf = so + bi * g_stride, bar = inf_base + bi * 8;
           const int cb = n_tile * CH_TILE + (R % NR) * RC;
-          mbar_arrive_expect_tx(&gin_full[R & 1], tx);
+          mbar_arrive_expect_tx(&gin_full[bi], tx);
           tma_load_4d_s(buf, &gmaps.c_prev, bar, cb, x0, y0, b);
           if (p.dc_next) tma_load_4d_s(buf + kF, &gmaps.dc_next, bar, cb, x0, y0, b);
           tma_load_4d_s(buf + 2 * kF, &gmaps.dh, bar, cb, x0, y0, b);
@@ -618,19 +624,18 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                                 (R % NR) * (2 * 128);
 #pragma unroll
             for (int gate = 0; gate < 4; ++gate)
-              bulk_load_1d_s(gsb + (R & 1) * 16384 + gate * 4096, gsrc + gate * (8 * 128), 4096, bar);
+              bulk_load_1d_s(buf + Cfg::kGateBufBytes + gate * 4096, gsrc + gate * (8 * 128), 4096, bar);
           }
         }
         __syncwarp();
       };
-      load_round(0);
-      load_round(1);
+      for (int R = 0; R < g_nb; ++R) load_round(R);
       for (int R = 0; R < rounds; ++R) {
-        mbar_wait(&gout_ready[R & 1], (R >> 1) & 1);
+        mbar_wait(&gout_ready[R % g_nb], (R / g_nb) & 1);
         int n_tile, b, y0, x0;
         decode_tile<kCta>(p, tile0 + (R / NR) * tile_step, rank, n_tile, b, y0, x0);
         if (lane == 0) {   // OOB rows / images (ragged tiles, odd tail pair) are clipped by TMA
-          const uint32_t buf = so + (R & 1) * Cfg::kGateBufBytes;
+          const uint32_t buf = so + (R % g_nb) * g_stride;
           const int cb = n_tile * CH_TILE + (R % NR) * RC;
           tma_store_4d(&tmap_o1, buf, cb, x0, y0, b);                                    // dc_prev
 #pragma unroll
@@ -640,7 +645,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           tma_store_wait_read();
         }
         __syncwarp();
-        load_round(R + 2);
+        load_round(R + g_nb);
       }
       if (lane == 0) tma_store_wait_all();   // bulk stores complete before the CTA retires
     }
@@ -856,13 +861,14 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
         const bool pw4 = (kProfEnabled && p.prof) && warp == 4 && lane == 0;
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          const uint32_t buf = smem_u32(stage_out) + (r & 1) * Cfg::kGateBufBytes;
+          const int gR = it * NR + r, gbi = gR % g_nb;       // global round index of this CTA, its buffer
+          const uint32_t buf = (saved ? smem_u32(smem_a) : smem_u32(stage_out)) + gbi * g_stride;
           const uint32_t crow = buf + row * 64;                  // c_prev -> dc_prev   [128 px][16 ch] fp32, SWIZZLE_64B
           const uint32_t nrow = buf + kF + row * 64;             // dc_next             (same layout)
           const uint32_t zrow = buf + kF + row * 32;             // dZ_i, dZ_f, dZ_o (over dh), dZ_g (over dh2): four
                                                                  // [128 px][16 ch] bf16 boxes, 32-byte rows, SWIZZLE_32B
           long long tA = pw4 ? clock64() : 0;
-          mbar_wait(&gin_full[r & 1], ((it * NR + r) >> 1) & 1);
+          mbar_wait(&gin_full[gbi], (gR / g_nb) & 1);
           if (pw4) pa_barA += clock64() - tA;                    // waiting for the round's operands
           uint4 dn[GPR][2];
 #pragma unroll
@@ -892,7 +898,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
               tmem_ld8(t_acc + 2 * CH_TILE + g * 8, vo);
               tmem_ld8(t_acc + 3 * CH_TILE + g * 8, vg);
             } else {
-              const uint32_t ga = smem_u32(smem_a) + (r & 1) * 16384 + gl * 2048 + row * 16;
+              const uint32_t ga = buf + Cfg::kGateBufBytes + gl * 2048 + row * 16;
 #pragma unroll
               for (int gate = 0; gate < 4; ++gate) sg[gate] = ld_shared_v4(ga + gate * 4096);
             }
@@ -983,7 +989,7 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
           }
           fence_proxy_async_smem();                 // my st.shared -> visible to the TMA (async proxy)
           __syncwarp();
-          if (lane == 0) mbar_arrive(&gout_ready[r & 1]);
+          if (lane == 0) mbar_arrive(&gout_ready[gbi]);
         }
       } else if constexpr (EPI == EPI_LSTM_BWD_GATES) {
         // ---- direct-store variant (channel slices narrower than 64): 16-channel chunks
