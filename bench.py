@@ -357,6 +357,8 @@ def run_train(args):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = gb * K / (ms * 1e-3)
+    from plconv import nn as _pnn
+    saved_bytes = _pnn.LAST_SAVED_GATES_BYTES        # what the measured step did (decided when it was recorded)
 
     # ---------------- end-to-end region: pinned host batches -> DevicePrefetcher (side stream, one batch ahead) ->
     # step -> the step's loss back to pinned host memory; every step copies ITS batch in and ITS result out.
@@ -383,6 +385,9 @@ def run_train(args):
     # launches, tagged with its kind and algorithmic FLOPs (plc_timing_*)
     n_prof = 2
     torch.cuda.synchronize()
+    if hasattr(step, "close"):
+        step.close()                                # the graph's private pool (rings, saved gates) goes back to the driver:
+                                                    # at radar scale the eager pass below needs that memory again
     _lib.timing_enable(True)
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
@@ -461,8 +466,6 @@ def run_train(args):
                                   f"step); oracle port = the reference's ATen CPU ops, fp32 autograd"}
 
     if rank == 0:
-        from plconv import nn as _pnn
-        saved_bytes = _pnn.LAST_SAVED_GATES_BYTES
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         print(json.dumps({
             "metric": train_metric(args), "value": value, "unit": "sequences/s", "n_gpus": world, "steps": K,

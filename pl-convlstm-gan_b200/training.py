@@ -93,6 +93,9 @@ class GraphedStep:
                 step_fn(*self.static_in)
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
+        # the capture allocates the step's buffers (state rings: tens of GB at radar scale) from the graph's PRIVATE pool;
+        # blocks the eager warm-up left in the caching allocator cannot be reused there, so hand them back first
+        torch.cuda.empty_cache()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = step_fn(*self.static_in)
@@ -117,3 +120,5 @@ class GraphedStep:
             torch.cuda.synchronize(dev)
             self.graph.reset()
             self.graph = None
+            self.static_out = None
+            torch.cuda.empty_cache()                 # return the private pool to the driver
