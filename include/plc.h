@@ -161,6 +161,11 @@ int plc_conv_pack_weight(const PlcConvDesc* d, int pack_kind, const float* w_oih
                          float* bias_packed, void* stream);
 int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, void* out,
                  void* stream);
+/* plc_conv_fwd with an fp32 output tensor [B,H,W,Cout] (no PixelShuffle): for the LAST layer of a model
+ * (generator.py:67-71 post_process[2], 32 -> 1), so the predicted rain keeps the fp32 accumulator instead of being
+ * rounded to 8 mantissa bits before the loss.                                                                    */
+int plc_conv_fwd_f32(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, float* out,
+                     void* stream);
 int plc_conv_grad_mask(const PlcConvDesc* d, const void* y, const void* dy, void* dz, void* stream);
 size_t plc_conv_wgrad_acc_bytes(const PlcConvDesc* d);
 int plc_conv_wgrad_unpack(const PlcConvDesc* d, const float* dW_acc, float* dW_oihw, void* stream);

@@ -72,6 +72,7 @@ SIGNATURES = {
     "plc_conv_packed_weight_bytes": (_sz, [_cp, _int]),
     "plc_conv_pack_weight": (_int, [_cp, _int, _vp, _vp, _vp, _vp, _vp]),
     "plc_conv_fwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp]),
+    "plc_conv_fwd_f32": (_int, [_cp, _vp, _vp, _vp, _vp, _vp]),
     "plc_conv_grad_mask": (_int, [_cp, _vp, _vp, _vp, _vp]),
     "plc_conv_im2col_narrow": (_int, [_cp, _int, _vp, _vp, _vp]),
     "plc_conv_bwd": (_int, [_cp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -92,6 +92,8 @@ struct ConvTcParams {
   int plain_relu;            // PLAIN: apply max(x, plain_slope * x): slope 0 = ReLU, 0.2 = LeakyReLU(0.2)
   float plain_slope;
   int plain_shuffle;         // PLAIN: PixelShuffle(2) store: column n' = sub*(n_total/4) + c -> out0[b, 2y+sub/2, 2x+sub%2, c]
+  int plain_f32;             // PLAIN: out0 is an fp32 [M, n_total] tensor (per-thread stores; the last layer of a model keeps
+                             // its fp32 accumulator instead of rounding the prediction to bf16)
   int plain_tma;             // PLAIN: outputs leave through smem staging + TMA tensor stores (tmap_o0 / tmap_o1 valid;
                              // needs no shuffle and 64-channel-aligned out0 / out1); 0 = per-thread 16-byte stores
   unsigned long long* prof;  // debug: per-CTA cycle counters [gridDim][16] or nullptr (plc_debug_set_prof)
@@ -1187,6 +1189,12 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
                 if (p.plain_relu) {
 #pragma unroll
                   for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], p.plain_slope * f[e]);
+                }
+                if (p.plain_f32) {
+                  float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + pix * p.n_total + n0);
+                  dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+                  dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+                  continue;
                 }
                 uint4 o;
                 o.x = pack_bf16x2(f[0], f[1]);

@@ -1218,11 +1218,12 @@ int plc_conv_pack_weight(const PlcConvDesc* d, int pack_kind, const float* w_oih
   return PLC_OK;
 }
 
-int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, void* out,
-                 void* stream) {
+static int conv_fwd_impl(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, void* out,
+                         bool out_f32, void* stream) {
   int rc = check_conv(d);
   if (rc) return rc;
   if (!x || !w_packed_fwd || !out) return fail(PLC_ERR_NULL_ARG, "plc_conv_fwd: null pointer");
+  if (out_f32 && d->pixel_shuffle) return fail(PLC_ERR_UNSUPPORTED, "plc_conv_fwd_f32: no PixelShuffle store in fp32");
   if (!aligned16(x) || !aligned16(w_packed_fwd) || !aligned16(out) || !aligned16(bias_packed))
     return fail(PLC_ERR_ALIGNMENT, "plc_conv_fwd: all device pointers must be 16-byte aligned");
   PlcCellDesc cd{d->B, d->H, d->W, d->Cin, d->Cout, d->k, PLC_MODE_BF16_TC, 0};
@@ -1241,14 +1242,23 @@ int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, 
   q.plain_bias = d->has_bias ? bias_packed : nullptr;
   q.plain_relu = d->relu;
   q.plain_shuffle = d->pixel_shuffle;
+  q.plain_f32 = out_f32 ? 1 : 0;
   const int cta = pick_cta_group(q.num_m_tiles);
   CUtensorMap ta, tb;
   if ((rc = make_tmap_src(&ta, x, d->B, d->H, d->W, d->Cin, q))) return rc;
   if ((rc = make_tmap_mat(&tb, w_packed_fwd, d->Cout, (long)q.num_kb * 64, 64, nt / cta))) return rc;
   CUtensorMap to0 = ta, to1 = ta;
-  if ((rc = setup_plain_stores(&q, d->B, d->H, d->W, &to0, &to1))) return rc;
+  if (!out_f32 && (rc = setup_plain_stores(&q, d->B, d->H, d->W, &to0, &to1))) return rc;   // fp32: per-thread stores
   return launch_conv_tc<plc::EPI_PLAIN>(nt, cta, q, ta, ta, tb, to0, to1, static_cast<cudaStream_t>(stream),
                                         PLC_K_CONV_FWD, conv_flops(d->B, d->H, d->W, d->Cin, d->Cout, d->k));
+}
+int plc_conv_fwd(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, void* out,
+                 void* stream) {
+  return conv_fwd_impl(d, x, w_packed_fwd, bias_packed, out, false, stream);
+}
+int plc_conv_fwd_f32(const PlcConvDesc* d, const void* x, const void* w_packed_fwd, const float* bias_packed, float* out,
+                     void* stream) {
+  return conv_fwd_impl(d, x, w_packed_fwd, bias_packed, out, true, stream);
 }
 
 size_t plc_conv_wgrad_acc_bytes(const PlcConvDesc* d) {

@@ -343,8 +343,10 @@ class ConvParams:
     Wraps the reference's `nn.Conv2d` PARAMETER HOLDER (weight [Cout, Cin, k, k], bias [Cout]); channel counts are
     zero-padded to the kernel's granularity (Cin -> multiple of 8, Cout -> multiple of 8, or 32 with PixelShuffle)."""
 
-    def __init__(self, conv: torch.nn.Conv2d, relu: bool = False, pixel_shuffle: bool = False):
-        self.conv, self.relu, self.shuffle = conv, relu, pixel_shuffle
+    def __init__(self, conv: torch.nn.Conv2d, relu: bool = False, pixel_shuffle: bool = False, out_f32: bool = False):
+        if out_f32 and (relu or pixel_shuffle):
+            raise ValueError("out_f32 is for a final linear layer: no ReLU, no PixelShuffle")
+        self.conv, self.relu, self.shuffle, self.out_f32 = conv, relu, pixel_shuffle, out_f32
         self.Cout, self.Cin, self.k, _ = conv.weight.shape
         self.cin_p = _rup(self.Cin, 8)
         self.cout_p = _rup(self.Cout, 32 if pixel_shuffle else 8)
@@ -398,9 +400,12 @@ class _ConvFn(torch.autograd.Function):
         if cp.shuffle:
             out = torch.empty(B, 2 * H, 2 * W, cp.cout_p // 4, dtype=torch.bfloat16, device=x.device)
         else:
-            out = torch.empty(B, H, W, cp.cout_p, dtype=torch.bfloat16, device=x.device)
+            out = torch.empty(B, H, W, cp.cout_p, dtype=torch.float32 if cp.out_f32 else torch.bfloat16, device=x.device)
         d = cp.desc(B, H, W)
-        _call(x, lib.plc_conv_fwd, "plc_conv_fwd", ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out))
+        if cp.out_f32:      # last layer of a model: keep the fp32 accumulator (plc_conv_fwd_f32)
+            _call(x, lib.plc_conv_fwd_f32, "plc_conv_fwd_f32", ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out))
+        else:
+            _call(x, lib.plc_conv_fwd, "plc_conv_fwd", ctypes.byref(d), _ptr(x), _ptr(fwd), _ptr(bias_packed), _ptr(out))
         ctx.cp, ctx.dg = cp, dg
         ctx.save_for_backward(x, out)
         ctx.x_needs_grad = x.requires_grad
@@ -415,6 +420,8 @@ class _ConvFn(torch.autograd.Function):
         dg = ctx.dg
         d = cp.desc(B, H, W)
         dy = dy.contiguous()
+        if dy.dtype != torch.bfloat16:                     # fp32-output layer: the gradient enters the bf16 backward here
+            dy = dy.to(torch.bfloat16)
         if cp.relu or cp.shuffle:
             dz = torch.empty(B, H, W, cp.cout_p, dtype=torch.bfloat16, device=x.device)
             _call(dy, lib.plc_conv_grad_mask, "plc_conv_grad_mask", ctypes.byref(d), _ptr(out), _ptr(dy), _ptr(dz))
@@ -448,7 +455,8 @@ class _ConvFn(torch.autograd.Function):
 
 
 def conv2d_same(x: Tensor, cp: ConvParams) -> Tensor:
-    """x [B,H,W,cin_p] bf16 -> [B,H,W,cout_p] (or [B,2H,2W,cout_p/4] with PixelShuffle); padded channels are zero."""
+    """x [B,H,W,cin_p] bf16 -> [B,H,W,cout_p] (or [B,2H,2W,cout_p/4] with PixelShuffle); padded channels are zero.
+    bf16 output, fp32 when ``cp.out_f32``."""
     return _ConvFn.apply(x, cp.conv.weight, cp.conv.bias, cp)
 
 

@@ -81,10 +81,10 @@ class Generator(nn.Module):
         self.mode = mode
         self._native = {}      # name -> functional.ConvParams (kernel-ready images of the plain convs, bf16 mode)
 
-    def _cp(self, name: str, conv: nn.Conv2d, relu: bool, shuffle: bool = False):
+    def _cp(self, name: str, conv: nn.Conv2d, relu: bool, shuffle: bool = False, out_f32: bool = False):
         cp = self._native.get(name)
         if cp is None or cp.conv is not conv:
-            cp = PF.ConvParams(conv, relu=relu, pixel_shuffle=shuffle)
+            cp = PF.ConvParams(conv, relu=relu, pixel_shuffle=shuffle, out_f32=out_f32)
             self._native[name] = cp
         return cp
 
@@ -230,7 +230,7 @@ class Generator(nn.Module):
         g = gate.permute(0, 2, 3, 1).to(torch.bfloat16)                                 # [B,hh,ww,hd1], time-invariant
         feat = (feat.view(T, B, hh, ww, hd1) * g.unsqueeze(0)).reshape(T * B, hh, ww, hd1)   # generator.py:198-199
         cpa = self._cp("post0", self.post_process[0], relu=True)
-        cpb = self._cp("post2", self.post_process[2], relu=False)
+        cpb = self._cp("post2", self.post_process[2], relu=False, out_f32=True)   # predicted rain stays fp32
         y = PF.conv2d_same(feat.contiguous(), cpa)                                      # generator.py:202
         if cpa.cout_p != cpb.cin_p:
             y = F.pad(y[..., :cpa.Cout], (0, cpb.cin_p - cpa.Cout)).contiguous()
