@@ -45,12 +45,14 @@ def test_generator_rollout_and_loss_vs_reference(path, mode, cuda_device):
     rain, dem, lu = (torch.from_numpy(g[k]).to(cuda_device) for k in ("rain", "dem", "lu"))
     pred = gen(rain, dem, lu)
     assert tuple(pred.shape) == g["pred"].shape
-    tol_pred = 2e-4 if mode == "fp32" else 2e-2
+    tol_pred = 2e-4 if mode == "fp32" else 1e-2      # bf16: measured 1.4e-3 .. 3.1e-3 (fp32 store of the last conv)
     assert rel_err(pred, torch.from_numpy(g["pred"])) < tol_pred, report("pred", pred, torch.from_numpy(g["pred"]))
     total, parts = L.combined_loss(pred.cpu(), torch.from_numpy(g["rain"]), torch.from_numpy(g["s_coords"]),
                                    torch.from_numpy(g["s_vals"]), scale_factor=int(g["scale"]))
-    # rollout loss tolerance (north_star "within a stated tolerance"): 1e-4 relative in fp32 mode, 1e-2 in bf16 mode
-    tol = 1e-4 if mode == "fp32" else 1e-2
+    # rollout loss tolerance (north_star "within a stated tolerance"): 1e-4 relative in fp32 mode, 5e-3 in bf16 mode
+    tol = 1e-4 if mode == "fp32" else 5e-3
+    print(f"{os.path.basename(path)} {mode}: pred err {rel_err(pred, torch.from_numpy(g['pred'])):.2e}, loss err "
+          f"{abs(float(total.detach()) - float(g['loss_total'])) / abs(float(g['loss_total'])):.2e}")
     assert abs(float(total.detach()) - float(g["loss_total"])) <= tol * abs(float(g["loss_total"]))
     for k in ("point", "conserve"):
         assert abs(float(parts[k].detach()) - float(g["loss_" + k])) <= tol * abs(float(g["loss_" + k])) + 1e-6, k
@@ -77,8 +79,8 @@ def test_generator_gradients_vs_reference_autograd(path, cuda_device):
 @pytest.mark.parametrize("path", golden_files("generator_b2"), ids=os.path.basename)
 def test_native_generator_gradients_bf16_vs_reference_autograd(path, cuda_device):
     """bf16 mode: the WHOLE generator (front-end, recurrence, PixelShuffle upsampling, post_process) runs in
-    libplc.so forward and backward; parameter gradients against the reference's fp32 autograd.  Tolerance 6e-2 of the
-    per-tensor max (bf16 activations and gradients through ~8 conv layers and T steps)."""
+    libplc.so forward and backward; parameter gradients against the reference's fp32 autograd.  Tolerance 3e-2 of the
+    per-tensor max (bf16 activations and gradients through ~8 conv layers and T steps; measured worst 1.5e-2)."""
     g = load_golden(path)
     gen = _build(g, "bf16", cuda_device)
     rain, dem, lu = (torch.from_numpy(g[k]).to(cuda_device) for k in ("rain", "dem", "lu"))
@@ -87,15 +89,19 @@ def test_native_generator_gradients_bf16_vs_reference_autograd(path, cuda_device
                                torch.from_numpy(g["s_vals"]).to(cuda_device), scale_factor=int(g["scale"]))
     total.backward()
     bad = []
+    errs = {}
     for name, p in gen.named_parameters():
         ref = torch.from_numpy(g["grad." + name])
         assert p.grad is not None, name
-        if rel_err(p.grad, ref) >= 6e-2:
+        errs[name] = rel_err(p.grad, ref)
+        if errs[name] >= 3e-2:
             bad.append(report(name, p.grad, ref))
+    worst = max(errs, key=errs.get)
+    print(f"{os.path.basename(path)} bf16 native grads: worst {worst} {errs[worst]:.2e}")
     assert not bad, " | ".join(bad)
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-3), ("bf16", 6e-2)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-3), ("bf16", 3e-2)])
 @pytest.mark.parametrize("path", golden_files("generator_b2"), ids=os.path.basename)
 def test_product_generator_plus_product_loss_vs_reference(path, mode, tol, cuda_device):
     """The whole trainer.py:297-310 path on product code only: plconv.Generator -> plconv.CombinedLoss
