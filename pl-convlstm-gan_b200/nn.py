@@ -14,6 +14,7 @@
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import List, Optional, Sequence, Tuple
 
@@ -180,6 +181,28 @@ def _saved_gates_plan(cells, pws, T, B, H, W, dev):
     return per
 
 
+# Layer wavefront (opt-in, PLC_LAYER_STREAMS=1): cell (t, l) depends on (t-1, l) and (t, l-1) only, so layer l's step t and
+# layer l-1's step t+1 are independent -- forward and backward -- and each layer's launches can go to their OWN stream
+# with event edges between layers (captured into CUDA graphs as parallel branches).  Measured on B200 and NOT a gain
+# (cfg3 at 8 sequences per GPU: 11.13 vs 11.03 ms per step; at 64: 79.7 vs 79.4): every kernel here is persistent with
+# one CTA per SM and ~200 KB of shared memory, so a second kernel's CTA can only start when the first one's CTA has
+# exited -- the idle tail of a launch (the last tile's epilogue, ~5 us) lies INSIDE the CTA's lifetime and cannot be
+# covered by another stream, and the launch / prologue gap is already hidden by programmatic dependent launch.  Kept
+# for multi-layer stacks with small tiles; default off.
+LAYER_STREAMS = os.environ.get("PLC_LAYER_STREAMS", "0") == "1"
+_side_streams = {}
+
+
+def _layer_streams(dev, L):
+    """[current stream] + (L-1) side streams of `dev` (created once per device), or None when disabled / L == 1."""
+    if not LAYER_STREAMS or L < 2:
+        return None
+    pool = _side_streams.setdefault(dev.index, [])
+    while len(pool) < L - 1:
+        pool.append(torch.cuda.Stream(dev))
+    return [torch.cuda.current_stream(dev)] + pool[:L - 1]
+
+
 class _StackRolloutFn(torch.autograd.Function):
     """The whole stacked T-step rollout (generator.py:156-171) as ONE autograd node.
 
@@ -213,12 +236,34 @@ class _StackRolloutFn(torch.autograd.Function):
         if need_grad:
             per = _saved_gates_plan(cells, pws, T, B, H, W, dev)
             sv = [torch.empty(T, n, device=dev, dtype=torch.uint8) if n else None for n in per]
-        for t in range(T):                                   # generator.py:164
-            inp = None if xs is None else xs[t]
-            for l in range(L):                               # generator.py:170-171
-                F.cell_forward(inp, hs[l][t], cs[l][t], pws[l], h_out=hs[l][t + 1], c_out=cs[l][t + 1],
-                               saved=None if sv[l] is None else sv[l][t])
-                inp = hs[l][t + 1]
+        streams = _layer_streams(dev, L)
+        if streams is None:
+            for t in range(T):                                   # generator.py:164
+                inp = None if xs is None else xs[t]
+                for l in range(L):                               # generator.py:170-171
+                    F.cell_forward(inp, hs[l][t], cs[l][t], pws[l], h_out=hs[l][t + 1], c_out=cs[l][t + 1],
+                                   saved=None if sv[l] is None else sv[l][t])
+                    inp = hs[l][t + 1]
+        else:
+            # wavefront over per-layer streams: layer l, step t waits for layer l-1, step t (its input h)
+            fork = torch.cuda.Event()
+            fork.record(streams[0])
+            for st in streams[1:]:
+                st.wait_event(fork)
+            done = [None] * L                                    # event after layer l's most recent step
+            for t in range(T):
+                for l in range(L):
+                    with torch.cuda.stream(streams[l]):
+                        if l > 0:
+                            streams[l].wait_event(done[l - 1])
+                        F.cell_forward((None if xs is None else xs[t]) if l == 0 else hs[l - 1][t + 1], hs[l][t], cs[l][t],
+                                       pws[l], h_out=hs[l][t + 1], c_out=cs[l][t + 1],
+                                       saved=None if sv[l] is None else sv[l][t])
+                        if l < L - 1 or t == T - 1:
+                            done[l] = torch.cuda.Event()
+                            done[l].record(streams[l])
+            for l in range(1, L):                                # join: everything after this node sees all layers done
+                streams[0].wait_event(done[l])
         ctx.cells, ctx.T, ctx.pws, ctx.sv = cells, T, pws, sv
         ctx.xs, ctx.hs, ctx.cs = xs, hs, cs
         ctx.x_needs_grad = xs is not None and xs.requires_grad
@@ -241,8 +286,10 @@ class _StackRolloutFn(torch.autograd.Function):
         # recurrent carries: dh ping-pong (read as dh2 while the next dh_prev is written), dc in place
         dh_buf = [[torch.empty_like(hs[l][0]) for _ in range(2)] for l in range(L)]
         dc_buf = [torch.empty_like(cs[l][0]) for l in range(L)]
-        dx_buf = [torch.empty(B, H, W, pws[l].Cin, device=dev, dtype=cells[l].act_dtype) if pws[l].Cin else None
-                  for l in range(L)]
+        # dx of layer l feeds layer l-1 at the same step: two buffers (step parity), so that with per-layer streams layer l
+        # can start step t-1 while layer l-1 still reads step t's
+        dx_buf = [[torch.empty(B, H, W, pws[l].Cin, device=dev, dtype=cells[l].act_dtype) for _ in range(2)]
+                  if (pws[l].Cin and l > 0) else None for l in range(L)]
         dh_carry = [None] * L
         dc_carry = [None] * L
         for l in range(L):
@@ -253,7 +300,7 @@ class _StackRolloutFn(torch.autograd.Function):
                 dc_buf[l].copy_(dcT)
                 dc_carry[l] = dc_buf[l]
         dxs = torch.empty_like(xs) if ctx.x_needs_grad else None
-        zero_top = None
+        zero_top = {}
         flip = [0] * L
         wgrads = [None] * L
 
@@ -274,32 +321,57 @@ class _StackRolloutFn(torch.autograd.Function):
             else:
                 wgrads[l] = (gw, gb)
 
+        if d_out is None:                                    # every layer may need it: allocate before the streams fork
+            zero_top = {}
+            for l in range(L):
+                if hs[l][0].shape not in zero_top:
+                    zero_top[hs[l][0].shape] = torch.zeros_like(hs[l][0])
+        # BPTT wavefront over per-layer streams (see LAYER_STREAMS): layer l, step t waits for layer l+1, step t (its dh
+        # from above) and -- before it overwrites the dx buffer of step t's parity -- for layer l-1's step t+1
+        streams = _layer_streams(dev, L)
+        done = [None] * L
+        if streams is not None:
+            fork = torch.cuda.Event()
+            fork.record(streams[0])
+            for st in streams[1:]:
+                st.wait_event(fork)
         for t in reversed(range(T)):
             d_above = None if d_out is None else d_out[t]
             for l in reversed(range(L)):
-                x_in = (xs[t] if xs is not None else None) if l == 0 else hs[l - 1][t + 1]
-                dh, dh2 = d_above, dh_carry[l]
-                if dh is None:
-                    dh, dh2 = dh2, None
-                if dh is None:
-                    if zero_top is None or zero_top.shape != hs[l][0].shape:
-                        zero_top = torch.zeros_like(hs[l][0])
-                    dh = zero_top
-                if not dh.is_contiguous():
-                    dh = dh.contiguous()
-                need_dx = pws[l].Cin > 0 and (l > 0 or ctx.x_needs_grad)
-                out_dx = None
-                if need_dx:
-                    out_dx = dxs[t] if (l == 0) else dx_buf[l]
-                dst = dh_buf[l][flip[l]]
-                F.cell_backward_acc(x_in, hs[l][t], cs[l][t], pws[l], dh, dh2, dc_carry[l], dW_img[l], db[l],
-                                    need_dx=need_dx, workspace=ws[l], dx=out_dx, dh_prev=dst, dc_prev=dc_buf[l],
-                                    saved=None if ctx.sv[l] is None else ctx.sv[l][t])
-                dh_carry[l], dc_carry[l] = dst, dc_buf[l]
-                flip[l] ^= 1
-                d_above = out_dx if l > 0 else None
-                if t == 0:
-                    finish_layer(l)
+                with (torch.cuda.stream(streams[l]) if streams is not None else contextlib.nullcontext()):
+                    if streams is not None:
+                        if l < L - 1 and done[l + 1] is not None:
+                            streams[l].wait_event(done[l + 1])       # dx of the layer above, this step
+                        if l > 0 and done[l - 1] is not None:
+                            streams[l].wait_event(done[l - 1])       # the layer below has consumed step t+1's dx
+                    x_in = (xs[t] if xs is not None else None) if l == 0 else hs[l - 1][t + 1]
+                    dh, dh2 = d_above, dh_carry[l]
+                    if dh is None:
+                        dh, dh2 = dh2, None
+                    if dh is None:
+                        dh = zero_top[hs[l][0].shape]
+                    if not dh.is_contiguous():
+                        dh = dh.contiguous()
+                    need_dx = pws[l].Cin > 0 and (l > 0 or ctx.x_needs_grad)
+                    out_dx = None
+                    if need_dx:
+                        out_dx = dxs[t] if (l == 0) else dx_buf[l][t & 1]
+                    dst = dh_buf[l][flip[l]]
+                    F.cell_backward_acc(x_in, hs[l][t], cs[l][t], pws[l], dh, dh2, dc_carry[l], dW_img[l], db[l],
+                                        need_dx=need_dx, workspace=ws[l], dx=out_dx, dh_prev=dst, dc_prev=dc_buf[l],
+                                        saved=None if ctx.sv[l] is None else ctx.sv[l][t])
+                    dh_carry[l], dc_carry[l] = dst, dc_buf[l]
+                    flip[l] ^= 1
+                    d_above = out_dx if l > 0 else None
+                    if t == 0:
+                        finish_layer(l)
+                    if streams is not None:
+                        done[l] = torch.cuda.Event()
+                        done[l].record(streams[l])
+        if streams is not None:
+            for l in range(1, L):                            # join: the gradients below are consumed on the node's stream
+                if done[l] is not None:
+                    streams[0].wait_event(done[l])
         grads = [None, None, dxs]
         for l in range(L):
             grads.append(dh_carry[l] if ctx.state_needs_grad[2 * l] else None)

@@ -360,3 +360,31 @@ def test_training_path_saved_gates_vs_recompute(cuda_device, monkeypatch):
     (ref - tgt.double()).abs().mean().backward()
     errs = {k: rel_err(g_s[k], P[k].grad) for k in g_s}
     assert max(errs.values()) < 3e-2, errs
+
+
+def test_training_path_layer_streams_match_single_stream(cuda_device, monkeypatch):
+    """PLC_LAYER_STREAMS (per-layer streams with event edges, forward and BPTT) computes the same rollout: identical
+    prediction and gradients equal up to the order of the fp32 red.add accumulation in wgrad (<= 1e-5 of max)."""
+    import plconv
+    from plconv import nn as pnn
+    torch.manual_seed(41)
+    B, T_in, T_out, H, W, hd = 2, 4, 3, 24, 32, [64, 64]
+    model = plconv.NowcastGenerator(1, hd, 3, T_in, T_out, "bf16").to(cuda_device)
+    frames = torch.relu(torch.randn(B, T_in, 1, H, W, device=cuda_device) + 0.3)
+    tgt = torch.relu(torch.randn(B, T_out, 1, H, W, device=cuda_device) + 0.3)
+
+    def run(on):
+        monkeypatch.setattr(pnn, "LAYER_STREAMS", on)
+        for p in model.parameters():
+            p.grad = None
+        pred = model(frames)
+        (pred - tgt).abs().mean().backward()
+        torch.cuda.synchronize()
+        return pred.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+    pred_a, g_a = run(False)
+    for _ in range(3):                                    # a race would not show every time
+        pred_b, g_b = run(True)
+        assert torch.equal(pred_a, pred_b)
+        errs = {k: rel_err(g_b[k], g_a[k]) for k in g_a}
+        assert max(errs.values()) < 1e-5, errs
