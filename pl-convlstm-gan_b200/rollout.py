@@ -42,8 +42,13 @@ class NowcastGenerator(nn.Module):
             raise RuntimeError("NowcastGenerator.forward is implemented for mode='bf16'")
         B, T, Cf, H, W = frames.shape
         cp0 = self._init_cp()
-        x = F.frames_to_nhwc(frames.contiguous(), cp0.cin_p)                       # + coord planes (coordconv.py:3-10)
-        feat = F.conv2d_same(x, cp0).view(T, B, H, W, cp0.cout_p)                   # generator.py:166-168
+        if (cp0.Cout == 64 and cp0.k == 3 and cp0.cin_p == 8 and cp0.Cin * 9 <= 32 and not frames.requires_grad
+                and F.frontend_tc_supported(Cf, 64, 64)):
+            # fused front-end: coordinate planes + im2col inside the kernel, straight from the fp32 frames
+            feat = F.frontend_tc_train(frames.contiguous(), cp0).view(T, B, H, W, 64)   # generator.py:166-168
+        else:
+            x = F.frames_to_nhwc(frames.contiguous(), cp0.cin_p)                   # + coord planes (coordconv.py:3-10)
+            feat = F.conv2d_same(x, cp0).view(T, B, H, W, cp0.cout_p)               # generator.py:166-168
         _, state = self.encoder.run_seq(feat)
         out, _ = self.forecaster.run_seq(None, state, steps=self.t_out)            # [T_out,B,H,W,Ch]
         y = F.head(out, self.head.weight, self.head.bias, _MODES[self.mode])       # [T_out,B,H,W] fp32

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Time one cell step (fwd, optionally bwd) with CUDA events.  python tools/microbench.py B Cin Ch H W k [--bwd]"""
+"""Time one cell step (fwd, optionally bwd) with CUDA events.  python tools/microbench.py B Cin Ch H W k [--bwd] [--saved]
+--saved: saved-gates form (plc_cell_fwd_save / plc_cell_bwd_saved) instead of gate recompute."""
 import os
 import sys
 
@@ -41,7 +42,13 @@ def main():  # noqa: C901
     c = torch.randn(B, H, W, ch, device=dev)
     h2, c2 = torch.empty_like(h), torch.empty_like(c)
     flops = 2.0 * B * H * W * (cin + ch) * k * k * 4 * ch
-    med, mn = time_fn(lambda: F.cell_forward(x, h, c, pw, h_out=h2, c_out=c2))
+    saved = None
+    if "--saved" in sys.argv:
+        n = F.saved_gates_bytes(B, H, W, pw)
+        if not n:
+            raise SystemExit("this shape has no saved-gates form")
+        saved = torch.empty(n, dtype=torch.uint8, device=dev)
+    med, mn = time_fn(lambda: F.cell_forward(x, h, c, pw, h_out=h2, c_out=c2, saved=saved))
     print(f"fwd  B{B} {cin}->{ch} {H}x{W} k{k}: median {med:.1f} us  min {mn:.1f} us  "
           f"{flops / med / 1e6:.1f} TFLOP/s (median) {flops / mn / 1e6:.1f} (min)")
     if "--bwd" in sys.argv:
@@ -53,7 +60,7 @@ def main():  # noqa: C901
         img = F.wgrad_accumulator(B, H, W, pw, dev)
         dx, dhp, dcp = (torch.empty_like(x) if cin else None), torch.empty_like(h), torch.empty_like(c)
         med, mn = time_fn(lambda: F.cell_backward_acc(x, h, c, pw, dh, None, dc, img, db, workspace=ws, dx=dx,
-                                                  dh_prev=dhp, dc_prev=dcp), iters=10, warm=2)
+                                                  dh_prev=dhp, dc_prev=dcp, saved=saved), iters=10, warm=2)
         print(f"bwd  median {med:.1f} us  min {mn:.1f} us  {2 * flops / med / 1e6:.1f} TFLOP/s (2F algorithmic)")
 
 
