@@ -118,6 +118,15 @@ int plc_cell_bwd(const PlcCellDesc* d, const void* x, const void* h_prev, const 
                  const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev, float* dW_acc, float* db_acc,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight / bias gradient alone: dW_acc, db_acc += sum over the pixels of d->B images of dZ x cat(x, h_prev) -- the third
+ * stage of plc_cell_bwd, which skips it when called with dW_acc = NULL.  `dz` [B,H,W,4Ch] is what plc_cell_bwd left in
+ * its workspace.  The images need not come from one time step: a rollout that keeps dZ of all T steps (a [T*B,H,W,4Ch]
+ * ring next to the state rings, whose slices ARE x and h_prev of every step) runs ONE call with B = T*B per layer
+ * instead of T -- the accumulator flush (partial tiles reduced into HBM by red.add), prologue and tail of a launch are
+ * fixed costs that dominate at small per-GPU batches.                                           */
+int plc_cell_wgrad(const PlcCellDesc* d, const void* x, const void* h_prev, const void* dz, float* dW_acc, float* db_acc,
+                   void* stream);
+
 /* ---- saved-gates BPTT (optional; trades HBM for tensor time and power) -----------------------------------------
  * The reference's autograd keeps the activated gates of every step (convlstm.py:21-24 outputs are saved tensors);
  * plc_cell_bwd recomputes them instead (one extra gate contraction per step, no extra memory).  Where memory allows,

@@ -66,6 +66,7 @@ SIGNATURES = {
     "plc_conv_wgrad_acc_bytes": (_sz, [_cp]),
     "plc_conv_wgrad_unpack": (_int, [_cp, _vp, _vp, _vp]),
     "plc_cell_bwd": (_int, [_dp] + [_vp] * 15 + [_sz, _vp]),
+    "plc_cell_wgrad": (_int, [_dp] + [_vp] * 6),
     "plc_saved_gates_bytes": (_sz, [_dp]),
     "plc_cell_fwd_save": (_int, [_dp] + [_vp] * 9),
     "plc_cell_bwd_saved": (_int, [_dp] + [_vp] * 14 + [_sz, _vp]),

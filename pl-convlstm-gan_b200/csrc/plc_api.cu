@@ -967,6 +967,28 @@ size_t plc_bwd_workspace_bytes(const PlcCellDesc* d) {
   return m * 4 * d->Ch * (d->mode == PLC_MODE_FP32 ? 4 : 2);
 }
 
+// fp32 validation mode: weight + bias gradient of one call (dW_acc is the OIHW layout itself)
+static int wgrad_fp32(const PlcCellDesc* d, const void* x, const void* h_prev, const void* dz, float* dW_acc, float* db_acc,
+                      cudaStream_t st) {
+  const int M = d->B * d->H * d->W, kk = d->k * d->k;
+  plc::WgradParams w;
+  memset(&w, 0, sizeof(w));
+  w.B = d->B; w.H = d->H; w.W = d->W; w.M = M;
+  w.ksize = d->k; w.pad = d->k / 2;
+  w.C0 = d->Cin; w.C1 = d->Ch; w.K = kk * (d->Cin + d->Ch); w.N = 4 * d->Ch;
+  w.src0 = x; w.src1 = h_prev; w.dz = dz; w.dW = dW_acc; w.db = d->has_bias ? db_acc : nullptr;
+  const int tiles = cdiv(w.N, plc::SBN) * cdiv(w.K, plc::SBM);
+  int splits = cdiv(sm_count() * 4, tiles);
+  if (splits < 1) splits = 1;
+  int ppb = cdiv(cdiv(M, splits), plc::SBK) * plc::SBK;
+  if (ppb < plc::SBK) ppb = plc::SBK;
+  w.pix_per_block = ppb;
+  dim3 g3(cdiv(w.N, plc::SBN), cdiv(w.K, plc::SBM), cdiv(M, ppb));
+  plc::wgrad_simt_kernel<float><<<g3, 256, 0, st>>>(w);
+  PLC_CUDA(cudaGetLastError());
+  return PLC_OK;
+}
+
 static int cell_bwd_impl(const PlcCellDesc* d, const void* x, const void* h_prev, const void* c_prev,
                          const void* w_packed_fwd, const void* w_packed_dgrad, const float* bias, const void* gates_saved,
                          const void* dh, const void* dh2, const float* dc_next, void* dx, void* dh_prev, float* dc_prev,
@@ -1019,23 +1041,7 @@ static int cell_bwd_impl(const PlcCellDesc* d, const void* x, const void* h_prev
       PLC_CUDA(cudaGetLastError());
     }
     // 3) wgrad (+ bias grad)
-    if (dW_acc) {
-      plc::WgradParams w;
-      memset(&w, 0, sizeof(w));
-      w.B = d->B; w.H = d->H; w.W = d->W; w.M = M;
-      w.ksize = d->k; w.pad = d->k / 2;
-      w.C0 = d->Cin; w.C1 = d->Ch; w.K = kk * (d->Cin + d->Ch); w.N = 4 * d->Ch;
-      w.src0 = x; w.src1 = h_prev; w.dz = workspace; w.dW = dW_acc; w.db = d->has_bias ? db_acc : nullptr;
-      const int tiles = cdiv(w.N, plc::SBN) * cdiv(w.K, plc::SBM);
-      int splits = cdiv(sm_count() * 4, tiles);
-      if (splits < 1) splits = 1;
-      int ppb = cdiv(cdiv(M, splits), plc::SBK) * plc::SBK;
-      if (ppb < plc::SBK) ppb = plc::SBK;
-      w.pix_per_block = ppb;
-      dim3 g3(cdiv(w.N, plc::SBN), cdiv(w.K, plc::SBM), cdiv(M, ppb));
-      plc::wgrad_simt_kernel<float><<<g3, 256, 0, st>>>(w);
-      PLC_CUDA(cudaGetLastError());
-    }
+    if (dW_acc) return wgrad_fp32(d, x, h_prev, workspace, dW_acc, db_acc, st);
     return PLC_OK;
   }
 
@@ -1145,6 +1151,19 @@ int plc_cell_bwd_saved(const PlcCellDesc* d, const void* x, const void* h_prev, 
   if (!gates_saved) return fail(PLC_ERR_NULL_ARG, "plc_cell_bwd_saved: gates_saved is null");
   return cell_bwd_impl(d, x, h_prev, c_prev, nullptr, w_packed_dgrad, nullptr, gates_saved, dh, dh2, dc_next, dx, dh_prev,
                        dc_prev, dW_acc, db_acc, workspace, workspace_bytes, stream);
+}
+
+int plc_cell_wgrad(const PlcCellDesc* d, const void* x, const void* h_prev, const void* dz, float* dW_acc, float* db_acc,
+                   void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if ((d->Cin > 0 && !x) || !h_prev || !dz || !dW_acc) return fail(PLC_ERR_NULL_ARG, "plc_cell_wgrad: null pointer");
+  if (d->has_bias && !db_acc) return fail(PLC_ERR_NULL_ARG, "plc_cell_wgrad: has_bias set but db_acc is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->mode == PLC_MODE_FP32) return wgrad_fp32(d, x, h_prev, dz, dW_acc, db_acc, st);
+  if (!aligned16(x) || !aligned16(h_prev) || !aligned16(dz))
+    return fail(PLC_ERR_ALIGNMENT, "plc_cell_wgrad: all device pointers must be 16-byte aligned");
+  return launch_wgrad_tc(d, x, h_prev, dz, dW_acc, d->has_bias ? db_acc : nullptr, st);
 }
 
 // ---------------------------------------------------------------------------------- weight-gradient accumulator

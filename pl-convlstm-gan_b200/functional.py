@@ -163,6 +163,12 @@ def cell_forward_zero_state(x: Tensor, pw: PackedWeights, h_out: Optional[Tensor
     return h_out, c_out
 
 
+def bwd_workspace_bytes(B: int, H: int, W: int, pw: PackedWeights) -> int:
+    lib = _lib.load()
+    d = make_desc(B, H, W, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)
+    return int(lib.plc_bwd_workspace_bytes(ctypes.byref(d)))
+
+
 def bwd_workspace(B: int, H: int, W: int, pw: PackedWeights, device) -> Tensor:
     lib = _lib.load()
     d = make_desc(B, H, W, pw.Cin, pw.Ch, pw.k, pw.mode, pw.bias is not None)
@@ -216,6 +222,18 @@ def cell_backward_acc(x: Optional[Tensor], h_prev: Tensor, c_prev: Tensor, pw: P
                                 _ptr(dx), _ptr(dh_prev), _ptr(dc_prev), _ptr(dW_img), _ptr(db_acc),
                                 _ptr(workspace), workspace.numel())
     return dx, dh_prev, dc_prev
+
+
+def cell_wgrad(x: Optional[Tensor], h_prev: Tensor, dz: Tensor, pw: PackedWeights, dW_img: Tensor,
+               db_acc: Optional[Tensor]) -> None:
+    """dW / db of MANY cell steps in one launch (plc_cell_wgrad): `h_prev` [N,H,W,Ch], `x` [N,H,W,Cin] and `dz` (the
+    per-step workspaces of :func:`cell_backward_acc` called with ``dW_img=None``, N*H*W*4Ch elements) stacked over the
+    steps, N = T*B.  Accumulates into `dW_img` / `db_acc` like the per-step form."""
+    lib = _lib.load()
+    N, H, W, Ch = h_prev.shape
+    d = make_desc(N, H, W, pw.Cin, Ch, pw.k, pw.mode, pw.bias is not None)
+    _call(h_prev, lib.plc_cell_wgrad, "plc_cell_wgrad", ctypes.byref(d), _ptr(x) if pw.Cin > 0 else None, _ptr(h_prev),
+          _ptr(dz), _ptr(dW_img), _ptr(db_acc))
 
 
 def cell_backward(x: Optional[Tensor], h_prev: Tensor, c_prev: Tensor, pw: PackedWeights, dh: Tensor,

@@ -181,6 +181,27 @@ def _saved_gates_plan(cells, pws, T, B, H, W, dev):
     return per
 
 
+# Chunked weight gradient (plc_cell_wgrad): keep dZ of `chunk` consecutive steps of a layer and run ONE wgrad launch over
+# [chunk*B] images instead of one per step -- the accumulator flush, prologue and tail of a wgrad launch are fixed costs
+# (~12 us) that weigh 1 % at 64 sequences per GPU and ~20 % of the kernel at 8 (cfg3 on 8 GPUs: 11.27 -> 10.83 ms per
+# step).  The chunk is sized so that a launch reduces about as many pixels as one step at 64 sequences of 128x128 does
+# (2^20): longer reductions are NOT free -- the tensor core's fp32 accumulation error grows with the chain length
+# (measured: all T = 10 steps of B = 64 in one launch moves dW by 1e-3 of its max, one step per launch by 1e-4), so the
+# chunk never exceeds the chain length the full-size parity tests validate.  PLC_DEFER_WGRAD = auto | off | <steps>.
+DEFER_WGRAD = os.environ.get("PLC_DEFER_WGRAD", "auto")
+_WGRAD_CHAIN_PIXELS = 1 << 20
+
+
+def _wgrad_chunk(T, B, H, W):
+    """steps per wgrad launch (1 = the per-step form inside plc_cell_bwd)."""
+    mode = str(DEFER_WGRAD)
+    if mode in ("off", "0", "1") or T < 2:
+        return 1
+    if mode.isdigit():
+        return max(1, min(T, int(mode)))
+    return max(1, min(T, _WGRAD_CHAIN_PIXELS // max(1, B * H * W)))
+
+
 # Layer wavefront (opt-in, PLC_LAYER_STREAMS=1): cell (t, l) depends on (t-1, l) and (t, l-1) only, so layer l's step t and
 # layer l-1's step t+1 are independent -- forward and backward -- and each layer's launches can go to their OWN stream
 # with event edges between layers (captured into CUDA graphs as parallel branches).  Measured on B200 and NOT a gain
@@ -282,7 +303,10 @@ class _StackRolloutFn(torch.autograd.Function):
         dev = hs[0].device
         dW_img = [F.wgrad_accumulator(B, H, W, pw, dev) for pw in pws]     # accumulated over all T steps
         db = [torch.zeros(4 * c.hidden_dim, device=dev) if pw.bias is not None else None for c, pw in zip(cells, pws)]
-        ws = [F.bwd_workspace(B, H, W, pw, dev) for pw in pws]
+        # dZ: one workspace per layer reused by every step, or -- deferred wgrad -- a ring over all T steps
+        ws_bytes = [F.bwd_workspace_bytes(B, H, W, pw) for pw in pws]
+        chunk = _wgrad_chunk(T, B, H, W)                     # steps per weight-gradient launch (see DEFER_WGRAD)
+        ws = [torch.empty(chunk, n, dtype=torch.uint8, device=dev) for n in ws_bytes]
         # recurrent carries: dh ping-pong (read as dh2 while the next dh_prev is written), dc in place
         dh_buf = [[torch.empty_like(hs[l][0]) for _ in range(2)] for l in range(L)]
         dc_buf = [torch.empty_like(cs[l][0]) for l in range(L)]
@@ -303,6 +327,17 @@ class _StackRolloutFn(torch.autograd.Function):
         zero_top = {}
         flip = [0] * L
         wgrads = [None] * L
+
+        def chunk_wgrad(l, t0):
+            """ONE weight-gradient launch over steps t0 .. t0+n-1 (their dZ sits in ws[l][0:n], in step order): the state
+            rings' slices ARE x and h_prev of those steps."""
+            n = min(chunk, T - t0)
+            if l == 0:
+                x_all = None if xs is None else xs[t0:t0 + n].reshape(n * B, H, W, xs.shape[-1])
+            else:
+                x_all = hs[l - 1][t0 + 1:t0 + n + 1].reshape(n * B, H, W, hs[l - 1].shape[-1])
+            F.cell_wgrad(x_all, hs[l][t0:t0 + n].reshape(n * B, H, W, cells[l].hidden_dim), ws[l][0:n], pws[l],
+                         dW_img[l], db[l])
 
         def finish_layer(l):
             """Layer l's last BPTT step (t = 0) has been queued: convert its accumulator to the reference layout and, if
@@ -357,9 +392,12 @@ class _StackRolloutFn(torch.autograd.Function):
                     if need_dx:
                         out_dx = dxs[t] if (l == 0) else dx_buf[l][t & 1]
                     dst = dh_buf[l][flip[l]]
-                    F.cell_backward_acc(x_in, hs[l][t], cs[l][t], pws[l], dh, dh2, dc_carry[l], dW_img[l], db[l],
-                                        need_dx=need_dx, workspace=ws[l], dx=out_dx, dh_prev=dst, dc_prev=dc_buf[l],
-                                        saved=None if ctx.sv[l] is None else ctx.sv[l][t])
+                    F.cell_backward_acc(x_in, hs[l][t], cs[l][t], pws[l], dh, dh2, dc_carry[l],
+                                        dW_img[l] if chunk == 1 else None, db[l] if chunk == 1 else None,
+                                        need_dx=need_dx, workspace=ws[l][t % chunk], dx=out_dx, dh_prev=dst,
+                                        dc_prev=dc_buf[l], saved=None if ctx.sv[l] is None else ctx.sv[l][t])
+                    if chunk > 1 and t % chunk == 0:
+                        chunk_wgrad(l, t)
                     dh_carry[l], dc_carry[l] = dst, dc_buf[l]
                     flip[l] ^= 1
                     d_above = out_dx if l > 0 else None

@@ -388,3 +388,32 @@ def test_training_path_layer_streams_match_single_stream(cuda_device, monkeypatc
         assert torch.equal(pred_a, pred_b)
         errs = {k: rel_err(g_b[k], g_a[k]) for k in g_a}
         assert max(errs.values()) < 1e-5, errs
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_deferred_wgrad_matches_per_step_wgrad(mode, cuda_device, monkeypatch):
+    """PLC_DEFER_WGRAD: one plc_cell_wgrad launch per chunk of steps (3 of T = 4 here: a full and a ragged chunk) against
+    one wgrad per step -- the same sums in a different order (fp32 accumulation; bf16 mode: red.add of partial tiles):
+    <= 2e-5 of max."""
+    import plconv
+    from plconv import nn as pnn
+    torch.manual_seed(43)
+    B, T, H, W = 2, 4, 20, 24
+    stack = plconv.ConvLSTMStack(64, [64, 64], 3, True, mode).to(cuda_device)
+    x = torch.randn(B, T, 64, H, W, device=cuda_device)
+    gy = torch.randn(B, T, 64, H, W, device=cuda_device)
+
+    def run(m):
+        monkeypatch.setattr(pnn, "DEFER_WGRAD", m)
+        for p in stack.parameters():
+            p.grad = None
+        out, _ = stack(x)
+        (out * gy).sum().backward()
+        torch.cuda.synchronize()
+        return {k: p.grad.detach().clone() for k, p in stack.named_parameters()}
+
+    g_off = run("off")
+    for m in ("3", "auto", "4"):
+        g_on = run(m)
+        errs = {k: rel_err(g_on[k], g_off[k]) for k in g_off}
+        assert max(errs.values()) < 2e-5, (m, errs)
