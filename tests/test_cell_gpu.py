@@ -141,6 +141,14 @@ def test_forward_vs_oracle(shape, mode_name, cuda_device):
     h2, c2 = run_cell(mode, x, h, c, w, b, cuda_device)
     eh, ec = rel_err(h2, h_ref), rel_err(c2, c_ref)
     assert eh < tol and ec < tol, report("h", h2, h_ref) + " | " + report("c", c2, c_ref)
+    # rel_err is a GLOBAL-max norm (max |err| / max |ref| over the tensor).  The cell state stays fp32 in both modes, so
+    # it can also be held to a PER-ELEMENT bound: |err| <= atol + rtol * |ref| for every element -- bf16 mode: the
+    # tanh.approx / ex2-based gates carry ~2^-11 relative error each (atol = rtol = 2e-3); fp32 mode: 1e-5.
+    a = 2e-3 if mode_name == "bf16" else 1e-5
+    err = (c2.double() - c_ref).abs()
+    bound = a + a * c_ref.abs()
+    worst = float((err / bound).max())
+    assert worst <= 1.0, f"per-element c check: worst err/bound {worst:.2f}; " + report("c", c2, c_ref)
 
 
 def test_kat_zero_weights_gpu(cuda_device):
