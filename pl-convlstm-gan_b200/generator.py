@@ -201,10 +201,13 @@ class Generator(nn.Module):
         c1, c2 = self.cell1, self.cell2
         # coord channels (coordconv.py:3-10) appended in NHWC, channels zero-padded to the kernel granularity
         cp0 = self._cp("init", self.init_conv, relu=True)
-        x = rain_lr.permute(1, 0, 3, 4, 2).reshape(T * B, H, W, C)
-        rows = torch.linspace(0, 1, H, device=dev, dtype=x.dtype).view(1, H, 1, 1).expand(T * B, H, W, 1)
-        cols = torch.linspace(0, 1, W, device=dev, dtype=x.dtype).view(1, 1, W, 1).expand(T * B, H, W, 1)
-        x = F.pad(torch.cat([x, rows, cols], dim=-1), (0, cp0.cin_p - (C + 2))).to(torch.bfloat16).contiguous()
+        if rain_lr.dtype == torch.float32 and not rain_lr.requires_grad:
+            x = PF.frames_to_nhwc(rain_lr.contiguous(), cp0.cin_p)      # one kernel: layout + coord planes + pad + cast
+        else:
+            x = rain_lr.permute(1, 0, 3, 4, 2).reshape(T * B, H, W, C)
+            rows = torch.linspace(0, 1, H, device=dev, dtype=x.dtype).view(1, H, 1, 1).expand(T * B, H, W, 1)
+            cols = torch.linspace(0, 1, W, device=dev, dtype=x.dtype).view(1, 1, W, 1).expand(T * B, H, W, 1)
+            x = F.pad(torch.cat([x, rows, cols], dim=-1), (0, cp0.cin_p - (C + 2))).to(torch.bfloat16).contiguous()
         feat0 = PF.conv2d_same(x, cp0)                                                  # generator.py:166-168
         xw = feat0.view(T, B, H, W, cp0.cout_p)
         if cp0.cout_p != c1.working_cin:
