@@ -150,6 +150,15 @@ def committed_traffic(key: str):
     return None
 
 
+def cfg3_traffic(which: str, saved: bool, per_gpu_batch: int, cfg):
+    """dram bytes per launch / per BPTT call for the cfg3 cell shape (64 -> 64, 128x128, k3) from the committed ncu --set
+    full captures at 64 sequences, scaled linearly to this run's per-GPU batch; None for other shapes (no capture)."""
+    if cfg["H"] != 128 or cfg["W"] != 128 or list(cfg["hidden"]) != [64, 64]:
+        return None
+    v = committed_traffic(f"{which}_cfg3_b64_{'saved' if saved else 'recompute'}")
+    return None if v is None else int(v * per_gpu_batch / 64)
+
+
 # ================================================================================= training workloads (cfg3 / cfg4)
 def train_cfg(args):
     cfg = RADAR_TRAIN if args.workload == "radar-train" else TRAIN
@@ -440,7 +449,7 @@ def run_train(args):
                         f"{n_prof} steps (never inside a reported region); share_of_step = the kind's event time per "
                         "step / the reported (graph-replayed) step time; peak = sustained bf16 matmul (the kernels run "
                         "inside a multi-second step), burst alongside",
-                "traffic": committed_traffic("cell_bwd_cfg3_dram_bytes_per_call"),
+                "traffic": cfg3_traffic("cell_bwd", saved_bytes > 0, B, cfg),
                 "cell_fwd": None if not fwd else {
                     "kernel": "conv_igemm_tc_kernel<256,EPI_LSTM_FWD,2> (fused cell step, full K loop; zero-state first "
                               "steps are timed separately as cell_fwd_zero)",
@@ -449,7 +458,7 @@ def run_train(args):
                     "frac": fwd["flops"] / (fwd["ms"] * 1e-3) / 1e12 / peak_sus,
                     "frac_of_burst": fwd["flops"] / (fwd["ms"] * 1e-3) / 1e12 / peak_burst,
                     "launches_timed": fwd["launches"],
-                    "traffic": committed_traffic("cell_fwd_cfg2_dram_bytes_per_launch")},
+                    "traffic": cfg3_traffic("cell_fwd", saved_bytes > 0, B, cfg)},
                 "step": {"algorithmic_tflops_per_gpu": step_tf, "frac": step_tf / peak_sus,
                          "frac_of_burst": step_tf / peak_burst,
                          "note": "3 * F_fwd of every cell step of the rollout / device-resident step time (cells only: "
