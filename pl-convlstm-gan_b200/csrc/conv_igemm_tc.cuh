@@ -808,10 +808,13 @@ conv_igemm_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap t
 #pragma unroll
                 for (int gate = 0; gate < 4; ++gate) {
                   const uint32_t* src = gate == 0 ? vi : gate == 1 ? vf : gate == 2 ? vo : vg;
-                  gs[gate * (8 * 128)] = make_uint4(pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1])),
-                                                    pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3])),
-                                                    pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5])),
-                                                    pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7])));
+                  // streaming store (evict-first): written once, read once a whole rollout later -- it must not push the
+                  // activation patches the mainloop re-reads out of L2
+                  __stcs(gs + gate * (8 * 128),
+                         make_uint4(pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1])),
+                                    pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3])),
+                                    pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5])),
+                                    pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7]))));
                 }
               }
             }
