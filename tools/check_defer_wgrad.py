@@ -1,5 +1,10 @@
+#!/usr/bin/env python
+"""Chunked weight gradient vs one wgrad per step at the bench's shapes (cfg3 generator, 8 and 64 sequences): largest
+relative deviation of every parameter gradient, next to the run-to-run noise of the per-step form (red.add order).
+    python tools/check_defer_wgrad.py        (PLC_DEFER_WGRAD semantics: plconv.nn.DEFER_WGRAD = "off" | "auto" | "<steps>")"""
 import sys, torch
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import plconv
 from plconv import nn as pnn
 torch.manual_seed(5)
