@@ -70,8 +70,8 @@ def main():
     print(f"reference columns: eager convlstm.py cell, fp32; GPU = same B200 (cuDNN, TF32 convs allowed = torch default), "
           f"CPU = {cores} cores, 1 sample x B (linear)\n")
     print(f"| B | Cin=Ch | HxW | k | fwd us | fwd TFLOP/s | frac of {peak:.0f} | bwd us | fwd+bwd TFLOP/s (3F) | frac | "
-          f"ref GPU fwd us | ref GPU fwd+bwd us | speed-up fwd / fwd+bwd | ref CPU fwd+bwd ms |")
-    print("|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|")
+          f"fwd+bwd us saved gates | ref GPU fwd us | ref GPU fwd+bwd us | speed-up fwd / fwd+bwd | ref CPU fwd+bwd ms |")
+    print("|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|")
     chs = [32, 64, 128, 256]
     sizes = [64, 128, 256] if quick else [64, 128, 256, 512]
     for ch in chs:
@@ -99,6 +99,15 @@ def main():
                 dx, dhp, dcp = torch.empty_like(x), torch.empty_like(h), torch.empty_like(c)
                 bwd, _ = time_fn(lambda: F.cell_backward_acc(x, h, c, pw, dh, None, dc, img, db, workspace=ws, dx=dx,
                                                          dh_prev=dhp, dc_prev=dcp), iters=10, warm=3)
+                sv_s = "-"                                          # saved-gates form (Ch % 64 == 0): fwd_save + bwd_saved
+                nsv = F.saved_gates_bytes(B, hw, hw, pw)
+                if nsv:
+                    saved = torch.empty(nsv, dtype=torch.uint8, device=dev)
+                    fs, _ = time_fn(lambda: F.cell_forward(x, h, c, pw, h_out=h2, c_out=c2, saved=saved), iters=10, warm=3)
+                    bs, _ = time_fn(lambda: F.cell_backward_acc(x, h, c, pw, dh, None, dc, img, db, workspace=ws, dx=dx,
+                                                                dh_prev=dhp, dc_prev=dcp, saved=saved), iters=10, warm=3)
+                    sv_s = f"{fs + bs:.1f}"
+                    del saved
                 tf_f = flops / fwd / 1e6
                 tf_t = 3 * flops / (fwd + bwd) / 1e6
                 del x, h, c, h2, c2, dh, dc, ws, dx, dhp, dcp, img
@@ -114,7 +123,7 @@ def main():
                     _, cb = ref_times(1, ch, hw, k, torch.device("cpu"))
                     cpu_s = f"{cb * B / 1e3:.0f}"
                 print(f"| {B} | {ch} | {hw}x{hw} | {k} | {fwd:.1f} | {tf_f:.0f} | {tf_f / peak:.2f} | {bwd:.1f} | "
-                      f"{tf_t:.0f} | {tf_t / peak:.2f} | {ref_s} | {cpu_s} |", flush=True)
+                      f"{tf_t:.0f} | {tf_t / peak:.2f} | {sv_s} | {ref_s} | {cpu_s} |", flush=True)
 
 
 if __name__ == "__main__":
